@@ -1,0 +1,192 @@
+/*
+ * mma_b200 -- C ABI of the B200-native multi-mask aggregation hot path.
+ *
+ * The reference (asarigun/mma) is pure Python and exposes no FFI; its boundary
+ * for this path is the nn.Module API.  The entry points below
+ * are what a maintainer would bind from those modules (ctypes stub in
+ * INTEGRATION.md); each cites the reference code it replaces (paths relative
+ * to /root/reference).
+ *
+ * Conventions
+ *   - every function returns 0 (MMA_OK) or a negative MMA_ERR_* code; nothing throws;
+ *   - all pointers are DEVICE pointers unless the parameter is documented "host";
+ *   - the library never allocates or frees: the caller owns inputs, outputs and
+ *     workspaces (query sizes with the *_workspace_bytes functions);
+ *   - no global mutable state; work is enqueued on `stream` of the CURRENT device;
+ *   - fp32 data, int32 indices inside (E, N < 2^31), row-major, leading
+ *     dimensions (ld*) in elements;
+ *   - no atomics on any data path: every output element has exactly one
+ *     owner thread and a fixed summation order => bit-reproducible runs.
+ */
+#ifndef MMA_B200_H
+#define MMA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st *mma_stream_t; /* == cudaStream_t */
+
+#define MMA_OK 0
+#define MMA_ERR_INVALID (-1)     /* bad argument (null, size, alignment, unknown kind) */
+#define MMA_ERR_CUDA (-2)        /* a CUDA runtime call failed (see mma_last_cuda_error) */
+#define MMA_ERR_UNSUPPORTED (-3) /* valid but outside the compiled limits (A > 8, S > 8 ...) */
+#define MMA_ERR_WORKSPACE (-4)   /* workspace too small */
+
+#define MMA_MAX_AGGR 8
+#define MMA_MAX_SCALER 8
+
+/* aggregator kinds: reduce names accepted by MMAConv.aggregate, mma_conv.py:163-174 */
+enum { MMA_AGGR_SUM = 0, MMA_AGGR_MEAN = 1, MMA_AGGR_MIN = 2, MMA_AGGR_MAX = 3,
+       MMA_AGGR_VAR = 4, MMA_AGGR_STD = 5 };
+/* scaler kinds: mma_conv.py:181-195 (applied cumulatively, in list order) */
+enum { MMA_SCALE_IDENTITY = 0, MMA_SCALE_AMPLIFICATION = 1, MMA_SCALE_ATTENUATION = 2,
+       MMA_SCALE_LINEAR = 3, MMA_SCALE_INVERSE_LINEAR = 4 };
+/* node-classification combine kinds: layers.py:221 / 328-329 / 452 / 562 / 676-682 */
+enum { MMA_NC_SUM = 0, MMA_NC_MEAN = 1, MMA_NC_MAX = 2, MMA_NC_MIN = 3, MMA_NC_NONE = 4 };
+/* node-classification mask activation: layers.py:217 (sigmoid) or the raw logit (Q8) */
+enum { MMA_ACT_SIGMOID = 0, MMA_ACT_RAW = 1 };
+
+/* library version / build info (host). */
+int mma_b200_version(void);
+/* cudaGetLastError() text of the last failing call on this thread (host string). */
+const char *mma_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------
+ * Graph preprocessing.  Replaces the implicit index plumbing of
+ * MessagePassing.propagate (mma_conv.py:130) / torch_scatter's scatter-by-index
+ * (mma_conv.py:166) and utils.py:98-100 (neighbour lists): a STABLE sort of the
+ * edges by `key` gives a CSR whose in-row order is the original edge order, so
+ * "first occurrence wins" (torch_scatter CPU) is preserved.
+ *   key   [E] int64  segment id of each edge (dst for CSR-by-destination, src for the transpose)
+ *   other [E] int64  the other endpoint (may be NULL -> col not written)
+ *   rowptr [n_keys+1], col [E] = other[perm], perm [E] = original edge id of each slot.
+ * ---------------------------------------------------------------------- */
+int mma_csr_build_workspace_bytes(int64_t E, int64_t n_keys, size_t *bytes);
+int mma_csr_build(const int64_t *key, const int64_t *other, int64_t E, int64_t n_keys,
+                  int32_t *rowptr, int32_t *col, int32_t *perm,
+                  void *workspace, size_t workspace_bytes, mma_stream_t stream);
+/* inverse of a permutation: inv[perm[k]] = k  (maps original edge id -> slot). */
+int mma_invert_perm(const int32_t *perm, int64_t E, int32_t *inv, mma_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * K1 forward: fused MultiMaskConv aggregate.  Replaces, in ONE pass over the
+ * destination-CSR, the x_j gather of MessagePassing.propagate (mma_conv.py:130),
+ * the (separable) mask linear + dropout of MMAConv.message (mma_conv.py:146-157)
+ * and MMAConv.aggregate (mma_conv.py:159-196: A scatter passes, degree, the
+ * cumulative scalers and both cats).
+ *
+ *   m[e,c] = ((P[dst(e),c] + Q[src(e),c]) + R[e,c]) * keepscale[e,c]       c in [0, T*F_in)
+ *   Y[i, t, (s*A + a)*F_in + f] = aggr_a({m[e, t*F_in+f] : dst(e)=i}) * prod_{s'<=s} scale_{s'}(deg_i)
+ *
+ *   rowptr/col/perm : CSR by destination from mma_csr_build (perm may be NULL = identity)
+ *   P [n_rows, F] ld ldp | Q [n_src, F] ld ldq | R [E, F] ld ldr, ORIGINAL edge order | any may be NULL
+ *   keep [E, F] ld ldk : explicit keep-scale (0 or 1/(1-p)), original edge order, or NULL
+ *   p_drop, seed      : if keep == NULL and p_drop > 0: in-kernel Philox4x32-10 dropout keyed by
+ *                       (seed, original edge id, column) -- identical in fwd/bwd and across shards
+ *   aggr_kinds (host) [A], scaler_kinds (host) [S]
+ *   scale_tab [4, tab_stride] : factor of scaler kind k (1..4) at clamped degree d is
+ *                       scale_tab[(k-1)*tab_stride + d], d <= tab_stride-1 (built by the
+ *                       caller with the reference's own expression, mma_conv.py:185-191);
+ *                       may be NULL when all scalers are identity
+ *   Y [n_rows, T, S*A*F_in] ld ldy
+ *   arg_min/arg_max [n_rows, F] int32 : ORIGINAL edge id of the selected edge (E if none); NULL ok
+ *   stat_mean/stat_var [n_rows, F] : saved for the var/std backward; NULL ok
+ * ---------------------------------------------------------------------- */
+int mmconv_aggregate_fwd(const int32_t *rowptr, const int32_t *col, const int32_t *perm,
+                         int64_t n_rows, int64_t E,
+                         const float *P, int64_t ldp, const float *Q, int64_t ldq,
+                         const float *R, int64_t ldr, const float *keep, int64_t ldk,
+                         float p_drop, uint64_t seed,
+                         int T, int F_in, int A, const int32_t *aggr_kinds,
+                         int S, const int32_t *scaler_kinds,
+                         const float *scale_tab, int64_t tab_stride,
+                         float *Y, int64_t ldy, int32_t *arg_min, int32_t *arg_max,
+                         float *stat_mean, float *stat_var, mma_stream_t stream);
+
+/* K1 backward, destination pass (replaces autograd of mma_conv.py:157-196):
+ *   G[gslot(pos), c] = dL/dm_pre[e, c]   for every edge (row of the per-edge gradient),
+ *   dP[i, c]        = sum over in-edges of i of that row.
+ * gslot [E] maps CSR position -> row of G (NULL = CSR position; pass `perm` to get G in
+ * original edge order == dL/dR).  arg_min/arg_max/stat_* are the forward's outputs. */
+int mmconv_aggregate_bwd_dst(const int32_t *rowptr, const int32_t *col, const int32_t *perm,
+                             int64_t n_rows, int64_t E,
+                             const float *P, int64_t ldp, const float *Q, int64_t ldq,
+                             const float *R, int64_t ldr, const float *keep, int64_t ldk,
+                             float p_drop, uint64_t seed,
+                             int T, int F_in, int A, const int32_t *aggr_kinds,
+                             int S, const int32_t *scaler_kinds,
+                             const float *scale_tab, int64_t tab_stride,
+                             const float *dY, int64_t ldy,
+                             const int32_t *arg_min, const int32_t *arg_max,
+                             const float *stat_mean, const float *stat_var,
+                             const int32_t *gslot, float *G, int64_t ldg,
+                             float *dP, int64_t lddp, mma_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * K3 / transpose pass: deterministic segmented row sum (CSR SpMM)
+ *   out[i, c] = sum_{k in [ptr[i], ptr[i+1])} val[k] * src[idx[k], c]      (val NULL = 1)
+ * Used as (a) K1 backward source pass: dQ[j] = sum of G rows of j's out-edges
+ * (replaces index_select-backward / index_add_ atomics), and
+ * (b) torch.spmm(adj, support) of layers.py:41 and layers.py:862, and its backward
+ * on the transposed CSR. */
+int mma_segment_sum_rows(const int32_t *ptr, const int32_t *idx, const float *val,
+                         int64_t n_rows, const float *src, int64_t lds, int F,
+                         float *out, int64_t ldo, mma_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * K2: masked multi-aggregator layer of node_classification (layers.py:201-728),
+ * all A aggregators in one pass over the CSR of neighbour lists (add_all):
+ *   logit[a] = PA[i, a, c] + QA[j, a, c]        PA = X @ M_a[:F], QA = X @ M_a[F:]  (layers.py:215-216)
+ *   mask     = act_a(logit) * keepscale_a[e, c]   (layers.py:217-219, dropout always on)
+ *   S[a,i,c] = sum_j mask * X[j, c]               (layers.py:221)
+ *   OUT[a,i,c] = combine_a(X[i,c], S[a,i,c], D_i) (sum/mean/max/min/none)
+ *   PA, QA [N, A*F] ld ldpa/ldqa; X [N,F] ld ldx; keep [A, E, F] contiguous or NULL; OUT, S_out [A, N, F]
+ *   edge id for dropout/keep = CSR position (neighbour-list order, as the reference consumes it).
+ * ---------------------------------------------------------------------- */
+int mma_nc_aggregate_fwd(const int32_t *rowptr, const int32_t *col, int64_t N, int64_t E,
+                         const float *X, int64_t ldx, const float *PA, int64_t ldpa,
+                         const float *QA, int64_t ldqa, int F, int A,
+                         const int32_t *act_kinds, const int32_t *comb_kinds,
+                         const float *keep, float p_drop, uint64_t seed,
+                         float *OUT, float *S_out, mma_stream_t stream);
+
+/* K2 backward, destination pass: from dOUT [A,N,F] computes
+ *   gS [N, A*F] = dL/dS, node-major so the transpose pass gathers one contiguous row per edge
+ *                 (max/min ties split 1/2 like torch.max/min backward),
+ *   dXdir [N,F] = direct gradient through x_i in combine (contiguous, ld = F),
+ *   dPA [N, A*F] = sum_j dL/dlogit. */
+int mma_nc_aggregate_bwd_dst(const int32_t *rowptr, const int32_t *col, int64_t N, int64_t E,
+                             const float *X, int64_t ldx, const float *PA, int64_t ldpa,
+                             const float *QA, int64_t ldqa, int F, int A,
+                             const int32_t *act_kinds, const int32_t *comb_kinds,
+                             const float *keep, float p_drop, uint64_t seed,
+                             const float *S_saved, const float *dOUT,
+                             float *gS, float *dXdir, float *dPA, int64_t lddpa,
+                             mma_stream_t stream);
+
+/* K2 backward, source (transpose) pass over the CSC (colptr/row/eid from
+ * mma_csr_build keyed by the neighbour id; eid = CSR position of the edge):
+ *   dQA[j, a, c] = sum_i dL/dlogit,   dXnbr[j, c] = sum_i sum_a gS[a,i,c] * mask. */
+int mma_nc_aggregate_bwd_src(const int32_t *colptr, const int32_t *row, const int32_t *eid,
+                             int64_t N, int64_t E,
+                             const float *X, int64_t ldx, const float *PA, int64_t ldpa,
+                             const float *QA, int64_t ldqa, int F, int A,
+                             const int32_t *act_kinds,
+                             const float *keep, float p_drop, uint64_t seed,
+                             const float *gS, float *dQA, int64_t lddqa, float *dXnbr, int64_t lddx,
+                             mma_stream_t stream);
+
+/* Materialises the in-kernel Philox dropout keep-scale (0 or 1/(1-p)) for
+ * `stream_id` (0 for K1; the aggregator slot a for K2) as [E, F] floats, so that
+ * tests can inject the identical mask into the CPU oracle. */
+int mma_dropout_keep_scale(float p_drop, uint64_t seed, uint32_t stream_id,
+                           int64_t E, int F, float *out, int64_t ldo, mma_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMA_B200_H */

@@ -1,0 +1,112 @@
+"""ctypes binding of libmma_b200.so (include/mma_b200.h).
+
+There is deliberately NO fallback: if the library is missing or a call fails,
+the product path raises.  (The CPU oracle under oracle/ is test infrastructure
+and is never imported from here.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmma_b200.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_WORKSPACE = 0, -1, -2, -3, -4
+MAX_AGGR, MAX_SCALER = 8, 8
+AGGR_KINDS = {"sum": 0, "mean": 1, "min": 2, "max": 3, "var": 4, "std": 5}
+SCALER_KINDS = {"identity": 0, "amplification": 1, "attenuation": 2, "linear": 3, "inverse_linear": 4}
+NC_COMBINE = {"sum": 0, "mean": 1, "max": 2, "min": 3, "none": 4}
+ACT_SIGMOID, ACT_RAW = 0, 1
+
+_vp, _i64, _i32, _f32, _u64, _u32 = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_uint64, C.c_uint32
+
+_SIGS = {
+    "mma_b200_version": ([], C.c_int),
+    "mma_last_cuda_error": ([], C.c_char_p),
+    "mma_csr_build_workspace_bytes": ([_i64, _i64, C.POINTER(C.c_size_t)], C.c_int),
+    "mma_csr_build": ([_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, C.c_size_t, _vp], C.c_int),
+    "mma_invert_perm": ([_vp, _i64, _vp, _vp], C.c_int),
+    "mmconv_aggregate_fwd": ([_vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64,
+                              _f32, _u64, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _i64,
+                              _vp, _i64, _vp, _vp, _vp, _vp, _vp], C.c_int),
+    "mmconv_aggregate_bwd_dst": ([_vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64,
+                                  _f32, _u64, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _i64,
+                                  _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp], C.c_int),
+    "mma_segment_sum_rows": ([_vp, _vp, _vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp], C.c_int),
+    "mma_nc_aggregate_fwd": ([_vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32,
+                              _vp, _vp, _vp, _f32, _u64, _vp, _vp, _vp], C.c_int),
+    "mma_nc_aggregate_bwd_dst": ([_vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32,
+                                  _vp, _vp, _vp, _f32, _u64, _vp, _vp, _vp, _vp, _vp, _i64, _vp], C.c_int),
+    "mma_nc_aggregate_bwd_src": ([_vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32,
+                                  _vp, _vp, _f32, _u64, _vp, _vp, _i64, _vp, _i64, _vp], C.c_int),
+    "mma_dropout_keep_scale": ([_f32, _u64, _u32, _i64, _i32, _vp, _i64, _vp], C.c_int),
+}
+EXPORTS = tuple(_SIGS)
+
+_lib = None
+
+
+class MMAError(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads the library once.  Raises (never falls back) if it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise MMAError(
+                f"{LIB_PATH} not found: build it with `python -m mma_b200.build` "
+                "(nvcc, sm_100a).  mma_b200 has no CPU or PyTorch fallback.")
+        l = C.CDLL(LIB_PATH)
+        for name, (argtypes, restype) in _SIGS.items():
+            fn = getattr(l, name)          # AttributeError if a declared symbol is not exported
+            fn.argtypes = argtypes
+            fn.restype = restype
+        _lib = l
+    return _lib
+
+
+_ERR = {ERR_INVALID: "invalid argument", ERR_CUDA: "CUDA error", ERR_UNSUPPORTED: "unsupported size/limit",
+        ERR_WORKSPACE: "workspace too small"}
+
+
+def check(rc: int, what: str) -> None:
+    if rc != OK:
+        extra = ""
+        if rc == ERR_CUDA:
+            extra = ": " + lib().mma_last_cuda_error().decode()
+        raise MMAError(f"{what} failed: {_ERR.get(rc, rc)}{extra}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(*tensors) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("mma_b200 kernels need CUDA tensors (there is no CPU fallback); got a "
+                               f"{t.device} tensor")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"tensors on different devices: {dev} vs {t.device}")
+    if dev is None:
+        raise RuntimeError("no tensor given")
+    return dev
+
+
+def i32_array(values):
+    return (C.c_int32 * len(values))(*values)

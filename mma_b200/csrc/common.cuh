@@ -1,0 +1,158 @@
+// Shared device helpers for the mma_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#include "../../include/mma_b200.h"
+
+namespace mma {
+
+void set_last_error(cudaError_t e);
+
+#define MMA_CUDA_CHECK(expr)                                   \
+    do {                                                       \
+        cudaError_t _e = (expr);                               \
+        if (_e != cudaSuccess) { ::mma::set_last_error(_e); return MMA_ERR_CUDA; } \
+    } while (0)
+
+#define MMA_LAUNCH_CHECK() MMA_CUDA_CHECK(cudaGetLastError())
+
+constexpr int kSMs = 148;   // B200: 2 dies x 74 SMs
+
+// ---------------------------------------------------------------------------
+// VEC-wide register tiles.  VEC = 4 -> one 128-bit access per lane; VEC = 1 is
+// the fallback for widths/alignments that do not allow it (e.g. F_in = 75).
+// ---------------------------------------------------------------------------
+template <int VEC> struct Vec { float v[VEC]; };
+
+template <int VEC>
+__device__ __forceinline__ Vec<VEC> ld_vec(const float *p) {
+    Vec<VEC> r;
+    if constexpr (VEC == 4) {
+        float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+        r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+    } else if constexpr (VEC == 2) {
+        float2 t = __ldg(reinterpret_cast<const float2 *>(p));
+        r.v[0] = t.x; r.v[1] = t.y;
+    } else {
+        r.v[0] = __ldg(p);
+    }
+    return r;
+}
+
+// gather of a feature row that is touched ~deg times over the whole kernel but
+// far apart in time: keep it out of L1 (no_allocate) so index lines stay resident.
+template <int VEC>
+__device__ __forceinline__ Vec<VEC> ld_vec_stream(const float *p) {
+    Vec<VEC> r;
+    if constexpr (VEC == 4) {
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "l"(p));
+    } else if constexpr (VEC == 2) {
+        asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];"
+                     : "=f"(r.v[0]), "=f"(r.v[1]) : "l"(p));
+    } else {
+        asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r.v[0]) : "l"(p));
+    }
+    return r;
+}
+
+template <int VEC>
+__device__ __forceinline__ Vec<VEC> ld_vec_i32_as(const int32_t *p, int32_t *out) {
+    Vec<VEC> dummy{};
+    if constexpr (VEC == 4) {
+        int4 t = __ldg(reinterpret_cast<const int4 *>(p));
+        out[0] = t.x; out[1] = t.y; out[2] = t.z; out[3] = t.w;
+    } else if constexpr (VEC == 2) {
+        int2 t = __ldg(reinterpret_cast<const int2 *>(p));
+        out[0] = t.x; out[1] = t.y;
+    } else {
+        out[0] = __ldg(p);
+    }
+    return dummy;
+}
+
+template <int VEC>
+__device__ __forceinline__ void st_vec(float *p, const Vec<VEC> &r) {
+    if constexpr (VEC == 4) {
+        *reinterpret_cast<float4 *>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    } else if constexpr (VEC == 2) {
+        *reinterpret_cast<float2 *>(p) = make_float2(r.v[0], r.v[1]);
+    } else {
+        *p = r.v[0];
+    }
+}
+
+// write-once outputs: streaming store (evict-first) so they do not displace
+// the gathered feature rows from the 126 MB L2.
+template <int VEC>
+__device__ __forceinline__ void st_vec_stream(float *p, const Vec<VEC> &r) {
+    if constexpr (VEC == 4) {
+        __stcs(reinterpret_cast<float4 *>(p), make_float4(r.v[0], r.v[1], r.v[2], r.v[3]));
+    } else if constexpr (VEC == 2) {
+        __stcs(reinterpret_cast<float2 *>(p), make_float2(r.v[0], r.v[1]));
+    } else {
+        __stcs(p, r.v[0]);
+    }
+}
+
+template <int VEC>
+__device__ __forceinline__ void st_vec_i32_stream(int32_t *p, const int32_t *r) {
+    if constexpr (VEC == 4) {
+        __stcs(reinterpret_cast<int4 *>(p), make_int4(r[0], r[1], r[2], r[3]));
+    } else if constexpr (VEC == 2) {
+        __stcs(reinterpret_cast<int2 *>(p), make_int2(r[0], r[1]));
+    } else {
+        __stcs(p, r[0]);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 counter-based RNG (Salmon et al., SC'11).  The dropout decision
+// of element (edge id e, column c) of mask stream s depends only on
+// (seed, e, c/4, s): forward, both backward passes and every shard of a
+// partitioned graph regenerate the same bits without storing a mask.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0; key.y += W1;
+    }
+    return ctr;
+}
+
+struct Dropout {
+    uint32_t thr;     // drop iff random u32 < thr   (thr = round(p * 2^32), saturated)
+    float scale;      // 1 / (1 - p)
+    uint32_t k0, k1;  // seed
+};
+
+__host__ inline Dropout make_dropout(float p, uint64_t seed) {
+    Dropout d;
+    double t = (double)p * 4294967296.0;
+    d.thr = t >= 4294967295.0 ? 0xFFFFFFFFu : (t <= 0.0 ? 0u : (uint32_t)(t + 0.5));
+    d.scale = p < 1.0f ? 1.0f / (1.0f - p) : 0.0f;
+    d.k0 = (uint32_t)(seed & 0xFFFFFFFFull);
+    d.k1 = (uint32_t)(seed >> 32);
+    return d;
+}
+
+// keep-scale (0 or 1/(1-p)) for VEC consecutive columns starting at c (c % VEC == 0).
+template <int VEC>
+__device__ __forceinline__ Vec<VEC> dropout_keep(const Dropout &d, uint32_t eid, int c, uint32_t stream_id) {
+    Vec<VEC> r;
+    const uint4 bits = philox4x32_10(make_uint4(eid, (uint32_t)(c >> 2), stream_id, 0u), make_uint2(d.k0, d.k1));
+    const uint32_t w[4] = {bits.x, bits.y, bits.z, bits.w};
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) r.v[v] = (w[(c + v) & 3] < d.thr) ? 0.0f : d.scale;
+    return r;
+}
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace mma

@@ -1,0 +1,211 @@
+"""Autograd-aware wrappers over the C-ABI kernels (include/mma_b200.h).
+
+PyTorch is used for device memory, streams and autograd plumbing only; every
+aggregation op below runs in libmma_b200.so.  No CPU path exists.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from .graph import Graph
+
+_SCALE_TAB_CACHE: Dict[tuple, Tensor] = {}
+
+
+def scale_table(avg_deg: Dict[str, float], max_deg: int, device) -> Tensor:
+    """[4, max_deg+1] lookup of the degree scalers, evaluated with the reference's own fp32
+    expressions on the CPU (graph_regression/mma_conv.py:185-191: `deg` is the clamped
+    in-degree as float32, avg_deg[...] a Python float) so the factors are bit-identical
+    to the reference's; row k-1 holds scaler kind k (include/mma_b200.h)."""
+    key = (float(avg_deg["log"]), float(avg_deg["lin"]), int(max_deg), str(device))
+    tab = _SCALE_TAB_CACHE.get(key)
+    if tab is None:
+        deg = torch.arange(0, max_deg + 1, dtype=torch.float32).clamp_(1)
+        amp = torch.log(deg + 1) / avg_deg["log"]
+        att = avg_deg["log"] / torch.log(deg + 1)
+        lin = deg / avg_deg["lin"]
+        inv = avg_deg["lin"] / deg
+        tab = torch.stack([amp, att, lin, inv]).contiguous().to(device)
+        if len(_SCALE_TAB_CACHE) > 64:
+            _SCALE_TAB_CACHE.clear()
+        _SCALE_TAB_CACHE[key] = tab
+    return tab
+
+
+def _c(t: Optional[Tensor]) -> Optional[Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"mma_b200 computes in fp32; got {t.dtype}")
+    return t if t.stride(-1) == 1 and t.dim() == 2 else t.contiguous()
+
+
+def _ld(t: Optional[Tensor]) -> int:
+    return 0 if t is None else t.stride(0)
+
+
+class _MMConvAggregate(torch.autograd.Function):
+    """Y = fused gather + mask-add + dropout + multi-aggregate + cumulative scalers (K1)."""
+
+    @staticmethod
+    def forward(ctx, P, Q, R, keep, graph: Graph, T: int, F_in: int, akinds: tuple, skinds: tuple,
+                tab: Optional[Tensor], p_drop: float, seed: int):
+        dev = _lib.require_cuda(P, Q, R, keep, graph.rowptr)
+        P, Q, R, keep = _c(P), _c(Q), _c(R), _c(keep)
+        F = T * F_in
+        for name, t, rows in (("P", P, graph.n_dst), ("Q", Q, None), ("R", R, graph.E), ("keep", keep, graph.E)):
+            if t is not None and (t.shape[1] != F or (rows is not None and t.shape[0] != rows)):
+                raise RuntimeError(f"{name} has shape {tuple(t.shape)}, expected [{rows}, {F}]")
+        A, S = len(akinds), len(skinds)
+        n = graph.n_dst
+        Y = torch.empty((n, T, S * A * F_in), dtype=torch.float32, device=dev)
+        has_min, has_max = 2 in akinds, 3 in akinds
+        need_sq = 4 in akinds or 5 in akinds
+        arg_min = torch.empty((n, F), dtype=torch.int32, device=dev) if has_min else None
+        arg_max = torch.empty((n, F), dtype=torch.int32, device=dev) if has_max else None
+        stat_mean = torch.empty((n, F), dtype=torch.float32, device=dev) if need_sq else None
+        stat_var = torch.empty((n, F), dtype=torch.float32, device=dev) if need_sq else None
+        ak, sk = _lib.i32_array(akinds), _lib.i32_array(skinds)
+        perm = None if graph.perm is None else graph.perm
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().mmconv_aggregate_fwd(
+                _lib.ptr(graph.rowptr), _lib.ptr(graph.col), _lib.ptr(perm), n, graph.E,
+                _lib.ptr(P), _ld(P), _lib.ptr(Q), _ld(Q), _lib.ptr(R), _ld(R), _lib.ptr(keep), _ld(keep),
+                float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, T, F_in, A, ak, S, sk,
+                _lib.ptr(tab), 0 if tab is None else tab.shape[1],
+                _lib.ptr(Y), Y.stride(0), _lib.ptr(arg_min), _lib.ptr(arg_max),
+                _lib.ptr(stat_mean), _lib.ptr(stat_var), _lib.stream_ptr(dev)), "mmconv_aggregate_fwd")
+        ctx.graph, ctx.cfg = graph, (T, F_in, akinds, skinds, p_drop, seed)
+        ctx.has = (P is not None, Q is not None, R is not None)
+        ctx.save_for_backward(P, Q, R, keep, tab, arg_min, arg_max, stat_mean, stat_var)
+        ctx.mark_non_differentiable(*[t for t in (arg_min, arg_max) if t is not None])
+        E_t = torch.empty(0, dtype=torch.int32, device=dev)
+        return Y, (arg_min if has_min else E_t), (arg_max if has_max else E_t)
+
+    @staticmethod
+    def backward(ctx, dY, _ga, _gb):
+        P, Q, R, keep, tab, arg_min, arg_max, stat_mean, stat_var = ctx.saved_tensors
+        graph: Graph = ctx.graph
+        T, F_in, akinds, skinds, p_drop, seed = ctx.cfg
+        need_P = P is not None and ctx.needs_input_grad[0]
+        need_Q = Q is not None and ctx.needs_input_grad[1]
+        need_R = R is not None and ctx.needs_input_grad[2]
+        if not (need_P or need_Q or need_R):
+            return (None,) * 12
+        dev = dY.device
+        F = T * F_in
+        n, E = graph.n_dst, graph.E
+        dY = dY.contiguous().view(n, -1)
+        A, S = len(akinds), len(skinds)
+        dP = torch.empty((n, F), dtype=torch.float32, device=dev) if need_P else None
+        G = gslot = None
+        if need_R:                      # G in original edge order IS dL/dR
+            G = torch.empty((E, F), dtype=torch.float32, device=dev)
+            gslot = graph.perm
+        elif need_Q:                    # G in CSC order: the source pass streams it sequentially
+            graph.build_transpose()
+            G = torch.empty((E, F), dtype=torch.float32, device=dev)
+            gslot = graph.csr2csc
+        ak, sk = _lib.i32_array(akinds), _lib.i32_array(skinds)
+        l = _lib.lib()
+        with torch.cuda.device(dev):
+            _lib.check(l.mmconv_aggregate_bwd_dst(
+                _lib.ptr(graph.rowptr), _lib.ptr(graph.col), _lib.ptr(graph.perm), n, E,
+                _lib.ptr(P), _ld(P), _lib.ptr(Q), _ld(Q), _lib.ptr(R), _ld(R), _lib.ptr(keep), _ld(keep),
+                float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, T, F_in, A, ak, S, sk,
+                _lib.ptr(tab), 0 if tab is None else tab.shape[1],
+                _lib.ptr(dY), dY.stride(0), _lib.ptr(arg_min), _lib.ptr(arg_max),
+                _lib.ptr(stat_mean), _lib.ptr(stat_var), _lib.ptr(gslot), _lib.ptr(G), F,
+                _lib.ptr(dP), F, _lib.stream_ptr(dev)), "mmconv_aggregate_bwd_dst")
+            dQ = None
+            if need_Q:
+                graph.build_transpose()
+                dQ = torch.empty((Q.shape[0], F), dtype=torch.float32, device=dev)
+                if Q.shape[0] != graph.n_src:
+                    raise RuntimeError("Q rows != number of source nodes of the graph")
+                idx = graph.perm_t if need_R else None
+                _lib.check(l.mma_segment_sum_rows(_lib.ptr(graph.colptr), _lib.ptr(idx), None, graph.n_src,
+                                                  _lib.ptr(G), F, F, _lib.ptr(dQ), F,
+                                                  _lib.stream_ptr(dev)), "mma_segment_sum_rows")
+        return (dP, dQ, G if need_R else None) + (None,) * 9
+
+
+def mmconv_aggregate(P: Optional[Tensor], Q: Optional[Tensor], R: Optional[Tensor], graph: Graph, *,
+                     towers: int, F_in: int, aggregators: Sequence[str], scalers: Sequence[str],
+                     avg_deg: Optional[Dict[str, float]] = None, keep: Optional[Tensor] = None,
+                     p_drop: float = 0.0, seed: int = 0, return_args: bool = False):
+    """Fused MultiMaskConv aggregate (K1).  m_e = ((P[dst]+Q[src])+R[e]) * keepscale, then the
+    reductions + cumulative scalers of MMAConv.aggregate (graph_regression/mma_conv.py:159-196).
+    Returns Y [n_dst, towers, S*A*F_in] (and original-edge-id arg_min/arg_max [n_dst, towers*F_in])."""
+    for a in aggregators:
+        if a not in _lib.AGGR_KINDS:
+            raise ValueError(f'Unknown aggregator "{a}".')
+    for s in scalers:
+        if s not in _lib.SCALER_KINDS:
+            raise ValueError(f'Unknown scaler "{s}".')
+    if len(aggregators) > _lib.MAX_AGGR or len(scalers) > _lib.MAX_SCALER:
+        raise _lib.MMAError("more than 8 aggregators or scalers in one call")
+    akinds = tuple(_lib.AGGR_KINDS[a] for a in aggregators)
+    skinds = tuple(_lib.SCALER_KINDS[s] for s in scalers)
+    tab = None
+    if any(k != 0 for k in skinds):
+        if avg_deg is None:
+            raise ValueError("avg_deg is required for non-identity scalers")
+        tab = scale_table(avg_deg, max(graph.max_deg, 1), graph.device)
+    Y, amin, amax = _MMConvAggregate.apply(P, Q, R, keep, graph, towers, F_in, akinds, skinds, tab,
+                                           float(p_drop), int(seed))
+    if return_args:
+        return Y, (amin if amin.numel() else None), (amax if amax.numel() else None)
+    return Y
+
+
+class _SegmentSumRows(torch.autograd.Function):
+    """out[i] = sum_k val[k] * src[idx[k]] over CSR segments (K3); backward on the transposed CSR."""
+
+    @staticmethod
+    def forward(ctx, src, ptr, idx, val, n_rows, ptr_t, idx_t, val_t):
+        dev = _lib.require_cuda(src, ptr)
+        src = _c(src)
+        F = src.shape[1]
+        out = torch.empty((n_rows, F), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().mma_segment_sum_rows(_lib.ptr(ptr), _lib.ptr(idx), _lib.ptr(val), n_rows,
+                                                       _lib.ptr(src), src.stride(0), F, _lib.ptr(out), F,
+                                                       _lib.stream_ptr(dev)), "mma_segment_sum_rows")
+        ctx.t = (ptr_t, idx_t, val_t, src.shape[0])
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        ptr_t, idx_t, val_t, n_src = ctx.t
+        if ptr_t is None:
+            raise RuntimeError("segment_sum_rows: transposed structure not provided, cannot backpropagate")
+        g = g.contiguous()
+        dev, F = g.device, g.shape[1]
+        d = torch.empty((n_src, F), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().mma_segment_sum_rows(_lib.ptr(ptr_t), _lib.ptr(idx_t), _lib.ptr(val_t), n_src,
+                                                       _lib.ptr(g), F, F, _lib.ptr(d), F,
+                                                       _lib.stream_ptr(dev)), "mma_segment_sum_rows")
+        return (d,) + (None,) * 7
+
+
+def segment_sum_rows(src: Tensor, ptr: Tensor, idx: Optional[Tensor], val: Optional[Tensor], n_rows: int,
+                     ptr_t: Optional[Tensor] = None, idx_t: Optional[Tensor] = None,
+                     val_t: Optional[Tensor] = None) -> Tensor:
+    return _SegmentSumRows.apply(src, ptr, idx, val, n_rows, ptr_t, idx_t, val_t)
+
+
+def dropout_keep_scale(p: float, seed: int, E: int, F: int, device, stream_id: int = 0) -> Tensor:
+    """The keep-scale tensor [E,F] (0 or 1/(1-p)) that the kernels generate on the fly for
+    (seed, stream_id) -- for injecting the identical dropout into the CPU oracle in tests."""
+    out = torch.empty((E, F), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib().mma_dropout_keep_scale(float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream_id),
+                                                     E, F, _lib.ptr(out), F, _lib.stream_ptr(out.device)),
+                   "mma_dropout_keep_scale")
+    return out

@@ -1,0 +1,143 @@
+"""Device-side graph structures for the aggregation kernels.
+
+The reference hands an unsorted `edge_index` [2,E] to PyG's propagate
+(graph_regression/mma_conv.py:130) and Python neighbour lists `add_all` to the
+node-classification layer (node_classification/utils.py:98-100).  The kernels
+work on a CSR by destination (stable sort => in-row order == original edge
+order) and, for the backward, on its transpose.  Building them is a one-off per
+graph; results are cached.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+
+def csr_build(key: Tensor, other: Optional[Tensor], n_keys: int):
+    """Stable sort of edges by `key` (int64 [E]) -> (rowptr [n_keys+1], col [E] = other[perm],
+    perm [E]) as int32 CUDA tensors.  Calls mma_csr_build (CUB radix sort)."""
+    dev = _lib.require_cuda(key, other)
+    key = key.contiguous()
+    if key.dtype != torch.int64:
+        key = key.to(torch.int64)
+    if other is not None:
+        other = other.contiguous().to(torch.int64)
+    E = key.numel()
+    l = _lib.lib()
+    rowptr = torch.empty(n_keys + 1, dtype=torch.int32, device=dev)
+    col = torch.empty(E, dtype=torch.int32, device=dev) if other is not None else None
+    perm = torch.empty(E, dtype=torch.int32, device=dev)
+    nbytes = C.c_size_t(0)
+    _lib.check(l.mma_csr_build_workspace_bytes(E, n_keys, C.byref(nbytes)), "mma_csr_build_workspace_bytes")
+    ws = torch.empty(max(int(nbytes.value), 1), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(l.mma_csr_build(_lib.ptr(key), _lib.ptr(other), E, n_keys, _lib.ptr(rowptr),
+                                   _lib.ptr(col), _lib.ptr(perm), _lib.ptr(ws), ws.numel(),
+                                   _lib.stream_ptr(dev)), "mma_csr_build")
+    return rowptr, col, perm
+
+
+def invert_perm(perm: Tensor) -> Tensor:
+    dev = _lib.require_cuda(perm)
+    inv = torch.empty_like(perm)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().mma_invert_perm(_lib.ptr(perm), perm.numel(), _lib.ptr(inv),
+                                              _lib.stream_ptr(dev)), "mma_invert_perm")
+    return inv
+
+
+class Graph:
+    """CSR by destination + its transpose for one edge list.
+
+    rowptr [n_dst+1], col [E] (source of each slot), perm [E] (original edge id of each slot);
+    colptr [n_src+1], row_t [E] (destination of each transposed slot), perm_t [E];
+    csr2csc [E]: CSR slot -> CSC slot (row of the per-edge gradient buffer in the backward).
+    `identity_perm` is True when the input was already sorted by destination.
+    """
+
+    def __init__(self, src: Tensor, dst: Tensor, n_dst: int, n_src: Optional[int] = None,
+                 need_transpose: bool = True):
+        dev = _lib.require_cuda(src, dst)
+        self.device = dev
+        self.E = int(dst.numel())
+        self.n_dst = int(n_dst)
+        self.n_src = int(n_src if n_src is not None else n_dst)
+        self.rowptr, self.col, self.perm = csr_build(dst, src, self.n_dst)
+        self._src, self._dst = src, dst
+        self._t_built = False
+        self.colptr = self.row_t = self.perm_t = self.csr2csc = None
+        self._max_deg = None
+        if need_transpose:
+            self.build_transpose()
+
+    def build_transpose(self):
+        if self._t_built:
+            return
+        self.colptr, self.row_t, self.perm_t = csr_build(self._src, self._dst, self.n_src)
+        if self.E > 0:
+            inv_t = invert_perm(self.perm_t)                       # original edge id -> CSC slot
+            self.csr2csc = inv_t.index_select(0, self.perm.to(torch.int64)).contiguous()
+        else:
+            self.csr2csc = torch.empty(0, dtype=torch.int32, device=self.device)
+        self._t_built = True
+        self._src = self._dst = None
+
+    @property
+    def max_deg(self) -> int:
+        """Largest in-degree (one host sync, cached): sizes the scaler lookup table."""
+        if self._max_deg is None:
+            if self.n_dst == 0 or self.E == 0:
+                self._max_deg = 0
+            else:
+                self._max_deg = int((self.rowptr[1:] - self.rowptr[:-1]).max().item())
+        return self._max_deg
+
+    @staticmethod
+    def from_edge_index(edge_index: Tensor, num_nodes: int, need_transpose: bool = True) -> "Graph":
+        return Graph(edge_index[0], edge_index[1], num_nodes, num_nodes, need_transpose)
+
+    @staticmethod
+    def from_index(index: Tensor, dim_size: int) -> "Graph":
+        """Segments only (MMAConv.aggregate called on its own): no sources, no transpose."""
+        g = Graph.__new__(Graph)
+        g.device = _lib.require_cuda(index)
+        g.E = int(index.numel())
+        g.n_dst = int(dim_size)
+        g.n_src = 0
+        g.rowptr, g.col, g.perm = csr_build(index, None, g.n_dst)
+        g._t_built = False
+        g.colptr = g.row_t = g.perm_t = g.csr2csc = None
+        g._max_deg = None
+        g._src = g._dst = None
+        return g
+
+
+_CACHE: "OrderedDict[tuple, Graph]" = OrderedDict()
+_CACHE_SIZE = 16
+
+
+def cached_graph(edge_index: Tensor, num_nodes: int) -> Graph:
+    """Graph for an `edge_index` tensor, cached on (storage pointer, shape, version, N).
+    A tensor mutated in place bumps `_version` and is rebuilt; pass a `Graph`
+    explicitly to the layers to bypass the cache altogether."""
+    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes),
+           str(edge_index.device))
+    g = _CACHE.get(key)
+    if g is None:
+        g = Graph.from_edge_index(edge_index, num_nodes)
+        _CACHE[key] = g
+        while len(_CACHE) > _CACHE_SIZE:
+            _CACHE.popitem(last=False)
+    else:
+        _CACHE.move_to_end(key)
+    return g
+
+
+def clear_cache() -> None:
+    _CACHE.clear()

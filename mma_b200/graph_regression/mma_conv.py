@@ -1,0 +1,277 @@
+"""Drop-in for /root/reference/graph_regression/mma_conv.py (`MMAConv`, "MultiMaskConv").
+
+Constructor, forward signature, attributes and quirks are the reference's
+(mma_conv.py:47-51,121-122); the compute is the fused sm_100a kernel K1 instead of
+PyG propagate + T edge-level Linears + A torch_scatter passes:
+
+  reference (per layer call)                         here
+  -------------------------------------------------  ------------------------------------------
+  x_i, x_j = x[dst], x[src]         (:130)           never materialised (gathered in-kernel)
+  h = cat([x_i, x_j, enc(e)])       (:146)           never materialised
+  hs = Linear_{a*}(h) per tower     (:150-156, Q2)   P = X W_i^T + b, Q = X W_j^T   (node-level GEMMs)
+                                                     R = enc(e) W_e^T               (edge-level GEMM)
+  dropout(hs, 0.5) always           (:157, Q3)       in-kernel Philox, p = self.dropout
+  A scatters, degree, S scalers     (:159-196)       one pass over the destination CSR
+  autograd with atomic index_add_   (mma.py:157)     deterministic dst pass + transpose-CSR pass
+
+Quirks kept: only aggregators[-1]'s mask linears are applied (Q2); pre_nns /
+aggregation_layers are plain dicts so their weights are unregistered (Q1); dropout ignores
+self.training (Q3); scalers compound (Q4); avg_deg is computed from the histogram tensor
+itself (Q5); aggregator names not starting with sum/mean/min/max raise ValueError in
+forward (Q6) and names torch_scatter does not know ('min2', ...) raise ValueError in
+aggregate.
+
+Extensions (keyword-only, defaults keep reference behaviour):
+  strict_reference=True   False lets 'var'/'std' through forward (unreachable upstream, Q6;
+                          needed for BASELINE config 4 "all aggregators").
+`edge_index` may also be a prebuilt `mma_b200.graph.Graph`.
+"""
+from __future__ import annotations
+
+import itertools
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor
+from torch.nn import ModuleList, ReLU, Sequential
+
+from .. import functional as MF
+from ..graph import Graph, cached_graph
+from ..linear import Linear, reset
+from .mask_aggr import MaskAggregateLinear
+
+_UID = itertools.count(1)
+
+
+class MMAConv(torch.nn.Module):
+    def __init__(self, in_channels: int, out_channels: int, aggregators: List[str], scalers: List[str],
+                 deg: Tensor, edge_dim: Optional[int] = None, towers: int = 1, pre_layers: int = 1,
+                 post_layers: int = 1, mask: bool = True, divide_input: bool = False, **kwargs):
+        self.strict_reference = bool(kwargs.pop("strict_reference", True))
+        kwargs.setdefault("aggr", None)
+        super().__init__()
+        self.aggr = kwargs.get("aggr")
+        self.node_dim = 0                       # MessagePassing(node_dim=0), mma_conv.py:54
+
+        if divide_input:
+            assert in_channels % towers == 0
+        assert out_channels % towers == 0
+
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.aggregators = aggregators
+        self.scalers = scalers
+        self.edge_dim = edge_dim
+        self.towers = towers
+        self.divide_input = divide_input
+        self.dropout = 0.5                      # mma_conv.py:67
+        self.mask = mask
+        self.pre_layers, self.post_layers = pre_layers, post_layers
+
+        self.F_in = in_channels // towers if divide_input else in_channels
+        self.F_out = self.out_channels // towers
+
+        deg = deg.to(torch.float)               # statistics of the histogram itself (Q5), :72-78
+        self.avg_deg: Dict[str, float] = {
+            "lin": deg.mean().item(),
+            "log": (deg + 1).log().mean().item(),
+            "exp": deg.exp().mean().item(),
+        }
+
+        if self.edge_dim is not None:
+            self.edge_encoder = Linear(edge_dim, self.F_in)
+
+        self.pre_nns = {}                       # plain dict: unregistered (Q1), :84-86
+        for aggr in aggregators:
+            self.pre_nns[aggr] = ModuleList()
+
+        self.post_nns = ModuleList()
+        for _ in range(towers):
+            for aggr in aggregators:
+                modules = [MaskAggregateLinear((3 if edge_dim else 2) * self.F_in, self.F_in, aggregators,
+                                               aggr, mask=self.mask)]
+                for _ in range(pre_layers - 1):
+                    modules += [ReLU()]
+                    modules += [MaskAggregateLinear(self.F_in, self.F_in, aggregators, aggr, mask=self.mask)]
+                self.pre_nns[aggr].append(Sequential(*modules))
+            in_ch = (len(aggregators) * len(scalers) + 1) * self.F_in
+            modules = [Linear(in_ch, self.F_out)]
+            for _ in range(post_layers - 1):
+                modules += [ReLU()]
+                modules += [Linear(self.F_out, self.F_out)]
+            self.post_nns.append(Sequential(*modules))
+
+        self.lin = Linear(out_channels, out_channels)
+
+        self._uid = next(_UID)
+        self._calls = 0
+        self._inject_keep: Optional[Tensor] = None      # test hook: explicit keep-scale [E,T,F_in]
+        self.last_seed: Optional[int] = None
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        if self.edge_dim is not None:
+            self.edge_encoder.reset_parameters()
+        for aggr in self.pre_nns:               # iterates the KEYS (strings): a no-op upstream, :113-115
+            for nn in aggr:
+                reset(nn)
+        for nn in self.post_nns:
+            reset(nn)
+        self.lin.reset_parameters()
+
+    # ------------------------------------------------------------------ helpers
+    def mask_parameters(self) -> List[torch.nn.Parameter]:
+        """The live (unregistered, Q1) mask-projection weights, e.g. to hand to an optimizer."""
+        out = []
+        if self.mask == "no_linear":
+            return out
+        for seq in self.pre_nns[self.aggregators[-1]]:
+            for m in seq:
+                if isinstance(m, MaskAggregateLinear):
+                    lin = m.live()
+                    out += [lin.weight] + ([lin.bias] if lin.bias is not None else [])
+        return out
+
+    def _next_seed(self) -> int:
+        self._calls += 1
+        s = (torch.initial_seed() + 0x9E3779B97F4A7C15 * (self._uid * 1000003 + self._calls)) & 0xFFFFFFFFFFFFFFFF
+        self.last_seed = s
+        return s
+
+    def _check_names(self):
+        for aggregator in self.aggregators:     # message(), :150-154
+            ok = ("sum", "mean", "min", "max") if self.strict_reference else ("sum", "mean", "min", "max", "var", "std")
+            if not aggregator.startswith(ok):
+                raise ValueError(f'Unknown aggregator "{aggregator}".')
+
+    def _graph(self, edge_index, n: int) -> Graph:
+        if isinstance(edge_index, Graph):
+            return edge_index
+        if not edge_index.is_cuda:
+            raise RuntimeError("mma_b200.MMAConv needs CUDA tensors (no CPU fallback)")
+        return cached_graph(edge_index, n)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x: Tensor, edge_index, edge_attr: Optional[Tensor] = None) -> Tensor:
+        T, F_in = self.towers, self.F_in
+        if self.divide_input:
+            xt = x.view(-1, T, F_in)
+        else:
+            xt = x.view(-1, 1, F_in)            # towers share x; the repeat (:128) is never materialised
+        n = xt.size(0)
+        out = self.propagate(edge_index, x=xt, edge_attr=edge_attr, size=None)      # [N,T,S*A*F_in]
+
+        # post_nns over cat([x, out]) (:132-133) without the cat: split the first Linear's weight
+        K = out.size(-1)
+        first = [seq[0] for seq in self.post_nns]
+        if out.size(-1) + F_in != first[0].weight.size(1):
+            # e.g. mask="no_linear": same shape error class as the reference's post Linear
+            raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({n}x{K + F_in} and "
+                               f"{first[0].weight.size(1)}x{first[0].weight.size(0)})")
+        if T == 1:
+            w = first[0].weight
+            h = F.linear(out[:, 0], w[:, F_in:], first[0].bias) + F.linear(xt[:, 0], w[:, :F_in])
+            hs = [h]
+        else:
+            W = torch.stack([m.weight for m in first])                  # [T, F_out, F_in + K]
+            b = torch.stack([m.bias for m in first])                    # [T, F_out]
+            h = torch.einsum("ntk,tok->nto", out, W[:, :, F_in:]) + b
+            if self.divide_input:
+                h = h + torch.einsum("ntk,tok->nto", xt, W[:, :, :F_in])
+            else:
+                h = h + torch.einsum("nk,tok->nto", xt[:, 0], W[:, :, :F_in])
+            hs = [h[:, t] for t in range(T)]
+        outs = []
+        for t, seq in enumerate(self.post_nns):
+            v = hs[t]
+            for m in list(seq)[1:]:
+                v = m(v)
+            outs.append(v)
+        out = outs[0] if T == 1 else torch.cat(outs, dim=1)
+        return self.lin(out)
+
+    def propagate(self, edge_index, size=None, **kwargs):
+        """PyG's propagate for this layer (x_j = x[edge_index[0]], x_i = x[edge_index[1]],
+        segments = edge_index[1]) -- fused when the mask linear is separable."""
+        xt: Tensor = kwargs["x"]
+        edge_attr: Optional[Tensor] = kwargs.get("edge_attr")
+        n = xt.size(0)
+        graph = self._graph(edge_index, n)
+        T, F_in = self.towers, self.F_in
+        self._check_names()
+        if self.pre_layers != 1 or self.mask == "no_linear":
+            return self._propagate_materialised(graph, edge_index, xt, edge_attr)
+
+        live = [seq[0].live() for seq in self.pre_nns[self.aggregators[-1]]]        # Q2
+        W = torch.stack([m.weight for m in live])                                   # [T, F_in, (2|3)F_in]
+        b = torch.stack([m.bias for m in live]).reshape(1, T * F_in)
+        if xt.size(1) == 1:                     # towers share x: one GEMM gives P and Q of all towers
+            Wpq = torch.cat([W[:, :, :F_in].reshape(T * F_in, F_in), W[:, :, F_in:2 * F_in].reshape(T * F_in, F_in)])
+            PQ = F.linear(xt[:, 0], Wpq)                                            # [N, 2*T*F_in]
+            P = PQ[:, :T * F_in] + b
+            Q = PQ[:, T * F_in:]
+        else:
+            P = torch.einsum("ntk,tok->nto", xt, W[:, :, :F_in]).reshape(n, T * F_in) + b
+            Q = torch.einsum("ntk,tok->nto", xt, W[:, :, F_in:2 * F_in]).reshape(n, T * F_in)
+        R = None
+        if edge_attr is not None:
+            e = self.edge_encoder(edge_attr)                                        # [E, F_in], :143
+            R = F.linear(e, W[:, :, 2 * F_in:].reshape(T * F_in, F_in))             # [E, T*F_in]
+        keep = self._inject_keep
+        if keep is not None:
+            keep = keep.reshape(graph.E, T * F_in)
+        return MF.mmconv_aggregate(P, Q, R, graph, towers=T, F_in=F_in, aggregators=self.aggregators,
+                                   scalers=self.scalers, avg_deg=self.avg_deg, keep=keep,
+                                   p_drop=self.dropout, seed=self._next_seed())
+
+    def _propagate_materialised(self, graph: Graph, edge_index, xt, edge_attr):
+        """General path (pre_layers > 1 or mask == 'no_linear'): the mask MLP is not separable,
+        so messages are built per edge with torch ops; reductions still run in K1."""
+        T = self.towers
+        if isinstance(edge_index, Graph):
+            raise RuntimeError("the materialised-message path needs the raw edge_index tensor")
+        if xt.size(1) == 1 and T > 1:
+            xt = xt.repeat(1, T, 1)
+        x_j = xt.index_select(0, edge_index[0])
+        x_i = xt.index_select(0, edge_index[1])
+        h = self._message_pre_dropout(x_i, x_j, edge_attr)                          # [E,T,F']
+        keep = self._inject_keep
+        Fm = h.size(-1)
+        out = MF.mmconv_aggregate(None, None, h.reshape(h.size(0), T * Fm), graph, towers=T, F_in=Fm,
+                                  aggregators=self.aggregators, scalers=self.scalers, avg_deg=self.avg_deg,
+                                  keep=None if keep is None else keep.reshape(h.size(0), T * Fm),
+                                  p_drop=self.dropout, seed=self._next_seed())
+        return out
+
+    def _message_pre_dropout(self, x_i: Tensor, x_j: Tensor, edge_attr: Optional[Tensor]) -> Tensor:
+        if edge_attr is not None:
+            edge_attr = self.edge_encoder(edge_attr)
+            edge_attr = edge_attr.view(-1, 1, self.F_in).repeat(1, self.towers, 1)
+            h = torch.cat([x_i, x_j, edge_attr], dim=-1)
+        else:
+            h = torch.cat([x_i, x_j], dim=-1)
+        self._check_names()
+        hs = [nn(h[:, i]) for i, nn in enumerate(self.pre_nns[self.aggregators[-1]])]
+        return torch.stack(hs, dim=1)
+
+    def message(self, x_i: Tensor, x_j: Tensor, edge_attr: Optional[Tensor]) -> Tensor:
+        """mma_conv.py:138-157, callable on its own (dense torch ops; forward() does not use it)."""
+        hs = self._message_pre_dropout(x_i, x_j, edge_attr)
+        if self._inject_keep is not None:
+            return hs * self._inject_keep
+        return F.dropout(hs, self.dropout)
+
+    def aggregate(self, inputs: Tensor, index: Tensor, dim_size: Optional[int] = None) -> Tensor:
+        """mma_conv.py:159-196, callable on its own: inputs [E,T,F], index [E] -> [N,T,S*A*F]."""
+        if not inputs.is_cuda:
+            raise RuntimeError("mma_b200.MMAConv.aggregate needs CUDA tensors (no CPU fallback)")
+        n = int(index.max()) + 1 if dim_size is None else int(dim_size)
+        E, T, Fm = inputs.shape
+        graph = Graph.from_index(index, n)
+        return MF.mmconv_aggregate(None, None, inputs.reshape(E, T * Fm), graph, towers=T, F_in=Fm,
+                                   aggregators=self.aggregators, scalers=self.scalers, avg_deg=self.avg_deg)
+
+    def __repr__(self):
+        return (f"{self.__class__.__name__}({self.in_channels}, {self.out_channels}, "
+                f"towers={self.towers}, edge_dim={self.edge_dim})")

@@ -45,6 +45,7 @@ def _minmax_first(flat: Tensor, index: Tensor, n: int, is_max: bool) -> Tuple[Te
     E, K = flat.shape
     init = -FLT_MAX if is_max else FLT_MAX
     idx = index.view(E, 1).expand(E, K)
+    flat = torch.where(torch.isnan(flat), torch.full_like(flat, init), flat)   # NaN never wins a strict compare
     ext = torch.full((n, K), init, dtype=flat.dtype).scatter_reduce_(
         0, idx, flat, "amax" if is_max else "amin", include_self=True)
     eid = torch.arange(E, dtype=torch.int64).view(E, 1).expand(E, K)

@@ -1,0 +1,48 @@
+"""CPU: the C-ABI library loads and exports every symbol include/mma_b200.h declares
+(no compute calls without a GPU), argument validation paths return error codes."""
+import ctypes
+import os
+import re
+
+from mma_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "mma_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(?:int|const char \*)\s*(mma\w+|mmconv\w+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    names = declared_functions()
+    assert len(names) >= 12, names
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(raw, n), f"{n} declared in include/mma_b200.h but not exported"
+    assert sorted(_lib.EXPORTS) == names, "ctypes binding table out of sync with the header"
+    assert _lib.lib().mma_b200_version() >= 100
+
+
+def test_argument_validation_without_gpu():
+    l = _lib.lib()
+    n = ctypes.c_size_t(0)
+    assert l.mma_csr_build_workspace_bytes(-1, 4, ctypes.byref(n)) == _lib.ERR_INVALID
+    assert l.mma_csr_build_workspace_bytes(2**31, 4, ctypes.byref(n)) == _lib.ERR_UNSUPPORTED
+    ak = _lib.i32_array([0]); sk = _lib.i32_array([0])
+    # all data pointers NULL -> invalid, before any CUDA call
+    rc = l.mmconv_aggregate_fwd(None, None, None, 4, 0, None, 0, None, 0, None, 0, None, 0, 0.0, 0, 1, 4, 1, ak, 1, sk,
+                                None, 0, None, 0, None, None, None, None, None)
+    assert rc == _lib.ERR_INVALID
+    assert l.mma_segment_sum_rows(None, None, None, 4, None, 0, 4, None, 0, None) == _lib.ERR_INVALID
+
+
+def test_no_oracle_import_in_product_path():
+    pkg = os.path.join(ROOT, "mma_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "from oracle" not in src and "import oracle" not in src, f

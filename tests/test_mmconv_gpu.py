@@ -1,0 +1,278 @@
+"""Parity of the CUDA MultiMaskConv path (K1 + drop-in MMAConv) against the oracle and the
+golden vectors produced by the verbatim reference.  Bar (BASELINE.json north_star):
+min/max selections and arg indices BIT-EXACT; sum/mean/std and all gradients within 1e-5
+relative error (fp32), measured against the largest magnitude of the reference tensor."""
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-5      # north_star tolerance for sum/mean/std/gradients
+
+
+def close(a, b, rel=REL, what=""):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    if b.numel() == 0:
+        return
+    scale = max(b.abs().max().item(), 1e-30)
+    err = (a - b).abs().max().item()
+    assert err <= rel * scale, f"{what}: max err {err:.3e} vs scale {scale:.3e} (rel {err / scale:.3e})"
+
+
+def bitexact(a, b, what=""):
+    a, b = a.detach().cpu().contiguous(), b.detach().cpu().contiguous()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    assert torch.equal(a.view(torch.int32), b.view(torch.int32)), f"{what}: not bit-exact"
+
+
+def rand_graph(n, E, seed, empty_tail=3):
+    g = torch.Generator().manual_seed(seed)
+    src = torch.randint(0, n, (E,), generator=g)
+    dst = torch.randint(0, max(n - empty_tail, 1), (E,), generator=g)
+    return src, dst
+
+
+ALL_AGGR = ["mean", "sum", "min", "max", "std", "var"]
+ALL_SCALE = ["identity", "amplification", "attenuation", "linear", "inverse_linear"]
+
+
+@pytest.mark.parametrize("n,E,T,F_in,use", [
+    (300, 4000, 1, 128, "PQ"),       # warp per row, float4
+    (257, 3000, 1, 64, "PQR"),       # 16 lanes per row
+    (100, 900, 2, 8, "PQRK"),        # 4 lanes per row, towers, explicit keep
+    (64, 700, 5, 75, "PQRK"),        # c2 shape: F_in % 4 != 0 -> scalar path, 12 chunks
+    (50, 600, 1, 200, "QK"),         # F > 128: two float4 chunks
+    (40, 300, 1, 16, "R"),           # materialised messages only
+    (30, 0, 1, 16, "PQ"),            # no edges at all
+    (1, 50, 1, 4, "PQ"),             # single node, self loops / multi-edges
+])
+def test_fused_aggregate_vs_oracle(n, E, T, F_in, use):
+    import mma_b200
+    from oracle import restate, seq
+    F = T * F_in
+    src, dst = rand_graph(n, E, seed=n + E, empty_tail=3 if n > 4 else 0)
+    g = torch.Generator().manual_seed(1)
+    def mk(rows):
+        t = torch.randn(rows, F, generator=g)
+        t[torch.rand(rows, F, generator=g) < 0.3] = 0.0       # exact ties
+        t[torch.rand(rows, F, generator=g) < 0.05] = -0.0     # signed zeros
+        return t
+    P = mk(n) if "P" in use else None
+    Q = mk(n) if "Q" in use else None
+    R = mk(E) if "R" in use else None
+    keep = (torch.rand(E, F, generator=g) < 0.5).float() * 2 if "K" in use else None
+    hist = torch.bincount(torch.bincount(dst, minlength=n)) if E else torch.tensor([n])
+    avg = restate.avg_deg_from_hist(hist)
+
+    dev = "cuda"
+    graph = mma_b200.Graph(src.to(dev), dst.to(dev), n)
+    gl = [t.clone().to(dev).requires_grad_() for t in (P, Q, R) if t is not None]
+    it = iter(gl)
+    Pg, Qg, Rg = (next(it) if t is not None else None for t in (P, Q, R))
+    Y, amin, amax = mma_b200.mmconv_aggregate(Pg, Qg, Rg, graph, towers=T, F_in=F_in, aggregators=ALL_AGGR,
+                                              scalers=ALL_SCALE, avg_deg=avg,
+                                              keep=None if keep is None else keep.to(dev), return_args=True)
+    assert Y.shape == (n, T, len(ALL_SCALE) * len(ALL_AGGR) * F_in)
+
+    # the oracle's layout is [n, S*A*F] with F the flat width; re-tile to [n,T,(s,a),F_in]
+    ref_flat, rargs = restate.mmconv_fused_op(P, Q, R, keep, src, dst, n, ALL_AGGR, ALL_SCALE, avg, return_args=True)
+    S, A = len(ALL_SCALE), len(ALL_AGGR)
+    ref_t = ref_flat.view(n, S * A, T, F_in).permute(0, 2, 1, 3).reshape(n, T, S * A * F_in)
+    Yc = Y.detach().cpu()
+    Yv, Rv = Yc.view(n, T, S, A, F_in), ref_t.view(n, T, S, A, F_in)
+    for ai, name in enumerate(ALL_AGGR):
+        if name in ("min", "max"):
+            bitexact(Yv[:, :, :, ai], Rv[:, :, :, ai], f"{name} (all scaler blocks)")
+        else:
+            close(Yv[:, :, :, ai], Rv[:, :, :, ai], what=name)
+    assert torch.equal(amin.cpu().long(), rargs["min"].view(n, F)), "argmin indices"
+    assert torch.equal(amax.cpu().long(), rargs["max"].view(n, F)), "argmax indices"
+
+    # sequential C ground truth (tie-breaking order) on the raw aggregates
+    if E > 0:
+        so = seq.mmconv_aggregate(P, Q, R, keep, src, dst, n, F)
+        assert torch.equal(amin.cpu().long(), so["arg_min"]) and torch.equal(amax.cpu().long(), so["arg_max"])
+        id_block = Yc.view(n, T, S, A, F_in)[:, :, 0]                        # identity scaler block
+        for ai, name in enumerate(ALL_AGGR):
+            got = id_block[:, :, ai].reshape(n, F)
+            if name in ("min", "max"):
+                bitexact(got, so[name], f"seq {name}")
+            else:
+                close(got, so[name], what=f"seq {name}")
+
+    # gradients (deterministic upstream gradient)
+    gy = torch.cos(torch.arange(Y.numel(), dtype=torch.float32) * 0.37).view_as(Y)
+    gy_ref = gy.view(n, T, S * A, F_in).permute(0, 2, 1, 3).reshape(n, -1)
+    leaves_ref = [t.clone().requires_grad_() for t in (P, Q, R) if t is not None]
+    it = iter(leaves_ref)
+    Pr, Qr, Rr = (next(it) if t is not None else None for t in (P, Q, R))
+    out = restate.mmconv_fused_op(Pr, Qr, Rr, keep, src, dst, n, ALL_AGGR, ALL_SCALE, avg)
+    gref = torch.autograd.grad(out, leaves_ref, gy_ref)
+    ggot = torch.autograd.grad(Y, gl, gy.to(dev))
+    for name, a, b in zip([k for k, t in zip("PQR", (P, Q, R)) if t is not None], ggot, gref):
+        close(a, b, what=f"d{name}")
+
+
+def test_determinism_and_edge_order_invariance():
+    import mma_b200
+    n, E, F = 500, 9000, 64
+    src, dst = rand_graph(n, E, 5)
+    P, Q = torch.randn(n, F).cuda(), torch.randn(n, F).cuda()
+    hist = torch.bincount(torch.bincount(dst, minlength=n))
+    from oracle import restate
+    avg = restate.avg_deg_from_hist(hist)
+    def run(s, d):
+        g = mma_b200.Graph(s.cuda(), d.cuda(), n)
+        Pg, Qg = P.clone().requires_grad_(), Q.clone().requires_grad_()
+        Y, amin, amax = mma_b200.mmconv_aggregate(Pg, Qg, None, g, towers=1, F_in=F, aggregators=ALL_AGGR[:5],
+                                                  scalers=ALL_SCALE[:4], avg_deg=avg, return_args=True)
+        gP, gQ = torch.autograd.grad(Y, [Pg, Qg], torch.ones_like(Y))
+        return Y, amin, amax, gP, gQ
+    a, b = run(src, dst), run(src, dst)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y), "two identical runs differ (must be bit-reproducible: no atomics)"
+    # permuting the edge list: min/max VALUES stay bit-exact, sums within tolerance
+    perm = torch.randperm(E, generator=torch.Generator().manual_seed(0))
+    c = run(src[perm], dst[perm])
+    S, A = 4, 5
+    Ya, Yc = a[0].view(n, S, A, F), c[0].view(n, S, A, F)
+    bitexact(Ya[:, :, 2:4], Yc[:, :, 2:4], "min/max under edge permutation")
+    close(Ya, Yc, what="sum/mean/std under edge permutation")
+    # arg follows the lowest ORIGINAL edge id among ties: map back through the permutation
+    m = (P.cpu()[dst] + Q.cpu()[src])
+    amin = a[1].cpu().long()
+    rows = torch.arange(n).view(n, 1).expand(n, F)
+    valid = amin < E
+    picked = m[amin.clamp(max=E - 1), torch.arange(F).view(1, F).expand(n, F)]
+    assert torch.equal(picked[valid], Ya[:, 0, 2].cpu()[valid]), "m[argmin] must equal the min value"
+    assert torch.equal(dst[amin.clamp(max=E - 1)][valid], rows[valid]), "argmin edge must end at its row"
+
+
+def test_philox_dropout_matches_injected_mask():
+    import mma_b200
+    from oracle import restate
+    n, E, F, p = 200, 3000, 32, 0.5
+    src, dst = rand_graph(n, E, 9)
+    P, Q = torch.randn(n, F), torch.randn(n, F)
+    g = mma_b200.Graph(src.cuda(), dst.cuda(), n)
+    seed = 1234567
+    keep = mma_b200.dropout_keep_scale(p, seed, E, F, "cuda")
+    frac = (keep > 0).float().mean().item()
+    assert abs(frac - (1 - p)) < 0.01 and set(keep.unique().tolist()) == {0.0, 2.0}
+    Pg, Qg = P.cuda().requires_grad_(), Q.cuda().requires_grad_()
+    Y = mma_b200.mmconv_aggregate(Pg, Qg, None, g, towers=1, F_in=F, aggregators=["sum", "max", "std"],
+                                  scalers=["identity"], p_drop=p, seed=seed)
+    Pr, Qr = P.clone().requires_grad_(), Q.clone().requires_grad_()
+    ref = restate.mmconv_fused_op(Pr, Qr, None, keep.cpu(), src, dst, n, ["sum", "max", "std"], ["identity"], {})
+    close(Y.view(n, -1), ref, what="philox fwd")
+    bitexact(Y.view(n, 3, F)[:, 1], ref.view(n, 3, F)[:, 1], "max under philox dropout")
+    gy = torch.randn(n, 3 * F)
+    a = torch.autograd.grad(Y, [Pg, Qg], gy.cuda().view_as(Y))
+    b = torch.autograd.grad(ref, [Pr, Qr], gy)
+    close(a[0], b[0], what="philox dP"); close(a[1], b[1], what="philox dQ")
+    # different seeds / p
+    k2 = mma_b200.dropout_keep_scale(p, seed + 1, E, F, "cuda")
+    assert not torch.equal(keep, k2)
+    k3 = mma_b200.dropout_keep_scale(0.75, seed, E, F, "cuda")
+    assert abs((k3 > 0).float().mean().item() - 0.25) < 0.01 and k3.max().item() == 4.0
+
+
+@pytest.mark.parametrize("name", ["aggregate_all.pt", "aggregate_c4_small.pt"])
+def test_aggregate_method_vs_reference_golden(name):
+    """MMAConv.aggregate on its own (mma_conv.py:159) against the verbatim reference's output."""
+    from mma_b200 import MMAConv
+    from oracle.make_golden import synthetic_grad
+    gd = load_golden(name)
+    inputs, index, n = gd["inputs"], gd["index"], gd["n"]
+    E, T, F_in = inputs.shape
+    conv = MMAConv(T * F_in, T * F_in, ["sum"], ["identity"], gd["deg_hist"], towers=T, divide_input=True)
+    conv.aggregators, conv.scalers = gd["aggregators"], gd["scalers"]
+    assert conv.avg_deg == gd["avg_deg"]
+    x = inputs.cuda().requires_grad_()
+    out = conv.aggregate(x, index.cuda(), dim_size=n)
+    A, S = len(gd["aggregators"]), len(gd["scalers"])
+    ov, rv = out.detach().cpu().view(n, T, S, A, F_in), gd["out"].view(n, T, S, A, F_in)
+    for ai, a in enumerate(gd["aggregators"]):
+        if a in ("min", "max"):
+            bitexact(ov[:, :, :, ai], rv[:, :, :, ai], f"{name}:{a}")
+        else:
+            close(ov[:, :, :, ai], rv[:, :, :, ai], what=f"{name}:{a}")
+    (gin,) = torch.autograd.grad(out, [x], synthetic_grad(gd["out"]).cuda())
+    close(gin, gd["ginputs"], what=f"{name}: d inputs")
+
+
+def _load_weights(conv, w):
+    with torch.no_grad():
+        if w["enc"] is not None:
+            conv.edge_encoder.weight.copy_(w["enc"][0]); conv.edge_encoder.bias.copy_(w["enc"][1])
+        a_star = conv.aggregators[-1]
+        for t, seqm in enumerate(conv.pre_nns[a_star]):
+            lins = [m for m in seqm if hasattr(m, "aggregation_layers")]
+            for li, m in enumerate(lins):
+                m.live().weight.copy_(w["pre"][t][li][0]); m.live().bias.copy_(w["pre"][t][li][1])
+        for t, seqm in enumerate(conv.post_nns):
+            lins = [m for m in seqm if hasattr(m, "weight")]
+            for li, m in enumerate(lins):
+                m.weight.copy_(w["post"][t][li][0]); m.bias.copy_(w["post"][t][li][1])
+        conv.lin.weight.copy_(w["lin"][0]); conv.lin.bias.copy_(w["lin"][1])
+
+
+@pytest.mark.parametrize("name", ["mmaconv_zinc.pt", "mmaconv_t1_noedge.pt", "mmaconv_divide_prepost2.pt"])
+def test_mmaconv_layer_vs_reference_golden(name):
+    """Whole drop-in layer (fwd + all gradients) against the verbatim reference's outputs."""
+    from mma_b200 import MMAConv
+    from oracle import restate
+    gd = load_golden(name)
+    conv = MMAConv(deg=gd["deg_hist"], **gd["ctor"]).cuda()
+    _load_weights(conv, gd["weights"])
+    assert conv.avg_deg == gd["weights"]["avg_deg"]
+    x = gd["x"].cuda().requires_grad_()
+    ea = None if gd["edge_attr"] is None else gd["edge_attr"].cuda().requires_grad_()
+    conv._inject_keep = gd["keep_bits"].float().cuda() / gd["p_keep"]
+    y = conv(x, gd["edge_index"].cuda(), ea)
+    close(y, gd["y"], what=f"{name}: y")
+    params = restate.weights_from_module(conv, clone=False).tensors()
+    grads = torch.autograd.grad(y, [x] + ([ea] if ea is not None else []) + params, gd["gy"].cuda())
+    close(grads[0], gd["gx"], what="dx")
+    k = 1
+    if ea is not None:
+        close(grads[1], gd["gea"], what="d edge_attr"); k = 2
+    for i, (a, b) in enumerate(zip(grads[k:], gd["gparams"])):
+        close(a, b, what=f"d param {i}")
+
+
+def test_mmaconv_api_and_errors():
+    from mma_b200 import MMAConv, MaskAggregateLinear
+    deg = torch.tensor([0, 3, 5, 2])
+    conv = MMAConv(8, 8, ["mean", "max"], ["identity", "amplification"], deg, edge_dim=3, towers=2)
+    assert conv.dropout == 0.5 and conv.F_in == 8 and conv.F_out == 4
+    assert set(conv.pre_nns) == {"mean", "max"} and isinstance(conv.pre_nns, dict)
+    names = [n for n, _ in conv.named_parameters()]
+    assert not any("pre_nns" in n or "aggregation_layers" in n for n in names)      # Q1
+    assert isinstance(conv.pre_nns["max"][0][0], MaskAggregateLinear)
+    assert len(conv.mask_parameters()) == 2 * 2
+    x = torch.randn(6, 8).cuda(); ei = torch.tensor([[0, 1, 2, 3], [1, 2, 3, 0]]).cuda(); ea = torch.randn(4, 3).cuda()
+    conv = conv.cuda()
+    assert conv(x, ei, ea).shape == (6, 8)
+    with pytest.raises(RuntimeError):
+        conv.cpu()(x.cpu(), ei.cpu(), ea.cpu())                                      # no CPU fallback
+    bad = MMAConv(8, 8, ["mean", "std"], ["identity"], deg).cuda()
+    with pytest.raises(ValueError, match='Unknown aggregator "std"'):                # Q6
+        bad(x, ei)
+    ok = MMAConv(8, 8, ["mean", "std"], ["identity"], deg, strict_reference=False).cuda()
+    assert ok(x, ei).shape == (6, 8)
+    bad2 = MMAConv(8, 8, ["min2"], ["identity"], deg).cuda()
+    with pytest.raises(ValueError):
+        bad2(x, ei)
+    bad3 = MMAConv(8, 8, ["min"], ["squash"], deg).cuda()
+    with pytest.raises(ValueError, match='Unknown scaler "squash"'):
+        bad3(x, ei)
+    # stochastic in eval mode too (Q3), reproducible per seed
+    conv.eval()
+    torch.manual_seed(3); conv._calls = 0; a = conv(x, ei, ea)
+    b = conv(x, ei, ea)
+    torch.manual_seed(3); conv._calls = 0; c = conv(x, ei, ea)
+    assert not torch.equal(a, b) and torch.equal(a, c)
