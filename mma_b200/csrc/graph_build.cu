@@ -73,7 +73,7 @@ extern "C" int mma_csr_build_workspace_bytes(int64_t E, int64_t n_keys, size_t *
 extern "C" int mma_csr_build(const int64_t *key, const int64_t *other, int64_t E, int64_t n_keys,
                              int32_t *rowptr, int32_t *col, int32_t *perm, void *workspace,
                              size_t workspace_bytes, mma_stream_t stream) {
-    if (!rowptr || !perm || E < 0 || n_keys < 0 || (E > 0 && !key)) return MMA_ERR_INVALID;
+    if (!rowptr || E < 0 || n_keys < 0 || (E > 0 && (!key || !perm))) return MMA_ERR_INVALID;
     if (E >= INT32_MAX || n_keys >= INT32_MAX) return MMA_ERR_UNSUPPORTED;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int block = 256;

@@ -347,8 +347,8 @@ static int fill_params(MMConvParams &p, const int32_t *rowptr, const int32_t *co
         return MMA_ERR_INVALID;
     if (E >= INT32_MAX || n_rows >= INT32_MAX) return MMA_ERR_UNSUPPORTED;
     if (A > MMA_MAX_AGGR || S > MMA_MAX_SCALER) return MMA_ERR_UNSUPPORTED;
-    if (!P && !Q && !R) return MMA_ERR_INVALID;
-    if (Q && !col) return MMA_ERR_INVALID;
+    if (!P && !Q && !R && E > 0) return MMA_ERR_INVALID;
+    if (Q && !col && E > 0) return MMA_ERR_INVALID;
     if (p_drop < 0.0f || p_drop > 1.0f) return MMA_ERR_INVALID;
     p = MMConvParams{};
     p.rowptr = rowptr; p.col = col; p.perm = perm; p.n_rows = n_rows; p.E = E;
@@ -448,7 +448,7 @@ extern "C" int mmconv_aggregate_bwd_dst(const int32_t *rowptr, const int32_t *co
     int rc = fill_params(p, rowptr, col, perm, n_rows, E, P, ldp, Q, ldq, R, ldr, keep, ldk, p_drop, seed,
                          T, F_in, A, aggr_kinds, S, scaler_kinds, scale_tab, tab_stride);
     if (rc != MMA_OK) return rc;
-    if (!dY || (!G && !dP)) return MMA_ERR_INVALID;
+    if (!dY || (!G && !dP && E > 0)) return MMA_ERR_INVALID;
     bool needm = false;
     for (int a = 0; a < A; ++a) {
         const int k = p.akind[a];

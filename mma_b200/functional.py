@@ -101,6 +101,9 @@ class _MMConvAggregate(torch.autograd.Function):
         n, E = graph.n_dst, graph.E
         dY = dY.contiguous().view(n, -1)
         A, S = len(akinds), len(skinds)
+        if E == 0:
+            z = lambda t, need: torch.zeros_like(t) if need else None
+            return (z(P, need_P), z(Q, need_Q), z(R, need_R)) + (None,) * 9
         dP = torch.empty((n, F), dtype=torch.float32, device=dev) if need_P else None
         G = gslot = None
         if need_R:                      # G in original edge order IS dL/dR
@@ -209,3 +212,73 @@ def dropout_keep_scale(p: float, seed: int, E: int, F: int, device, stream_id: i
                                                      E, F, _lib.ptr(out), F, _lib.stream_ptr(out.device)),
                    "mma_dropout_keep_scale")
     return out
+
+
+class _NcAggregate(torch.autograd.Function):
+    """All A masked neighbour sums + combine of node_classification/layers.py:201-728 (K2)."""
+
+    @staticmethod
+    def forward(ctx, X, PA, QA, nbr, acts: tuple, combs: tuple, keep, p_drop: float, seed: int):
+        dev = _lib.require_cuda(X, PA, QA, nbr.rowptr)
+        X, PA, QA = _c(X), _c(PA), _c(QA)
+        N, F = X.shape
+        A = len(acts)
+        if PA.shape != (N, A * F) or QA.shape != (N, A * F):
+            raise RuntimeError(f"PA/QA must be [{N}, {A * F}], got {tuple(PA.shape)} / {tuple(QA.shape)}")
+        if keep is not None:
+            keep = keep.contiguous()
+            if keep.shape != (A, nbr.E, F):
+                raise RuntimeError(f"keep must be [{A}, {nbr.E}, {F}]")
+        OUT = torch.empty((A, N, F), dtype=torch.float32, device=dev)
+        S = torch.empty((A, N, F), dtype=torch.float32, device=dev)
+        ak, ck = _lib.i32_array(acts), _lib.i32_array(combs)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().mma_nc_aggregate_fwd(
+                _lib.ptr(nbr.rowptr), _lib.ptr(nbr.col), N, nbr.E, _lib.ptr(X), X.stride(0),
+                _lib.ptr(PA), PA.stride(0), _lib.ptr(QA), QA.stride(0), F, A, ak, ck, _lib.ptr(keep),
+                float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.ptr(OUT), _lib.ptr(S),
+                _lib.stream_ptr(dev)), "mma_nc_aggregate_fwd")
+        ctx.nbr, ctx.cfg = nbr, (acts, combs, p_drop, seed)
+        ctx.save_for_backward(X, PA, QA, keep, S)
+        return OUT
+
+    @staticmethod
+    def backward(ctx, dOUT):
+        X, PA, QA, keep, S = ctx.saved_tensors
+        nbr = ctx.nbr
+        acts, combs, p_drop, seed = ctx.cfg
+        dev = dOUT.device
+        N, F = X.shape
+        A = len(acts)
+        dOUT = dOUT.contiguous()
+        gS = torch.empty((N, A * F), dtype=torch.float32, device=dev)
+        dXdir = torch.empty((N, F), dtype=torch.float32, device=dev)
+        dPA = torch.empty((N, A * F), dtype=torch.float32, device=dev)
+        dQA = torch.empty((N, A * F), dtype=torch.float32, device=dev)
+        dXn = torch.empty((N, F), dtype=torch.float32, device=dev)
+        ak, ck = _lib.i32_array(acts), _lib.i32_array(combs)
+        nbr.build_transpose()
+        l = _lib.lib()
+        sd = int(seed) & 0xFFFFFFFFFFFFFFFF
+        with torch.cuda.device(dev):
+            _lib.check(l.mma_nc_aggregate_bwd_dst(
+                _lib.ptr(nbr.rowptr), _lib.ptr(nbr.col), N, nbr.E, _lib.ptr(X), X.stride(0),
+                _lib.ptr(PA), PA.stride(0), _lib.ptr(QA), QA.stride(0), F, A, ak, ck, _lib.ptr(keep),
+                float(p_drop), sd, _lib.ptr(S), _lib.ptr(dOUT), _lib.ptr(gS), _lib.ptr(dXdir),
+                _lib.ptr(dPA), A * F, _lib.stream_ptr(dev)), "mma_nc_aggregate_bwd_dst")
+            _lib.check(l.mma_nc_aggregate_bwd_src(
+                _lib.ptr(nbr.colptr), _lib.ptr(nbr.row_t), _lib.ptr(nbr.perm_t), N, nbr.E,
+                _lib.ptr(X), X.stride(0), _lib.ptr(PA), PA.stride(0), _lib.ptr(QA), QA.stride(0), F, A, ak,
+                _lib.ptr(keep), float(p_drop), sd, _lib.ptr(gS), _lib.ptr(dQA), A * F, _lib.ptr(dXn), F,
+                _lib.stream_ptr(dev)), "mma_nc_aggregate_bwd_src")
+        return dXdir + dXn, dPA, dQA, None, None, None, None, None, None
+
+
+def nc_aggregate(X: Tensor, PA: Tensor, QA: Tensor, nbr, acts: Sequence[int], combs: Sequence[int],
+                 keep: Optional[Tensor] = None, p_drop: float = 0.0, seed: int = 0) -> Tensor:
+    """OUT[a] = combine_a(x_i, sum_j act_a(PA[i,a] + QA[j,a]) * keepscale * x_j)  -> [A, N, F].
+    `nbr` is a NeighbourLists (CSR of add_all; edge id == CSR position)."""
+    if len(acts) > _lib.MAX_AGGR:
+        raise _lib.MMAError("more than 8 aggregators in one call")
+    return _NcAggregate.apply(X, PA, QA, nbr, tuple(int(a) for a in acts), tuple(int(c) for c in combs),
+                              keep, float(p_drop), int(seed))

@@ -141,3 +141,65 @@ def cached_graph(edge_index: Tensor, num_nodes: int) -> Graph:
 
 def clear_cache() -> None:
     _CACHE.clear()
+
+
+class NeighbourLists:
+    """CSR of the node-classification neighbour lists `add_all` (node_classification/
+    utils.py:98-100: add_all[i] = column ids of row i of adj) plus its transpose.
+    Edge id == CSR position, i.e. the order in which the reference consumes neighbours."""
+
+    def __init__(self, rowptr: Tensor, col: Tensor):
+        self.device = _lib.require_cuda(rowptr, col)
+        self.rowptr = rowptr.to(torch.int32).contiguous()
+        self.col = col.to(torch.int32).contiguous()
+        self.N = int(rowptr.numel() - 1)
+        self.E = int(col.numel())
+        self.colptr = self.row_t = self.perm_t = None
+
+    @staticmethod
+    def from_add_all(add_all, device) -> "NeighbourLists":
+        import numpy as np
+        deg = np.fromiter((len(r) for r in add_all), dtype=np.int64, count=len(add_all))
+        rowptr = np.zeros(len(add_all) + 1, dtype=np.int64)
+        np.cumsum(deg, out=rowptr[1:])
+        col = (np.concatenate([np.asarray(r, dtype=np.int64).reshape(-1) for r in add_all])
+               if rowptr[-1] > 0 else np.zeros(0, dtype=np.int64))
+        return NeighbourLists(torch.from_numpy(rowptr).to(device), torch.from_numpy(col).to(device))
+
+    def build_transpose(self):
+        if self.colptr is None:
+            deg = (self.rowptr[1:] - self.rowptr[:-1]).to(torch.int64)
+            row = torch.repeat_interleave(torch.arange(self.N, device=self.device, dtype=torch.int64), deg)
+            self.colptr, self.row_t, self.perm_t = csr_build(self.col.to(torch.int64), row, self.N)
+
+
+class SparseAdj:
+    """CSR (+ transposed CSR) of a torch sparse COO adjacency for K3 (torch.spmm replacement,
+    node_classification/layers.py:41,862)."""
+
+    def __init__(self, adj: Tensor):
+        if adj.layout != torch.sparse_coo:
+            raise RuntimeError("adj must be a torch sparse COO tensor (node_classification/utils.py:139-146)")
+        adj = adj.coalesce()
+        idx, val = adj.indices(), adj.values().to(torch.float32)
+        self.device = _lib.require_cuda(idx, val)
+        self.n_rows, self.n_cols = int(adj.shape[0]), int(adj.shape[1])
+        self.rowptr, self.col, perm = csr_build(idx[0], idx[1], self.n_rows)
+        self.val = val.index_select(0, perm.to(torch.int64)).contiguous()
+        self.colptr, self.row_t, perm_t = csr_build(idx[1], idx[0], self.n_cols)
+        self.val_t = val.index_select(0, perm_t.to(torch.int64)).contiguous()
+
+
+_ADJ_CACHE: "OrderedDict[tuple, SparseAdj]" = OrderedDict()
+
+
+def cached_adj(adj: Tensor) -> SparseAdj:
+    a = adj if adj.is_coalesced() else adj.coalesce()
+    key = (a.indices().data_ptr(), a.values().data_ptr(), a._nnz(), tuple(a.shape), str(a.device))
+    s = _ADJ_CACHE.get(key)
+    if s is None:
+        s = SparseAdj(a)
+        _ADJ_CACHE[key] = s
+        while len(_ADJ_CACHE) > 8:
+            _ADJ_CACHE.popitem(last=False)
+    return s

@@ -1,0 +1,157 @@
+"""Parity of the node-classification drop-ins (K2 masked multi-aggregator layer, K3 SpMM,
+GraphConvolution) against the golden vectors produced by the verbatim reference
+(node_classification/layers.py) and against the oracle restatement.  fp32, tolerance 1e-5
+relative to the largest magnitude of the reference tensor (north_star)."""
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+REL = 1e-5
+
+ORDER = ["moment_3", "sum", "sum2", "sum3", "sum4", "mean", "mean2", "mean3", "mean4", "max", "max2", "max3",
+         "max4", "min", "min2", "min3", "min4", "softmax", "softmin", "std", "normalized_mean"]
+
+
+def close(a, b, rel=REL, what=""):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    scale = max(b.abs().max().item(), 1e-30)
+    err = (a - b).abs().max().item()
+    assert err <= rel * scale, f"{what}: max err {err:.3e} vs scale {scale:.3e} (rel {err / scale:.3e})"
+
+
+def build_layer(gd, dev="cuda"):
+    from mma_b200.node_classification.layers import MMA
+    from oracle import restate
+    Fd, C = gd["x"].shape[1], gd["weight"].shape[1]
+    n = gd["rowptr"].numel() - 1
+    add_all = [gd["col"][gd["rowptr"][i]:gd["rowptr"][i + 1]].numpy() for i in range(n)]
+    ps = {nm: torch.nn.Parameter(torch.empty(2 * Fd, Fd, device=dev)) for nm in ORDER}
+    W = torch.nn.Parameter(torch.empty(Fd, C, device=dev))
+    b = torch.nn.Parameter(torch.empty(C, device=dev))
+    L = MMA(add_all, gd["activation"], gd["k"], Fd, C, W, b, *[ps[nm] for nm in ORDER], gd["p"], gd["names"], dev)
+    with torch.no_grad():
+        W.copy_(gd["weight"]); b.copy_(gd["bias"])
+        for nm in gd["names"]:
+            ps[nm].copy_(gd["masks"][nm])
+    L._inject_keep = {nm: gd["keep_bits"][nm].float().to(dev) / (1.0 - gd["p"]) for nm in gd["names"]}
+    adj = restate.csr_to_sparse_adj(gd["rowptr"], gd["col"], n).to(dev)
+    return L, ps, W, b, adj
+
+
+@pytest.mark.parametrize("name", ["nc_small_mean.pt", "nc_small_min4.pt", "nc_small_mixed.pt",
+                                  "nc_small_sigmoid.pt", "nc_cora_mean_f8.pt"])
+def test_mma_layer_vs_reference_golden(name):
+    gd = load_golden(name)
+    L, ps, W, b, adj = build_layer(gd)
+    x = gd["x"].cuda().requires_grad_()
+    y = L(x, adj)
+    close(y, gd["y"], what=f"{name}: y")
+    grads = torch.autograd.grad(y, [x, W, b] + [ps[nm] for nm in gd["names"]], gd["gy"].cuda())
+    close(grads[0], gd["gx"], what="dx")
+    close(grads[1], gd["gweight"], what="dW")
+    close(grads[2], gd["gbias"], what="db")
+    for g, nm in zip(grads[3:], gd["names"]):
+        close(g, gd["gmasks"][nm], what=f"dmask_{nm}")
+
+
+def test_individual_aggregators_and_errors():
+    from oracle import restate
+    gd = load_golden("nc_small_mixed.pt")
+    L, ps, W, b, adj = build_layer(gd)
+    x = gd["x"].cuda()
+    n = x.shape[0]
+    keeps = {nm: gd["keep_bits"][nm].float() / (1.0 - gd["p"]) for nm in gd["names"]}
+    for nm in gd["names"]:
+        got = getattr(L, "learnable_" + nm)(x, adj)
+        ref = restate.nc_aggregate(gd["x"], gd["rowptr"], gd["col"], gd["masks"][nm], nm, gd["activation"],
+                                   gd["p"], keeps[nm])
+        assert got.shape == (n, x.shape[1])
+        close(got, ref, what=f"learnable_{nm}")
+    L._inject_keep = None
+    with pytest.raises(RuntimeError):
+        L.learnable_std(x, adj)
+    from mma_b200.node_classification.layers import MMA
+    with pytest.raises(KeyError):
+        MMA(L.add_all, "sigmoid", 2, 12, 5, W, b, *[ps[nm] for nm in ORDER], 0.5, ["median"], "cuda")
+    L5 = MMA(L.add_all, "sigmoid", 2, 12, 5, W, b, *[ps[nm] for nm in ORDER], 0.5,
+             ["sum", "sum2", "sum3", "sum4", "mean"], "cuda")
+    with pytest.raises(RuntimeError, match="must match the size"):
+        L5(x, adj)
+    with pytest.raises(RuntimeError):
+        L.cpu()(x.cpu(), adj.cpu())
+    # always-on dropout: stochastic in eval mode, reproducible per seed (Q3)
+    L = L.cuda().eval()
+    torch.manual_seed(7); L._calls = 0; a = L(x, adj)
+    c = L(x, adj)
+    torch.manual_seed(7); L._calls = 0; d = L(x, adj)
+    assert not torch.equal(a, c) and torch.equal(a, d)
+
+
+def test_philox_dropout_in_k2_matches_injected_mask():
+    import mma_b200
+    from oracle import restate
+    gd = load_golden("nc_small_min4.pt")
+    L, ps, W, b, adj = build_layer(gd)
+    L._inject_keep = None
+    x = gd["x"].cuda().requires_grad_()
+    torch.manual_seed(11); L._calls = 0
+    y = L(x, adj)
+    E, Fd = gd["col"].numel(), x.shape[1]
+    keeps = {nm: mma_b200.dropout_keep_scale(gd["p"], L.last_seed, E, Fd, "cuda", stream_id=a).cpu()
+             for a, nm in enumerate(gd["names"])}
+    xr = gd["x"].clone().requires_grad_()
+    masks = {k: v.clone().requires_grad_() for k, v in gd["masks"].items()}
+    n = x.shape[0]
+    yr = restate.nc_forward(xr, adj.cpu(), gd["rowptr"], gd["col"], masks, gd["weight"], gd["bias"], gd["names"],
+                            gd["activation"], gd["p"], keeps)
+    close(y, yr, what="philox y")
+    g = torch.autograd.grad(y, [x] + [ps[nm] for nm in gd["names"]], gd["gy"].cuda())
+    gr = torch.autograd.grad(yr, [xr] + [masks[nm] for nm in gd["names"]], gd["gy"])
+    for a, r in zip(g, gr):
+        close(a, r, what="philox grads")
+
+
+def test_spmm_and_graph_convolution():
+    from mma_b200.node_classification.layers import GraphConvolution, spmm
+    torch.manual_seed(0)
+    n, Fi, Fo = 300, 40, 7
+    dense = (torch.rand(n, n) < 0.03).float() * torch.rand(n, n)
+    adj = dense.to_sparse().cuda()
+    S = torch.randn(n, Fo, device="cuda", requires_grad=True)
+    out = spmm(adj, S)
+    close(out, dense @ S.detach().cpu(), what="spmm")
+    (g,) = torch.autograd.grad(out, [S], torch.ones_like(out))
+    close(g, dense.t() @ torch.ones(n, Fo), what="spmm backward")
+    W = torch.nn.Parameter(torch.empty(Fi, Fo, device="cuda")); b = torch.nn.Parameter(torch.empty(Fo, device="cuda"))
+    gc = GraphConvolution(Fi, Fo, W, b, "cuda")
+    x = torch.randn(n, Fi, device="cuda")
+    y = gc(x, adj)
+    ref = dense @ (x.cpu() @ W.detach().cpu()) + b.detach().cpu()
+    close(y, ref, what="GraphConvolution")
+    (gw,) = torch.autograd.grad(y.sum(), [W])
+    close(gw, x.cpu().t() @ (dense.t() @ torch.ones(n, Fo)), what="GraphConvolution dW")
+
+
+def test_model_trains_on_cora_topology():
+    """config 1 caller (models.py): a few Adam steps on the real Cora topology reduce the loss."""
+    from mma_b200.node_classification.models import MMAConv as Net
+    from oracle import restate
+    topo = load_golden("planetoid_topology.pt")["cora"]
+    rowptr, col = topo["rowptr"].long(), topo["col"].long()
+    n = rowptr.numel() - 1
+    add_all = [col[rowptr[i]:rowptr[i + 1]].numpy() for i in range(n)]
+    torch.manual_seed(42)
+    feats = (torch.rand(n, 64) < 0.05).float().cuda()
+    labels = torch.randint(0, 7, (n,)).cuda()
+    adj = restate.csr_to_sparse_adj(rowptr, col, n).cuda()
+    model = Net(add_all, "new_sigmoid", 2, 64, 16, 7, 0.5, ["mean", "mean2"], "cuda")
+    opt = torch.optim.Adam(model.parameters(), lr=0.01, weight_decay=5e-4)
+    losses = []
+    for _ in range(12):
+        model.train(); opt.zero_grad()
+        loss = torch.nn.functional.nll_loss(model(feats, adj)[:500], labels[:500])
+        loss.backward(); opt.step(); losses.append(loss.item())
+    assert all(torch.isfinite(torch.tensor(losses))) and losses[-1] < losses[0]
