@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""Benchmark of the MultiMaskConv hot path (BASELINE.json: "MultiMaskConv fwd+bwd edges/sec").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c4|c4s|c2]
+
+One step = ONE MultiMaskConv layer call, forward + backward (x -> out, all gradients), on
+BASELINE config 4: synthetic uniform random graph, 2M nodes / 32M edges, hidden 128, aggregators
+mean,sum,min,max,std x scalers identity,amplification,attenuation,linear, always-on dropout 0.5
+(the reference's behaviour, Q3), fp32.  N > 1: the graph is partitioned by destination range
+(strong scaling, one exchange per direction, mma_b200/parallel.py); launched by
+`python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...`.
+
+Rank 0 prints ONE JSON line.  `value` = E / (device time per step), max over ranks.  `e2e` feeds
+x from pinned host memory every step and reads the loss back.  `roofline` is for the dominant
+kernel of the step, timed live with CUDA events on the launching stream.  `cpu_baseline` is the
+oracle port of the reference layer (oracle/restate.py) timed on this box's host cores on a 1/16
+sub-graph.  `--impl reference` prints the same line for that CPU path alone.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+AGGR = ["mean", "sum", "min", "max", "std"]
+SCAL = ["identity", "amplification", "attenuation", "linear"]
+CONFIGS = {
+    # name: (nodes, edges, hidden)
+    "c4": (2_000_000, 32_000_000, 128),
+    "c4s": (125_000, 2_000_000, 128),      # the 1/16 sub-graph (CPU-baseline size), for quick checks
+}
+METRIC = "MultiMaskConv fwd+bwd edges/sec"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------
+# algorithmic bytes (int32 indices, fp32 data, one gathered row per edge,
+# no L2 credit, only tensors materialised at the op boundary)
+# ------------------------------------------------------------------------------------------
+def algo_bytes(N, E, F, A, S, n_mm, std):
+    fwd = 4 * (N + 1) + 4 * E + 4 * F * E + 4 * F * N + 4 * F * A * S * N + 4 * F * n_mm * N
+    bwd = (4 * F * A * S * N + 4 * F * n_mm * N + 8 * F * N + 8 * (N + 1) + 8 * E + 4 * E + 4 * F * E
+           + (4 * F * E if std else 0))
+    # per kernel of THIS implementation (its own contract: inputs once, outputs once)
+    k_fwd = fwd + (8 * F * N if std else 0)                         # + saved mean/var
+    k_dst = (4 * F * A * S * N + 4 * F * n_mm * N + 4 * F * N       # dY, args, dP
+             + 4 * (N + 1) + 4 * E + 4 * E + 4 * E                  # rowptr, col, perm, csr2csc
+             + (4 * F * E + 4 * F * N + 8 * F * N if std else 0)    # re-gather Q, P, mean/var
+             + 4 * F * E)                                           # per-edge gradient rows (write)
+    k_src = 4 * (N + 1) + 4 * F * E + 4 * F * N                     # colptr, G rows (read), dQ
+    return {"fwd": fwd, "bwd": bwd, "mmconv_aggregate_fwd": k_fwd, "mmconv_aggregate_bwd_dst": k_dst,
+            "mma_segment_sum_rows": k_src}
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        hi = [v for v in sm if v >= 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": (hi[len(hi) // 2] if hi else None), "sm_max_mhz": (max(mx) if mx else None),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference layer on a bounded sample
+# ------------------------------------------------------------------------------------------
+def cpu_reference_run(N, E, F, steps=1, warmup=0, seed=42):
+    """Times restate.mmaconv_forward + backward (the reference's own op sequence: two [E,T,F]
+    gathers, cat, edge-level Linear, dropout, A scatter passes, scalers, post Linears) with all
+    host threads.  Returns (edges/s, seconds per step, threads)."""
+    from oracle import restate
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(seed)
+    src = torch.randint(0, N, (E,), generator=g)
+    dst = torch.randint(0, N, (E,), generator=g)
+    ei = torch.stack([src, dst])
+    hist = torch.bincount(torch.bincount(dst, minlength=N))
+    avg = restate.avg_deg_from_hist(hist)
+    A, S = len(AGGR), len(SCAL)
+    lin = lambda o, i: ((torch.rand(o, i, generator=g) - 0.5) * (2 / i ** 0.5), (torch.rand(o, generator=g) - 0.5) * 0.1)
+    w = restate.MMAConvWeights(F, F, AGGR, SCAL, avg, 1, F, F, False, None, [[lin(F, 2 * F)]],
+                               [[lin(F, (A * S + 1) * F)]], lin(F, F))
+    for t in w.tensors():
+        t.requires_grad_()
+    x = torch.randn(N, F, generator=g).requires_grad_()
+    gy = torch.randn(N, F, generator=g)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        y = restate.mmaconv_forward(w, x, ei, None, None, strict=False)
+        torch.autograd.grad(y, [x] + w.tensors(), gy)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    best = min(times)
+    return E / best, best, torch.get_num_threads()
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="mma_b200", choices=["mma_b200", "reference"])
+    ap.add_argument("--config", default="c4", choices=sorted(CONFIGS))
+    ap.add_argument("--dropout", type=float, default=0.5, help="0.5 = the reference's always-on dropout")
+    ap.add_argument("--slices", type=int, default=4, help="feature windows of the sharded pipeline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    N, E, F = CONFIGS[args.config]
+    A, S = len(AGGR), len(SCAL)
+    warm = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    cfg = {"workload": f"config 4: uniform random graph N={N} E={E} hidden={F}, MMAConv fwd+bwd, aggregators "
+                       f"{','.join(AGGR)} x scalers {','.join(SCAL)}, towers=1, dropout {args.dropout}",
+           "nodes": N, "edges": E, "hidden": F, "aggregators": AGGR, "scalers": SCAL,
+           "parallelism": f"dst-range x{world}" if world > 1 else "single GPU",
+           "l2": "inputs larger than L2 (x, P, Q, Y, G are 1-20 GB each vs 126 MB L2): no flush needed"}
+
+    # ---------------- reference arm: the CPU path on a bounded sample (rank 0 only) ----------------
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        sub = 16
+        n_s, e_s = N // sub, E // sub
+        v, sec, thr = cpu_reference_run(n_s, e_s, F, steps=max(1, min(args.steps, 2)), warmup=min(args.warmup, 1))
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "edges/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+                "cpu_baseline": {"value": v, "unit": "edges/s", "cores": thr, "kind": "port",
+                                 "sample": f"1/{sub} sub-graph of the same generator (N={n_s}, E={e_s}, hidden={F}); "
+                                           "oracle port of the reference layer (the reference is pure Python + "
+                                           "PyG/torch_scatter, not installable here), best of "
+                                           f"{max(1, min(args.steps, 2))} fwd+bwd"},
+                "e2e": {"value": v, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ---------------- our arm ----------------
+    assert torch.cuda.is_available(), "bench.py needs a GPU (mma_b200 has no CPU path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import mma_b200
+    from mma_b200 import _lib
+    from mma_b200.parallel import ShardedGraph, allreduce_grads
+
+    torch.manual_seed(42)
+    gen = torch.Generator(device=dev).manual_seed(42)
+    src = torch.randint(0, N, (E,), generator=gen, device=dev)
+    dst = torch.randint(0, N, (E,), generator=gen, device=dev)
+    deg = torch.bincount(dst, minlength=N)
+    hist = torch.bincount(deg).cpu()
+    max_deg = int(deg.max().item())
+    del deg
+    conv = mma_b200.MMAConv(F, F, AGGR, SCAL, hist, towers=1, strict_reference=False).to(dev)
+    conv.dropout = args.dropout
+    conv.comm_slices = args.slices
+    conv.global_max_deg = max_deg
+    if world > 1:
+        graph = ShardedGraph(src, dst, N, rank, world, balance="nodes")
+        rows = graph.rows
+        graph.local.build_transpose()
+    else:
+        graph = mma_b200.Graph(src, dst, N)
+        rows = N
+        _ = graph.max_deg
+    del src, dst
+    torch.cuda.empty_cache()
+    x = torch.randn(rows, F, device=dev, generator=gen).requires_grad_()
+    gy = torch.randn(rows, F, device=dev, generator=gen)
+    params = list(conv.parameters()) + conv.mask_parameters()
+
+    def step(xin):
+        y = conv(xin, graph)
+        grads = torch.autograd.grad(y, [xin] + params, gy)
+        if world > 1:
+            for p, g in zip(params, grads[1:]):
+                p.grad = g
+            allreduce_grads(params)
+        return y, grads[0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warm):
+        step(x)
+    barrier()
+    _lib.reset_counters()
+    _lib.enable_timing(True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(x)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1) / args.steps
+    ktimes = _lib.timing_summary()
+    launches = sum(_lib.LAUNCH_COUNTS.values())
+    _lib.enable_timing(False)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+
+    # ---------------- e2e: host buffers, H2D of x each step, D2H of the loss ----------------
+    e2e = None
+    if not args.no_e2e:
+        xh = torch.randn(rows, F).pin_memory()
+        xd = torch.empty(rows, F, device=dev)
+        lossh = torch.empty((), dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            xd.copy_(xh, non_blocking=True)
+            xin = xd.detach().requires_grad_()
+            y, gx = step(xin)
+            lossh.copy_((y * gy).sum() + gx[0, 0] * 0, non_blocking=True)
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        e1.record()
+        barrier()
+        ms_e = e0.elapsed_time(e1) / args.steps
+        if world > 1:
+            t = torch.tensor([ms_e], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e = float(t.item())
+        e2e = {"value": E / (ms_e * 1e-3), "unit": "edges/s", "ms_per_step": ms_e,
+               "h2d_bytes_per_step": rows * F * 4 * world, "d2h_bytes_per_step": 4 * world}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---------------- roofline of the dominant kernel ----------------
+    peak, peak_kind = peaks()
+    n_loc, e_loc = N // world, E // world
+    ab = algo_bytes(n_loc, e_loc, F, A, S, 2, True)
+    per_kernel = {}
+    for name, (cnt, mean_ms) in ktimes.items():
+        per_step = cnt / args.steps
+        nbytes = ab.get(name)
+        if name == "mma_segment_sum_rows" and world > 1:
+            nbytes = 4 * (N + 1) + 4 * F * e_loc + 4 * F * N          # partial dQ over ALL sources
+        per_kernel[name] = {"launches_per_step": per_step, "ms_per_launch": mean_ms,
+                            "ms_per_step": mean_ms * per_step,
+                            "algorithmic_GB_per_step": None if nbytes is None else nbytes / 1e9,
+                            "GBps": None if nbytes is None else nbytes / 1e9 / (mean_ms * per_step * 1e-3)}
+    dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_step"]) if per_kernel else None
+    roofline = None
+    if dom:
+        d = per_kernel[dom]
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": d["GBps"], "peak": peak, "unit": "GB/s",
+                    "frac": d["GBps"] / peak, "traffic": None, "peak_kind": peak_kind,
+                    "launch_ms": d["ms_per_launch"], "share_of_step": d["ms_per_step"] / ms}
+    agg_ms = sum(v["ms_per_step"] for v in per_kernel.values())
+    step_algo = (ab["fwd"] + ab["bwd"]) / 1e9
+    extra = {"kernels": per_kernel,
+             "aggregate_only": {"ms_per_step": agg_ms, "edges_per_s": E / (agg_ms * 1e-3) if agg_ms else None,
+                                "algorithmic_GB_per_step_per_gpu": step_algo,
+                                "frac_of_hbm_peak": step_algo / (agg_ms * 1e-3) / peak if agg_ms else None,
+                                "note": "K1 fwd + bwd-dst + transpose pass only (SURVEY 8(d) formulas, "
+                                        "materialised Y with S scaler blocks); dense GEMMs excluded"},
+             "dense_and_other_ms_per_step": ms - agg_ms}
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        sub = 16
+        v, sec, thr = cpu_reference_run(N // sub, E // sub, F, steps=1, warmup=0)
+        cpu = {"value": v, "unit": "edges/s", "cores": thr, "kind": "port",
+               "sample": f"1/{sub} sub-graph (N={N // sub}, E={E // sub}, hidden={F}), oracle port of the reference "
+                         f"layer, one fwd+bwd = {sec:.1f} s"}
+
+    line = {"metric": METRIC, "value": E / (ms * 1e-3), "unit": "edges/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "clocks": clocks,
+            "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "detail": extra}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -83,6 +83,10 @@ int mma_invert_perm(const int32_t *perm, int64_t E, int32_t *inv, mma_stream_t s
  *   Y[i, t, (s*A + a)*F_in + f] = aggr_a({m[e, t*F_in+f] : dst(e)=i}) * prod_{s'<=s} scale_{s'}(deg_i)
  *
  *   rowptr/col/perm : CSR by destination from mma_csr_build (perm may be NULL = identity)
+ *   edge_gid [E], E_total : for one shard of a partitioned graph, the GLOBAL id of each local
+ *                       edge (local original order) and the global edge count; dropout and
+ *                       arg_min/arg_max then use global ids so results are shard-invariant.
+ *                       NULL = the local ids are the global ids.
  *   P [n_rows, F] ld ldp | Q [n_src, F] ld ldq | R [E, F] ld ldr, ORIGINAL edge order | any may be NULL
  *   keep [E, F] ld ldk : explicit keep-scale (0 or 1/(1-p)), original edge order, or NULL
  *   p_drop, seed      : if keep == NULL and p_drop > 0: in-kernel Philox4x32-10 dropout keyed by
@@ -95,9 +99,14 @@ int mma_invert_perm(const int32_t *perm, int64_t E, int32_t *inv, mma_stream_t s
  *   Y [n_rows, T, S*A*F_in] ld ldy
  *   arg_min/arg_max [n_rows, F] int32 : ORIGINAL edge id of the selected edge (E if none); NULL ok
  *   stat_mean/stat_var [n_rows, F] : saved for the var/std backward; NULL ok
+ *   col0, ncols : process only the column window [col0, col0+ncols) of F (ncols <= 0: all columns).
+ *                       Every tensor is still addressed with GLOBAL column indices, so windows of one
+ *                       problem can be launched independently (feature-sliced comm/compute pipeline)
+ *                       and produce exactly the unsliced result (the dropout stream is keyed by the
+ *                       global column).
  * ---------------------------------------------------------------------- */
 int mmconv_aggregate_fwd(const int32_t *rowptr, const int32_t *col, const int32_t *perm,
-                         int64_t n_rows, int64_t E,
+                         const int32_t *edge_gid, int64_t E_total, int64_t n_rows, int64_t E,
                          const float *P, int64_t ldp, const float *Q, int64_t ldq,
                          const float *R, int64_t ldr, const float *keep, int64_t ldk,
                          float p_drop, uint64_t seed,
@@ -105,7 +114,7 @@ int mmconv_aggregate_fwd(const int32_t *rowptr, const int32_t *col, const int32_
                          int S, const int32_t *scaler_kinds,
                          const float *scale_tab, int64_t tab_stride,
                          float *Y, int64_t ldy, int32_t *arg_min, int32_t *arg_max,
-                         float *stat_mean, float *stat_var, mma_stream_t stream);
+                         float *stat_mean, float *stat_var, int col0, int ncols, mma_stream_t stream);
 
 /* K1 backward, destination pass (replaces autograd of mma_conv.py:157-196):
  *   G[gslot(pos), c] = dL/dm_pre[e, c]   for every edge (row of the per-edge gradient),
@@ -113,7 +122,7 @@ int mmconv_aggregate_fwd(const int32_t *rowptr, const int32_t *col, const int32_
  * gslot [E] maps CSR position -> row of G (NULL = CSR position; pass `perm` to get G in
  * original edge order == dL/dR).  arg_min/arg_max/stat_* are the forward's outputs. */
 int mmconv_aggregate_bwd_dst(const int32_t *rowptr, const int32_t *col, const int32_t *perm,
-                             int64_t n_rows, int64_t E,
+                             const int32_t *edge_gid, int64_t E_total, int64_t n_rows, int64_t E,
                              const float *P, int64_t ldp, const float *Q, int64_t ldq,
                              const float *R, int64_t ldr, const float *keep, int64_t ldk,
                              float p_drop, uint64_t seed,
@@ -124,7 +133,7 @@ int mmconv_aggregate_bwd_dst(const int32_t *rowptr, const int32_t *col, const in
                              const int32_t *arg_min, const int32_t *arg_max,
                              const float *stat_mean, const float *stat_var,
                              const int32_t *gslot, float *G, int64_t ldg,
-                             float *dP, int64_t lddp, mma_stream_t stream);
+                             float *dP, int64_t lddp, int col0, int ncols, mma_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * K3 / transpose pass: deterministic segmented row sum (CSR SpMM)

@@ -29,12 +29,12 @@ _SIGS = {
     "mma_csr_build_workspace_bytes": ([_i64, _i64, C.POINTER(C.c_size_t)], C.c_int),
     "mma_csr_build": ([_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, C.c_size_t, _vp], C.c_int),
     "mma_invert_perm": ([_vp, _i64, _vp, _vp], C.c_int),
-    "mmconv_aggregate_fwd": ([_vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64,
+    "mmconv_aggregate_fwd": ([_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64,
                               _f32, _u64, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _i64,
-                              _vp, _i64, _vp, _vp, _vp, _vp, _vp], C.c_int),
-    "mmconv_aggregate_bwd_dst": ([_vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64,
+                              _vp, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _vp], C.c_int),
+    "mmconv_aggregate_bwd_dst": ([_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64,
                                   _f32, _u64, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _i64,
-                                  _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp], C.c_int),
+                                  _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i32, _i32, _vp], C.c_int),
     "mma_segment_sum_rows": ([_vp, _vp, _vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp], C.c_int),
     "mma_nc_aggregate_fwd": ([_vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32,
                               _vp, _vp, _vp, _f32, _u64, _vp, _vp, _vp], C.c_int),
@@ -110,3 +110,48 @@ def require_cuda(*tensors) -> torch.device:
 
 def i32_array(values):
     return (C.c_int32 * len(values))(*values)
+
+
+# ---------------------------------------------------------------------------
+# launch accounting / per-kernel CUDA-event timing (used by bench.py)
+# ---------------------------------------------------------------------------
+import contextlib
+
+LAUNCH_COUNTS = {}          # kernel-launching C-ABI call name -> number of launches
+_TIMERS = None              # None = off; else dict name -> list of (start, end) cuda events
+
+
+def reset_counters():
+    LAUNCH_COUNTS.clear()
+
+
+def enable_timing(on: bool = True):
+    global _TIMERS
+    _TIMERS = {} if on else None
+
+
+def timing_summary():
+    """name -> (launches, mean ms) from the recorded CUDA events (call after a synchronize)."""
+    out = {}
+    for name, evs in (_TIMERS or {}).items():
+        ms = [a.elapsed_time(b) for a, b in evs]
+        out[name] = (len(ms), sum(ms) / max(len(ms), 1))
+    return out
+
+
+@contextlib.contextmanager
+def kernel_scope(name: str, device):
+    """Wraps ONE kernel launch through the C ABI: counts it and, when timing is on, brackets it
+    with CUDA events on the launching (current) stream."""
+    LAUNCH_COUNTS[name] = LAUNCH_COUNTS.get(name, 0) + 1
+    if _TIMERS is None:
+        with torch.cuda.device(device):
+            yield
+        return
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.device(device):
+        st = torch.cuda.current_stream(device)
+        a.record(st)
+        yield
+        b.record(st)
+    _TIMERS.setdefault(name, []).append((a, b))

@@ -20,8 +20,8 @@
 namespace mma {
 
 struct MMConvParams {
-    const int32_t *rowptr, *col, *perm;
-    int64_t n_rows, E;
+    const int32_t *rowptr, *col, *perm, *gid;
+    int64_t n_rows, E, E_total;
     const float *P, *Q, *R, *keep;
     int64_t ldp, ldq, ldr, ldk;
     Dropout drop;
@@ -47,6 +47,7 @@ struct MMConvParams {
     int64_t lddp;
     // launch geometry
     int lanes_log2, chunks;
+    int col0, ncols;        // column window [col0, col0 + ncols) processed by this launch
     int64_t n_groups;
 };
 
@@ -81,7 +82,7 @@ __device__ __forceinline__ Vec<VEC> message(const MMConvParams &p, const Vec<VEC
 template <int VEC, int U, typename Consume>
 __device__ __forceinline__ void visit_edges(const MMConvParams &p, int pos, int c, const Vec<VEC> &pv,
                                             bool need_m, bool need_eid, Consume &&consume) {
-    int j[U], eid[U];
+    int j[U], eid[U], ge[U];
     Vec<VEC> q[U], r[U], ks[U];
     if (need_m && p.Q) {
 #pragma unroll
@@ -89,6 +90,8 @@ __device__ __forceinline__ void visit_edges(const MMConvParams &p, int pos, int 
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) eid[u] = (need_eid && p.perm) ? __ldg(p.perm + pos + u) : pos + u;
+#pragma unroll
+    for (int u = 0; u < U; ++u) ge[u] = (need_eid && p.gid) ? __ldg(p.gid + eid[u]) : eid[u];   // global edge id
     if (need_m && p.Q) {
 #pragma unroll
         for (int u = 0; u < U; ++u) q[u] = ld_vec_stream<VEC>(p.Q + (int64_t)j[u] * p.ldq + c);
@@ -103,13 +106,13 @@ __device__ __forceinline__ void visit_edges(const MMConvParams &p, int pos, int 
         for (int u = 0; u < U; ++u) ks[u] = ld_vec_stream<VEC>(p.keep + (int64_t)eid[u] * p.ldk + c);
     } else if (p.use_philox) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) ks[u] = dropout_keep<VEC>(p.drop, (uint32_t)eid[u], c, 0u);
+        for (int u = 0; u < U; ++u) ks[u] = dropout_keep<VEC>(p.drop, (uint32_t)ge[u], c, 0u);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         Vec<VEC> m{};
         if (need_m) m = message<VEC>(p, pv, q[u], r[u], ks[u], has_scale);
-        consume(pos + u, eid[u], m, ks[u], has_scale);
+        consume(pos + u, ge[u], m, ks[u], has_scale);
     }
 }
 
@@ -132,6 +135,12 @@ __device__ __forceinline__ bool locate(const MMConvParams &p, int64_t &row, int 
     const int chunk = (int)(group - row * p.chunks);
     c = ((chunk << p.lanes_log2) + sub) * vec;
     return c < p.F;
+}
+
+// CSR position -> (global) original edge id
+__device__ __forceinline__ int32_t orig_edge_id(const MMConvParams &p, int pos) {
+    const int32_t e = p.perm ? __ldg(p.perm + pos) : pos;
+    return p.gid ? __ldg(p.gid + e) : e;
 }
 
 __device__ __forceinline__ void scaler_factors(const MMConvParams &p, int degc, float *fac) {
@@ -229,8 +238,8 @@ __global__ void __launch_bounds__(256) mmconv_fwd_kernel(const __grid_constant__
         int32_t amn[VEC], amx[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-            amn[v] = acc.amn[v] < 0 ? (int32_t)p.E : (p.perm ? __ldg(p.perm + acc.amn[v]) : acc.amn[v]);
-            amx[v] = acc.amx[v] < 0 ? (int32_t)p.E : (p.perm ? __ldg(p.perm + acc.amx[v]) : acc.amx[v]);
+            amn[v] = acc.amn[v] < 0 ? (int32_t)p.E_total : orig_edge_id(p, acc.amn[v]);
+            amx[v] = acc.amx[v] < 0 ? (int32_t)p.E_total : orig_edge_id(p, acc.amx[v]);
         }
         if (p.arg_min) st_vec_i32_stream<VEC>(p.arg_min + row * p.F + c, amn);
         if (p.arg_max) st_vec_i32_stream<VEC>(p.arg_max + row * p.F + c, amx);
@@ -339,7 +348,7 @@ __global__ void __launch_bounds__(256) mmconv_bwd_dst_kernel(const __grid_consta
 // host side
 // ----------------------------------------------------------------------------------------
 static int fill_params(MMConvParams &p, const int32_t *rowptr, const int32_t *col, const int32_t *perm,
-                       int64_t n_rows, int64_t E, const float *P, int64_t ldp, const float *Q, int64_t ldq,
+                       const int32_t *gid, int64_t E_total, int64_t n_rows, int64_t E, const float *P, int64_t ldp, const float *Q, int64_t ldq,
                        const float *R, int64_t ldr, const float *keep, int64_t ldk, float p_drop, uint64_t seed,
                        int T, int F_in, int A, const int32_t *aggr_kinds, int S, const int32_t *scaler_kinds,
                        const float *scale_tab, int64_t tab_stride) {
@@ -351,7 +360,8 @@ static int fill_params(MMConvParams &p, const int32_t *rowptr, const int32_t *co
     if (Q && !col && E > 0) return MMA_ERR_INVALID;
     if (p_drop < 0.0f || p_drop > 1.0f) return MMA_ERR_INVALID;
     p = MMConvParams{};
-    p.rowptr = rowptr; p.col = col; p.perm = perm; p.n_rows = n_rows; p.E = E;
+    p.rowptr = rowptr; p.col = col; p.perm = perm; p.gid = gid; p.n_rows = n_rows; p.E = E;
+    p.E_total = gid ? E_total : E;
     p.P = P; p.Q = Q; p.R = R; p.keep = keep; p.ldp = ldp; p.ldq = ldq; p.ldr = ldr; p.ldk = ldk;
     p.drop = make_dropout(p_drop, seed);
     p.use_philox = (keep == nullptr && p_drop > 0.0f) ? 1 : 0;
@@ -371,9 +381,12 @@ static int fill_params(MMConvParams &p, const int32_t *rowptr, const int32_t *co
     return MMA_OK;
 }
 
-static int choose_geometry(MMConvParams &p, bool vec4_ok) {
+static int choose_geometry(MMConvParams &p, bool vec4_ok, int col0, int ncols) {
+    if (ncols <= 0) { col0 = 0; ncols = p.F; }
+    p.col0 = col0; p.ncols = ncols;
+    vec4_ok = vec4_ok && (col0 % 4 == 0) && (ncols % 4 == 0);
     const int vec = vec4_ok ? 4 : 1;
-    const int per_row = (p.F + vec - 1) / vec;       // lanes needed for one full row
+    const int per_row = (ncols + vec - 1) / vec;     // lanes needed for one row of the window
     int lg = 0;
     while ((1 << lg) < per_row && lg < 5) ++lg;
     p.lanes_log2 = lg;
@@ -390,15 +403,16 @@ static inline bool ok4(const void *ptr, int64_t ld) { return ptr == nullptr || (
 using namespace mma;
 
 extern "C" int mmconv_aggregate_fwd(const int32_t *rowptr, const int32_t *col, const int32_t *perm,
-                                    int64_t n_rows, int64_t E, const float *P, int64_t ldp,
+                                    const int32_t *edge_gid, int64_t E_total, int64_t n_rows, int64_t E, const float *P, int64_t ldp,
                                     const float *Q, int64_t ldq, const float *R, int64_t ldr,
                                     const float *keep, int64_t ldk, float p_drop, uint64_t seed,
                                     int T, int F_in, int A, const int32_t *aggr_kinds, int S,
                                     const int32_t *scaler_kinds, const float *scale_tab, int64_t tab_stride,
                                     float *Y, int64_t ldy, int32_t *arg_min, int32_t *arg_max,
-                                    float *stat_mean, float *stat_var, mma_stream_t stream) {
+                                    float *stat_mean, float *stat_var, int col0, int ncols,
+                                    mma_stream_t stream) {
     MMConvParams p;
-    int rc = fill_params(p, rowptr, col, perm, n_rows, E, P, ldp, Q, ldq, R, ldr, keep, ldk, p_drop, seed,
+    int rc = fill_params(p, rowptr, col, perm, edge_gid, E_total, n_rows, E, P, ldp, Q, ldq, R, ldr, keep, ldk, p_drop, seed,
                          T, F_in, A, aggr_kinds, S, scaler_kinds, scale_tab, tab_stride);
     if (rc != MMA_OK) return rc;
     if (!Y) return MMA_ERR_INVALID;
@@ -411,7 +425,8 @@ extern "C" int mmconv_aggregate_fwd(const int32_t *rowptr, const int32_t *col, c
     }
     const bool v4 = (F_in % 4 == 0) && ok4(P, ldp) && ok4(Q, ldq) && ok4(R, ldr) && ok4(keep, ldk) &&
                     ok4(Y, ldy) && ok4(arg_min, 4) && ok4(arg_max, 4) && ok4(stat_mean, 4) && ok4(stat_var, 4);
-    const int vec = choose_geometry(p, v4);
+    if (col0 < 0 || col0 + (ncols > 0 ? ncols : 0) > p.F) return MMA_ERR_INVALID;
+    const int vec = choose_geometry(p, v4, col0, ncols);
     const int64_t threads = p.n_groups << p.lanes_log2;
     const int block = 256;
     const int64_t grid = (threads + block - 1) / block;
@@ -435,7 +450,7 @@ extern "C" int mmconv_aggregate_fwd(const int32_t *rowptr, const int32_t *col, c
 }
 
 extern "C" int mmconv_aggregate_bwd_dst(const int32_t *rowptr, const int32_t *col, const int32_t *perm,
-                                        int64_t n_rows, int64_t E, const float *P, int64_t ldp,
+                                        const int32_t *edge_gid, int64_t E_total, int64_t n_rows, int64_t E, const float *P, int64_t ldp,
                                         const float *Q, int64_t ldq, const float *R, int64_t ldr,
                                         const float *keep, int64_t ldk, float p_drop, uint64_t seed,
                                         int T, int F_in, int A, const int32_t *aggr_kinds, int S,
@@ -443,9 +458,9 @@ extern "C" int mmconv_aggregate_bwd_dst(const int32_t *rowptr, const int32_t *co
                                         const float *dY, int64_t ldy, const int32_t *arg_min,
                                         const int32_t *arg_max, const float *stat_mean, const float *stat_var,
                                         const int32_t *gslot, float *G, int64_t ldg, float *dP, int64_t lddp,
-                                        mma_stream_t stream) {
+                                        int col0, int ncols, mma_stream_t stream) {
     MMConvParams p;
-    int rc = fill_params(p, rowptr, col, perm, n_rows, E, P, ldp, Q, ldq, R, ldr, keep, ldk, p_drop, seed,
+    int rc = fill_params(p, rowptr, col, perm, edge_gid, E_total, n_rows, E, P, ldp, Q, ldq, R, ldr, keep, ldk, p_drop, seed,
                          T, F_in, A, aggr_kinds, S, scaler_kinds, scale_tab, tab_stride);
     if (rc != MMA_OK) return rc;
     if (!dY || (!G && !dP && E > 0)) return MMA_ERR_INVALID;
@@ -462,7 +477,8 @@ extern "C" int mmconv_aggregate_bwd_dst(const int32_t *rowptr, const int32_t *co
     const bool v4 = (F_in % 4 == 0) && ok4(P, ldp) && ok4(Q, ldq) && ok4(R, ldr) && ok4(keep, ldk) &&
                     ok4(dY, ldy) && ok4(arg_min, 4) && ok4(arg_max, 4) && ok4(stat_mean, 4) &&
                     ok4(stat_var, 4) && ok4(G, ldg) && ok4(dP, lddp);
-    const int vec = choose_geometry(p, v4);
+    if (col0 < 0 || col0 + (ncols > 0 ? ncols : 0) > p.F) return MMA_ERR_INVALID;
+    const int vec = choose_geometry(p, v4, col0, ncols);
     const int64_t threads = p.n_groups << p.lanes_log2;
     const int block = 256;
     const int64_t grid = (threads + block - 1) / block;

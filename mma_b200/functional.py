@@ -71,14 +71,15 @@ class _MMConvAggregate(torch.autograd.Function):
         stat_var = torch.empty((n, F), dtype=torch.float32, device=dev) if need_sq else None
         ak, sk = _lib.i32_array(akinds), _lib.i32_array(skinds)
         perm = None if graph.perm is None else graph.perm
-        with torch.cuda.device(dev):
+        with _lib.kernel_scope("mmconv_aggregate_fwd", dev):
             _lib.check(_lib.lib().mmconv_aggregate_fwd(
-                _lib.ptr(graph.rowptr), _lib.ptr(graph.col), _lib.ptr(perm), n, graph.E,
+                _lib.ptr(graph.rowptr), _lib.ptr(graph.col), _lib.ptr(perm), _lib.ptr(graph.gid), graph.E_total,
+                n, graph.E,
                 _lib.ptr(P), _ld(P), _lib.ptr(Q), _ld(Q), _lib.ptr(R), _ld(R), _lib.ptr(keep), _ld(keep),
                 float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, T, F_in, A, ak, S, sk,
                 _lib.ptr(tab), 0 if tab is None else tab.shape[1],
                 _lib.ptr(Y), Y.stride(0), _lib.ptr(arg_min), _lib.ptr(arg_max),
-                _lib.ptr(stat_mean), _lib.ptr(stat_var), _lib.stream_ptr(dev)), "mmconv_aggregate_fwd")
+                _lib.ptr(stat_mean), _lib.ptr(stat_var), 0, 0, _lib.stream_ptr(dev)), "mmconv_aggregate_fwd")
         ctx.graph, ctx.cfg = graph, (T, F_in, akinds, skinds, p_drop, seed)
         ctx.has = (P is not None, Q is not None, R is not None)
         ctx.save_for_backward(P, Q, R, keep, tab, arg_min, arg_max, stat_mean, stat_var)
@@ -115,22 +116,24 @@ class _MMConvAggregate(torch.autograd.Function):
             gslot = graph.csr2csc
         ak, sk = _lib.i32_array(akinds), _lib.i32_array(skinds)
         l = _lib.lib()
-        with torch.cuda.device(dev):
+        with _lib.kernel_scope("mmconv_aggregate_bwd_dst", dev):
             _lib.check(l.mmconv_aggregate_bwd_dst(
-                _lib.ptr(graph.rowptr), _lib.ptr(graph.col), _lib.ptr(graph.perm), n, E,
+                _lib.ptr(graph.rowptr), _lib.ptr(graph.col), _lib.ptr(graph.perm), _lib.ptr(graph.gid),
+                graph.E_total, n, E,
                 _lib.ptr(P), _ld(P), _lib.ptr(Q), _ld(Q), _lib.ptr(R), _ld(R), _lib.ptr(keep), _ld(keep),
                 float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, T, F_in, A, ak, S, sk,
                 _lib.ptr(tab), 0 if tab is None else tab.shape[1],
                 _lib.ptr(dY), dY.stride(0), _lib.ptr(arg_min), _lib.ptr(arg_max),
                 _lib.ptr(stat_mean), _lib.ptr(stat_var), _lib.ptr(gslot), _lib.ptr(G), F,
-                _lib.ptr(dP), F, _lib.stream_ptr(dev)), "mmconv_aggregate_bwd_dst")
-            dQ = None
-            if need_Q:
-                graph.build_transpose()
-                dQ = torch.empty((Q.shape[0], F), dtype=torch.float32, device=dev)
-                if Q.shape[0] != graph.n_src:
-                    raise RuntimeError("Q rows != number of source nodes of the graph")
-                idx = graph.perm_t if need_R else None
+                _lib.ptr(dP), F, 0, 0, _lib.stream_ptr(dev)), "mmconv_aggregate_bwd_dst")
+        dQ = None
+        if need_Q:
+            graph.build_transpose()
+            dQ = torch.empty((Q.shape[0], F), dtype=torch.float32, device=dev)
+            if Q.shape[0] != graph.n_src:
+                raise RuntimeError("Q rows != number of source nodes of the graph")
+            idx = graph.perm_t if need_R else None
+            with _lib.kernel_scope("mma_segment_sum_rows", dev):
                 _lib.check(l.mma_segment_sum_rows(_lib.ptr(graph.colptr), _lib.ptr(idx), None, graph.n_src,
                                                   _lib.ptr(G), F, F, _lib.ptr(dQ), F,
                                                   _lib.stream_ptr(dev)), "mma_segment_sum_rows")
@@ -175,7 +178,7 @@ class _SegmentSumRows(torch.autograd.Function):
         src = _c(src)
         F = src.shape[1]
         out = torch.empty((n_rows, F), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.kernel_scope("mma_segment_sum_rows", dev):
             _lib.check(_lib.lib().mma_segment_sum_rows(_lib.ptr(ptr), _lib.ptr(idx), _lib.ptr(val), n_rows,
                                                        _lib.ptr(src), src.stride(0), F, _lib.ptr(out), F,
                                                        _lib.stream_ptr(dev)), "mma_segment_sum_rows")
@@ -190,7 +193,7 @@ class _SegmentSumRows(torch.autograd.Function):
         g = g.contiguous()
         dev, F = g.device, g.shape[1]
         d = torch.empty((n_src, F), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.kernel_scope("mma_segment_sum_rows", dev):
             _lib.check(_lib.lib().mma_segment_sum_rows(_lib.ptr(ptr_t), _lib.ptr(idx_t), _lib.ptr(val_t), n_src,
                                                        _lib.ptr(g), F, F, _lib.ptr(d), F,
                                                        _lib.stream_ptr(dev)), "mma_segment_sum_rows")
@@ -232,7 +235,7 @@ class _NcAggregate(torch.autograd.Function):
         OUT = torch.empty((A, N, F), dtype=torch.float32, device=dev)
         S = torch.empty((A, N, F), dtype=torch.float32, device=dev)
         ak, ck = _lib.i32_array(acts), _lib.i32_array(combs)
-        with torch.cuda.device(dev):
+        with _lib.kernel_scope("mma_nc_aggregate_fwd", dev):
             _lib.check(_lib.lib().mma_nc_aggregate_fwd(
                 _lib.ptr(nbr.rowptr), _lib.ptr(nbr.col), N, nbr.E, _lib.ptr(X), X.stride(0),
                 _lib.ptr(PA), PA.stride(0), _lib.ptr(QA), QA.stride(0), F, A, ak, ck, _lib.ptr(keep),
@@ -260,12 +263,13 @@ class _NcAggregate(torch.autograd.Function):
         nbr.build_transpose()
         l = _lib.lib()
         sd = int(seed) & 0xFFFFFFFFFFFFFFFF
-        with torch.cuda.device(dev):
+        with _lib.kernel_scope("mma_nc_aggregate_bwd_dst", dev):
             _lib.check(l.mma_nc_aggregate_bwd_dst(
                 _lib.ptr(nbr.rowptr), _lib.ptr(nbr.col), N, nbr.E, _lib.ptr(X), X.stride(0),
                 _lib.ptr(PA), PA.stride(0), _lib.ptr(QA), QA.stride(0), F, A, ak, ck, _lib.ptr(keep),
                 float(p_drop), sd, _lib.ptr(S), _lib.ptr(dOUT), _lib.ptr(gS), _lib.ptr(dXdir),
                 _lib.ptr(dPA), A * F, _lib.stream_ptr(dev)), "mma_nc_aggregate_bwd_dst")
+        with _lib.kernel_scope("mma_nc_aggregate_bwd_src", dev):
             _lib.check(l.mma_nc_aggregate_bwd_src(
                 _lib.ptr(nbr.colptr), _lib.ptr(nbr.row_t), _lib.ptr(nbr.perm_t), N, nbr.E,
                 _lib.ptr(X), X.stride(0), _lib.ptr(PA), PA.stride(0), _lib.ptr(QA), QA.stride(0), F, A, ak,

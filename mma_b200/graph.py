@@ -69,6 +69,7 @@ class Graph:
         self.n_dst = int(n_dst)
         self.n_src = int(n_src if n_src is not None else n_dst)
         self.rowptr, self.col, self.perm = csr_build(dst, src, self.n_dst)
+        self.gid, self.E_total = None, self.E      # set by the partitioner for a shard
         self._src, self._dst = src, dst
         self._t_built = False
         self.colptr = self.row_t = self.perm_t = self.csr2csc = None
@@ -111,6 +112,7 @@ class Graph:
         g.n_dst = int(dim_size)
         g.n_src = 0
         g.rowptr, g.col, g.perm = csr_build(index, None, g.n_dst)
+        g.gid, g.E_total = None, g.E
         g._t_built = False
         g.colptr = g.row_t = g.perm_t = g.csr2csc = None
         g._max_deg = None

@@ -38,6 +38,7 @@ from torch.nn import ModuleList, ReLU, Sequential
 
 from .. import functional as MF
 from ..graph import Graph, cached_graph
+from ..parallel import ShardedGraph, sharded_mmconv_aggregate
 from ..linear import Linear, reset
 from .mask_aggr import MaskAggregateLinear
 
@@ -104,6 +105,8 @@ class MMAConv(torch.nn.Module):
 
         self.lin = Linear(out_channels, out_channels)
 
+        self.comm_slices = 4                 # feature windows of the sharded comm/compute pipeline
+        self.global_max_deg = None           # sharded runs: global max in-degree (else all-reduced per call)
         self._uid = next(_UID)
         self._calls = 0
         self._inject_keep: Optional[Tensor] = None      # test hook: explicit keep-scale [E,T,F_in]
@@ -145,8 +148,8 @@ class MMAConv(torch.nn.Module):
             if not aggregator.startswith(ok):
                 raise ValueError(f'Unknown aggregator "{aggregator}".')
 
-    def _graph(self, edge_index, n: int) -> Graph:
-        if isinstance(edge_index, Graph):
+    def _graph(self, edge_index, n: int):
+        if isinstance(edge_index, (Graph, ShardedGraph)):
             return edge_index
         if not edge_index.is_cuda:
             raise RuntimeError("mma_b200.MMAConv needs CUDA tensors (no CPU fallback)")
@@ -218,6 +221,14 @@ class MMAConv(torch.nn.Module):
         if edge_attr is not None:
             e = self.edge_encoder(edge_attr)                                        # [E, F_in], :143
             R = F.linear(e, W[:, :, 2 * F_in:].reshape(T * F_in, F_in))             # [E, T*F_in]
+        if isinstance(graph, ShardedGraph):
+            # destination-range shard of one large graph: x holds this rank's rows only
+            if T != 1 or R is not None or self._inject_keep is not None:
+                raise RuntimeError("the sharded path supports towers=1 without edge features")
+            return sharded_mmconv_aggregate(P, Q, graph, F_in=F_in, aggregators=self.aggregators,
+                                            scalers=self.scalers, avg_deg=self.avg_deg, p_drop=self.dropout,
+                                            seed=self._next_seed(), n_slices=self.comm_slices,
+                                            max_deg=self.global_max_deg)
         keep = self._inject_keep
         if keep is not None:
             keep = keep.reshape(graph.E, T * F_in)

@@ -68,7 +68,7 @@ class _ScatterMinMax(torch.autograd.Function):
     @staticmethod
     def forward(ctx, src, index, n, is_max):
         E = src.shape[0]
-        out, arg = _minmax_first(src.reshape(E, -1), index, n, is_max)
+        out, arg = _minmax_first(src.reshape(E, int(math.prod(src.shape[1:]))), index, n, is_max)
         ctx.save_for_backward(arg)
         ctx.src_shape = src.shape
         shape = (n,) + tuple(src.shape[1:])
@@ -82,7 +82,7 @@ class _ScatterMinMax(torch.autograd.Function):
         E = ctx.src_shape[0]
         K = arg.shape[1]
         g = torch.zeros((E + 1, K), dtype=g_out.dtype)
-        g.scatter_(0, arg, g_out.reshape(-1, K))
+        g.scatter_(0, arg, g_out.reshape(arg.shape[0], K))
         return g[:E].reshape(ctx.src_shape), None, None, None
 
 
@@ -226,7 +226,7 @@ def mmaconv_aggregate(inputs: Tensor, index: Tensor, dim_size: int, aggregators:
 
 
 def mmaconv_message(w: MMAConvWeights, x_i: Tensor, x_j: Tensor, edge_attr: Optional[Tensor],
-                    keep: Optional[Tensor]) -> Tensor:
+                    keep: Optional[Tensor], strict: bool = True) -> Tensor:
     """mma_conv.py:138-157.  `keep` [E,T,F_in] is the dropout keep-scale tensor
     (0 or 1/(1-p)); None draws torch's own Bernoulli like F.dropout(hs, 0.5)."""
     T, F_in = w.towers, w.F_in
@@ -237,7 +237,8 @@ def mmaconv_message(w: MMAConvWeights, x_i: Tensor, x_j: Tensor, edge_attr: Opti
     else:
         h = torch.cat([x_i, x_j], dim=-1)                                            # :148
     for aggregator in w.aggregators:                                                 # :150-154
-        if not aggregator.startswith(("sum", "mean", "min", "max")):
+        # strict=False: BASELINE config 4 names 'std', which upstream's message() rejects (Q6)
+        if strict and not aggregator.startswith(("sum", "mean", "min", "max")):
             raise ValueError(f'Unknown aggregator "{aggregator}".')
     hs = []
     for t in range(T):                       # only aggregators[-1]'s mask linears survive (Q2)
@@ -254,7 +255,8 @@ def mmaconv_message(w: MMAConvWeights, x_i: Tensor, x_j: Tensor, edge_attr: Opti
 
 
 def mmaconv_forward(w: MMAConvWeights, x: Tensor, edge_index: Tensor,
-                    edge_attr: Optional[Tensor] = None, keep: Optional[Tensor] = None) -> Tensor:
+                    edge_attr: Optional[Tensor] = None, keep: Optional[Tensor] = None,
+                    strict: bool = True) -> Tensor:
     """mma_conv.py:121-136 `MMAConv.forward` through PyG's propagate
     (x_j = x[edge_index[0]], x_i = x[edge_index[1]], index = edge_index[1])."""
     T, F_in = w.towers, w.F_in
@@ -264,7 +266,7 @@ def mmaconv_forward(w: MMAConvWeights, x: Tensor, edge_index: Tensor,
         xt = x.view(-1, 1, F_in).repeat(1, T, 1)                                     # :128
     x_j = xt.index_select(0, edge_index[0])
     x_i = xt.index_select(0, edge_index[1])
-    msg = mmaconv_message(w, x_i, x_j, edge_attr, keep)
+    msg = mmaconv_message(w, x_i, x_j, edge_attr, keep, strict)
     out = mmaconv_aggregate(msg, edge_index[1], xt.size(0), w.aggregators, w.scalers, w.avg_deg)
     out = torch.cat([xt, out], dim=-1)                                               # :132
     outs = []

@@ -259,6 +259,7 @@ def test_mmaconv_api_and_errors():
     assert conv(x, ei, ea).shape == (6, 8)
     with pytest.raises(RuntimeError):
         conv.cpu()(x.cpu(), ei.cpu(), ea.cpu())                                      # no CPU fallback
+    conv = conv.cuda()
     bad = MMAConv(8, 8, ["mean", "std"], ["identity"], deg).cuda()
     with pytest.raises(ValueError, match='Unknown aggregator "std"'):                # Q6
         bad(x, ei)
