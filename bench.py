@@ -226,7 +226,7 @@ def main():
         rows = graph.rows
         graph.local.build_transpose()
     else:
-        graph = mma_b200.Graph(src, dst, N)
+        graph = mma_b200.Graph(src, dst, N, sort_rows=True)      # degree-sorted rows: scalers folded into the post GEMM
         rows = N
         _ = graph.max_deg
     del src, dst
@@ -311,7 +311,8 @@ def main():
     # ---------------- roofline of the dominant kernel ----------------
     peak, peak_kind = peaks()
     n_loc, e_loc = N // world, E // world
-    ab = algo_bytes(n_loc, e_loc, F, A, S, 2, True)
+    S_mat = 1 if world == 1 else S          # scaler blocks actually materialised by K1 (folded on 1 GPU)
+    ab = algo_bytes(n_loc, e_loc, F, A, S_mat, 2, True)
     per_kernel = {}
     for name, (cnt, mean_ms) in ktimes.items():
         per_step = cnt / args.steps
@@ -335,8 +336,10 @@ def main():
              "aggregate_only": {"ms_per_step": agg_ms, "edges_per_s": E / (agg_ms * 1e-3) if agg_ms else None,
                                 "algorithmic_GB_per_step_per_gpu": step_algo,
                                 "frac_of_hbm_peak": step_algo / (agg_ms * 1e-3) / peak if agg_ms else None,
-                                "note": "K1 fwd + bwd-dst + transpose pass only (SURVEY 8(d) formulas, "
-                                        "materialised Y with S scaler blocks); dense GEMMs excluded"},
+                                "scaler_blocks_materialised": S_mat,
+                                "note": "K1 fwd + bwd-dst + transpose pass only; bytes from the SURVEY 8(d) "
+                                        "formulas with the materialised shapes (S=1 when the scalers are "
+                                        "folded into the post GEMM); dense GEMMs excluded"},
              "dense_and_other_ms_per_step": ms - agg_ms}
 
     cpu = None

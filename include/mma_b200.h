@@ -87,10 +87,15 @@ int mma_invert_perm(const int32_t *perm, int64_t E, int32_t *inv, mma_stream_t s
  *                       edge (local original order) and the global edge count; dropout and
  *                       arg_min/arg_max then use global ids so results are shard-invariant.
  *                       NULL = the local ids are the global ids.
+ *   row_map [n_rows]  : node id of each CSR row, used to address P (and dP in the backward) when
+ *                       the CSR rows are a permutation of the nodes (degree-sorted rows for the
+ *                       bucketed post-transform); all other per-row tensors are in CSR row order.
+ *                       NULL = identity.
  *   P [n_rows, F] ld ldp | Q [n_src, F] ld ldq | R [E, F] ld ldr, ORIGINAL edge order | any may be NULL
  *   keep [E, F] ld ldk : explicit keep-scale (0 or 1/(1-p)), original edge order, or NULL
  *   p_drop, seed      : if keep == NULL and p_drop > 0: in-kernel Philox4x32-10 dropout keyed by
- *                       (seed, original edge id, column) -- identical in fwd/bwd and across shards
+ *                       (seed, original edge id, column) -- identical in fwd/bwd and across shards;
+ *                       p is quantised to round(256 p)/256 (exact for the reference's 0.5 / 0.75)
  *   aggr_kinds (host) [A], scaler_kinds (host) [S]
  *   scale_tab [4, tab_stride] : factor of scaler kind k (1..4) at clamped degree d is
  *                       scale_tab[(k-1)*tab_stride + d], d <= tab_stride-1 (built by the
@@ -106,7 +111,8 @@ int mma_invert_perm(const int32_t *perm, int64_t E, int32_t *inv, mma_stream_t s
  *                       global column).
  * ---------------------------------------------------------------------- */
 int mmconv_aggregate_fwd(const int32_t *rowptr, const int32_t *col, const int32_t *perm,
-                         const int32_t *edge_gid, int64_t E_total, int64_t n_rows, int64_t E,
+                         const int32_t *edge_gid, int64_t E_total, const int32_t *row_map,
+                         int64_t n_rows, int64_t E,
                          const float *P, int64_t ldp, const float *Q, int64_t ldq,
                          const float *R, int64_t ldr, const float *keep, int64_t ldk,
                          float p_drop, uint64_t seed,
@@ -122,7 +128,8 @@ int mmconv_aggregate_fwd(const int32_t *rowptr, const int32_t *col, const int32_
  * gslot [E] maps CSR position -> row of G (NULL = CSR position; pass `perm` to get G in
  * original edge order == dL/dR).  arg_min/arg_max/stat_* are the forward's outputs. */
 int mmconv_aggregate_bwd_dst(const int32_t *rowptr, const int32_t *col, const int32_t *perm,
-                             const int32_t *edge_gid, int64_t E_total, int64_t n_rows, int64_t E,
+                             const int32_t *edge_gid, int64_t E_total, const int32_t *row_map,
+                         int64_t n_rows, int64_t E,
                              const float *P, int64_t ldp, const float *Q, int64_t ldq,
                              const float *R, int64_t ldr, const float *keep, int64_t ldk,
                              float p_drop, uint64_t seed,

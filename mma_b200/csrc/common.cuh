@@ -126,31 +126,42 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
     return ctr;
 }
 
+// Dropout resolution is 8 bits per element: p is quantised to thr/256 (exact for the
+// reference's 0.5 and 0.75) and the keep-scale is 1/(1 - thr/256), so the estimator stays
+// unbiased.  One Philox call covers 16 consecutive columns of one edge: call (eid, c >> 4,
+// stream); column c uses byte (c & 3) of word ((c >> 2) & 3).
 struct Dropout {
-    uint32_t thr;     // drop iff random u32 < thr   (thr = round(p * 2^32), saturated)
-    float scale;      // 1 / (1 - p)
+    uint32_t thr;     // drop iff random byte < thr   (thr = round(p * 256), 0..256)
+    float scale;      // 1 / (1 - thr/256)
     uint32_t k0, k1;  // seed
 };
 
 __host__ inline Dropout make_dropout(float p, uint64_t seed) {
     Dropout d;
-    double t = (double)p * 4294967296.0;
-    d.thr = t >= 4294967295.0 ? 0xFFFFFFFFu : (t <= 0.0 ? 0u : (uint32_t)(t + 0.5));
-    d.scale = p < 1.0f ? 1.0f / (1.0f - p) : 0.0f;
+    int t = (int)(p * 256.0f + 0.5f);
+    d.thr = t < 0 ? 0u : (t > 256 ? 256u : (uint32_t)t);
+    d.scale = d.thr < 256u ? 256.0f / (float)(256u - d.thr) : 0.0f;
     d.k0 = (uint32_t)(seed & 0xFFFFFFFFull);
     d.k1 = (uint32_t)(seed >> 32);
     return d;
 }
 
-// keep-scale (0 or 1/(1-p)) for VEC consecutive columns starting at c (c % VEC == 0).
+// keep-scale of VEC consecutive columns whose random bytes start at byte `b0` of word `w`
+template <int VEC>
+__device__ __forceinline__ Vec<VEC> keep_from_word(const Dropout &d, uint32_t w, int b0) {
+    Vec<VEC> r;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) r.v[v] = (((w >> (8 * ((b0 + v) & 3))) & 0xFFu) < d.thr) ? 0.0f : d.scale;
+    return r;
+}
+
+// keep-scale (0 or 1/(1-p)) for VEC consecutive columns starting at c (c % VEC == 0, VEC in {1,2,4}).
 template <int VEC>
 __device__ __forceinline__ Vec<VEC> dropout_keep(const Dropout &d, uint32_t eid, int c, uint32_t stream_id) {
-    Vec<VEC> r;
-    const uint4 bits = philox4x32_10(make_uint4(eid, (uint32_t)(c >> 2), stream_id, 0u), make_uint2(d.k0, d.k1));
-    const uint32_t w[4] = {bits.x, bits.y, bits.z, bits.w};
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) r.v[v] = (w[(c + v) & 3] < d.thr) ? 0.0f : d.scale;
-    return r;
+    const uint4 bits = philox4x32_10(make_uint4(eid, (uint32_t)(c >> 4), stream_id, 0u), make_uint2(d.k0, d.k1));
+    const int ws = (c >> 2) & 3;
+    const uint32_t w = ws == 0 ? bits.x : (ws == 1 ? bits.y : (ws == 2 ? bits.z : bits.w));
+    return keep_from_word<VEC>(d, w, c & 3);
 }
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

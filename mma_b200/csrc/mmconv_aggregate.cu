@@ -7,25 +7,33 @@
 //   mma_conv.py:159-196  aggregate: A torch_scatter passes (+2 for var/std), degree, cumulative scalers, cats
 // and the autograd backward of all of it, without atomics.
 //
-// Mapping: a group of LANES (<=32, power of two) threads owns one destination row x one
-// chunk of LANES*VEC feature columns; each lane keeps its VEC columns' running
-// sum / sum-of-squares / (min,pos) / (max,pos) in registers and walks the row's in-edges in
-// CSR order == original edge order (the CSR is a STABLE sort by destination).  Because a
-// column is owned by one lane and scanned sequentially, "first strict improvement wins"
-// (torch_scatter CPU) and the sequential fp32 summation order are reproduced exactly, with
-// no cross-lane combine.  Loads of the gathered rows are 128-bit, coalesced along F, issued
-// U at a time before use for memory-level parallelism.
+// Mapping: a group of L (<=32, power of two) threads owns one destination row x one window of
+// L*VEC feature columns; each lane keeps its VEC columns' running sum / sum-of-squares /
+// (min,pos) / (max,pos) in registers and walks the row's in-edges in CSR order == original edge
+// order (the CSR is a STABLE sort by destination).  A column is owned by one lane and scanned
+// sequentially, so "first strict improvement wins" (torch_scatter CPU) and the sequential fp32
+// summation order are reproduced exactly, with no cross-lane combine of values.
+//
+// Per row the group cooperates on everything that is NOT per-column:
+//   * edge indices: lane s loads col[base+s] / perm[base+s] (one coalesced load per L edges) and
+//     the group broadcasts them with __shfl_sync -> no dependent uniform loads in the hot loop;
+//   * dropout bits: one Philox4x32-10 call yields 16 columns x 8 bits; for a batch of 4 edges the
+//     L lanes generate the L calls the group needs (one per lane) and exchange the words by
+//     shuffle, instead of every lane running Philox for every edge;
+//   * the gathered rows Q[src] (and R[e], keep[e]) are fetched with 128-bit loads, 4 edges
+//     (4 x 512 B per warp at F=128) in flight per group before any is consumed.
 #include "common.cuh"
 
 namespace mma {
 
+enum { DROP_NONE = 0, DROP_KEEP = 1, DROP_PHILOX_SHARED = 2, DROP_PHILOX_LANE = 3 };
+
 struct MMConvParams {
-    const int32_t *rowptr, *col, *perm, *gid;
+    const int32_t *rowptr, *col, *perm, *gid, *row_map;
     int64_t n_rows, E, E_total;
     const float *P, *Q, *R, *keep;
     int64_t ldp, ldq, ldr, ldk;
     Dropout drop;
-    int use_philox;
     int T, F_in, F, A, S;
     int akind[MMA_MAX_AGGR];
     int skind[MMA_MAX_SCALER];
@@ -51,13 +59,29 @@ struct MMConvParams {
     int64_t n_groups;
 };
 
-template <int VEC, bool MINMAX, bool SQ>
-struct Acc {
-    float sum[VEC];
-    float sq[SQ ? VEC : 1];
-    float mn[MINMAX ? VEC : 1], mx[MINMAX ? VEC : 1];
-    int amn[MINMAX ? VEC : 1], amx[MINMAX ? VEC : 1];
+struct GroupCtx {
+    int64_t row;            // CSR row handled by this group
+    int c;                  // first (global) column of this lane
+    int s;                  // lane index inside the group
+    int L;                  // group size
+    unsigned mask;          // shuffle mask of the group
+    bool live;              // lane owns real columns (ghost lanes only help with indices / RNG)
 };
+
+__device__ __forceinline__ bool locate(const MMConvParams &p, GroupCtx &g, int vec) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t group = tid >> p.lanes_log2;
+    if (group >= p.n_groups) return false;                 // whole groups leave together
+    g.L = 1 << p.lanes_log2;
+    g.s = (int)(tid & (g.L - 1));
+    const int lane = threadIdx.x & 31;
+    g.mask = (g.L == 32) ? 0xffffffffu : (((1u << g.L) - 1u) << (lane & ~(g.L - 1)));
+    g.row = group / p.chunks;
+    const int chunk = (int)(group - g.row * p.chunks);
+    g.c = p.col0 + ((chunk << p.lanes_log2) + g.s) * vec;
+    g.live = g.c < p.col0 + p.ncols;
+    return true;
+}
 
 // message of one edge for this lane's columns, in the reference's arithmetic order
 template <int VEC>
@@ -78,63 +102,84 @@ __device__ __forceinline__ Vec<VEC> message(const MMConvParams &p, const Vec<VEC
     return m;
 }
 
-// loads everything U edges need (all loads issued before any use), then consumes in order
-template <int VEC, int U, typename Consume>
-__device__ __forceinline__ void visit_edges(const MMConvParams &p, int pos, int c, const Vec<VEC> &pv,
-                                            bool need_m, bool need_eid, Consume &&consume) {
-    int j[U], eid[U], ge[U];
-    Vec<VEC> q[U], r[U], ks[U];
-    if (need_m && p.Q) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) j[u] = __ldg(p.col + pos + u);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) eid[u] = (need_eid && p.perm) ? __ldg(p.perm + pos + u) : pos + u;
-#pragma unroll
-    for (int u = 0; u < U; ++u) ge[u] = (need_eid && p.gid) ? __ldg(p.gid + eid[u]) : eid[u];   // global edge id
-    if (need_m && p.Q) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) q[u] = ld_vec_stream<VEC>(p.Q + (int64_t)j[u] * p.ldq + c);
-    }
-    if (need_m && p.R) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) r[u] = ld_vec_stream<VEC>(p.R + (int64_t)eid[u] * p.ldr + c);
-    }
-    const bool has_scale = p.keep != nullptr || p.use_philox;
-    if (p.keep) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) ks[u] = ld_vec_stream<VEC>(p.keep + (int64_t)eid[u] * p.ldk + c);
-    } else if (p.use_philox) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) ks[u] = dropout_keep<VEC>(p.drop, (uint32_t)ge[u], c, 0u);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        Vec<VEC> m{};
-        if (need_m) m = message<VEC>(p, pv, q[u], r[u], ks[u], has_scale);
-        consume(pos + u, ge[u], m, ks[u], has_scale);
-    }
+// Dropout bits are generated cooperatively by the group: for a batch of 4 edges, lane s runs
+// Philox for (edge s / (L/4), 16-column block s % (L/4)); word k of that call belongs to the lane
+// 4*block + k.  Requires VEC == 4 and L >= 4 with every group starting on a 16-column boundary.
+__device__ __forceinline__ uint4 philox_shared_generate(const MMConvParams &p, const GroupCtx &g,
+                                                        const int (&ge)[4]) {
+    const int per_edge = g.L >> 2;                      // calls (16-column blocks) per edge
+    const int u_mine = g.s / per_edge, b_mine = g.s - u_mine * per_edge;
+    const int e_mine = u_mine == 0 ? ge[0] : (u_mine == 1 ? ge[1] : (u_mine == 2 ? ge[2] : ge[3]));
+    const int c_blk = ((g.c - g.s * 4) >> 4) + b_mine;  // global 16-column block of my call
+    return philox4x32_10(make_uint4((uint32_t)e_mine, (uint32_t)c_blk, 0u, 0u), make_uint2(p.drop.k0, p.drop.k1));
 }
 
-template <int VEC, typename Consume>
-__device__ __forceinline__ void for_each_edge(const MMConvParams &p, int beg, int end, int c,
-                                              const Vec<VEC> &pv, bool need_m, bool need_eid,
-                                              Consume &&consume) {
-    constexpr int U = (VEC == 4) ? 4 : 8;
-    int pos = beg;
-    for (; pos + U <= end; pos += U) visit_edges<VEC, U>(p, pos, c, pv, need_m, need_eid, consume);
-    for (; pos < end; ++pos) visit_edges<VEC, 1>(p, pos, c, pv, need_m, need_eid, consume);
+__device__ __forceinline__ Vec<4> philox_shared_fetch(const MMConvParams &p, const GroupCtx &g, const uint4 &bits,
+                                                      int u) {
+    const int src = u * (g.L >> 2) + (g.s >> 2);
+    const uint32_t w0 = __shfl_sync(g.mask, bits.x, src, g.L);
+    const uint32_t w1 = __shfl_sync(g.mask, bits.y, src, g.L);
+    const uint32_t w2 = __shfl_sync(g.mask, bits.z, src, g.L);
+    const uint32_t w3 = __shfl_sync(g.mask, bits.w, src, g.L);
+    const int wsel = g.s & 3;
+    const uint32_t w = wsel == 0 ? w0 : (wsel == 1 ? w1 : (wsel == 2 ? w2 : w3));
+    return keep_from_word<4>(p.drop, w, 0);
 }
 
-__device__ __forceinline__ bool locate(const MMConvParams &p, int64_t &row, int &c, int vec) {
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t group = tid >> p.lanes_log2;
-    if (group >= p.n_groups) return false;
-    const int sub = (int)(tid & ((1 << p.lanes_log2) - 1));
-    row = group / p.chunks;
-    const int chunk = (int)(group - row * p.chunks);
-    c = ((chunk << p.lanes_log2) + sub) * vec;
-    return c < p.F;
+// Visits the in-edges [beg, end) of the group's row in order, 4 at a time: indices by shuffle,
+// then all gathers of the batch issued, then the edges consumed one by one.
+//   consume(pos, global_edge_id, m, ks, has_scale) is called for live lanes only.
+template <int VEC, int DROP, bool HAS_R, typename Consume>
+__device__ __forceinline__ void for_each_edge(const MMConvParams &p, const GroupCtx &g, int beg, int end,
+                                              const Vec<VEC> &pv, bool need_m, bool need_eid, Consume &&consume) {
+    constexpr bool kHasScale = DROP != DROP_NONE;
+    constexpr bool kShared = DROP == DROP_PHILOX_SHARED && VEC == 4;
+    const bool need_j = need_m && p.Q != nullptr;
+    for (int base = beg; base < end; base += g.L) {
+        const int nb = min(g.L, end - base);
+        int my_j = 0, my_e = base + g.s, my_g;
+        if (g.s < nb) {
+            if (need_j) my_j = __ldg(p.col + base + g.s);
+            if (need_eid && p.perm) my_e = __ldg(p.perm + base + g.s);
+        }
+        my_g = my_e;
+        if (g.s < nb && need_eid && p.gid) my_g = __ldg(p.gid + my_e);
+        for (int k = 0; k < nb; k += 4) {
+            int ge[4];
+            bool ok[4];
+            Vec<VEC> q[4], r[HAS_R ? 4 : 1], kp[DROP == DROP_KEEP ? 4 : 1];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                ok[u] = k + u < nb;
+                const int j = need_j ? __shfl_sync(g.mask, my_j, k + u, g.L) : 0;
+                const int e = (need_eid && p.perm) ? __shfl_sync(g.mask, my_e, k + u, g.L) : base + k + u;
+                ge[u] = (need_eid && p.gid) ? __shfl_sync(g.mask, my_g, k + u, g.L) : e;
+                if (g.live && ok[u]) {
+                    if (need_j) q[u] = ld_vec_stream<VEC>(p.Q + (int64_t)j * p.ldq + g.c);
+                    if constexpr (HAS_R) { if (need_m) r[u] = ld_vec_stream<VEC>(p.R + (int64_t)e * p.ldr + g.c); }
+                    if constexpr (DROP == DROP_KEEP) kp[u] = ld_vec_stream<VEC>(p.keep + (int64_t)e * p.ldk + g.c);
+                }
+            }
+            uint4 bits = make_uint4(0u, 0u, 0u, 0u);
+            if constexpr (kShared) bits = philox_shared_generate(p, g, ge);       // one Philox call per lane per batch
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                Vec<VEC> ks{};
+                if constexpr (kShared) {
+                    if constexpr (VEC == 4) ks = philox_shared_fetch(p, g, bits, u);   // every lane of the group takes part
+                } else if constexpr (DROP == DROP_PHILOX_LANE || DROP == DROP_PHILOX_SHARED) {
+                    ks = dropout_keep<VEC>(p.drop, (uint32_t)ge[u], g.c, 0u);
+                } else if constexpr (DROP == DROP_KEEP) {
+                    ks = kp[u];
+                }
+                if (g.live && ok[u]) {
+                    Vec<VEC> m{};
+                    if (need_m) m = message<VEC>(p, pv, q[u], r[HAS_R ? u : 0], ks, kHasScale);
+                    consume(base + k + u, ge[u], m, ks, kHasScale);
+                }
+            }
+        }
+    }
 }
 
 // CSR position -> (global) original edge id
@@ -157,38 +202,40 @@ __device__ __forceinline__ void scaler_factors(const MMConvParams &p, int degc, 
 // ----------------------------------------------------------------------------------------
 // forward
 // ----------------------------------------------------------------------------------------
-template <int VEC, bool MINMAX, bool SQ>
-__global__ void __launch_bounds__(256) mmconv_fwd_kernel(const __grid_constant__ MMConvParams p) {
-    int64_t row;
-    int c;
-    if (!locate(p, row, c, VEC)) return;
+template <int VEC, bool MINMAX, bool SQ, int DROP, bool HAS_R>
+__global__ void __launch_bounds__(256, 3) mmconv_fwd_kernel(const __grid_constant__ MMConvParams p) {
+    GroupCtx g;
+    if (!locate(p, g, VEC)) return;
+    const int64_t row = g.row;
+    const int c = g.c;
     const int beg = __ldg(p.rowptr + row), end = __ldg(p.rowptr + row + 1);
+    const int64_t prow = p.row_map ? (int64_t)__ldg(p.row_map + row) : row;
 
     Vec<VEC> pv{};
-    if (p.P) pv = ld_vec<VEC>(p.P + row * p.ldp + c);
+    if (p.P && g.live) pv = ld_vec<VEC>(p.P + prow * p.ldp + c);
 
-    Acc<VEC, MINMAX, SQ> acc;
+    float sum[VEC], sq[VEC], mn[VEC], mx[VEC];
+    int amn[VEC], amx[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
-        acc.sum[v] = 0.0f;
-        if constexpr (SQ) acc.sq[v] = 0.0f;
-        if constexpr (MINMAX) { acc.mn[v] = FLT_MAX; acc.mx[v] = -FLT_MAX; acc.amn[v] = -1; acc.amx[v] = -1; }
+        sum[v] = 0.0f; sq[v] = 0.0f; mn[v] = FLT_MAX; mx[v] = -FLT_MAX; amn[v] = -1; amx[v] = -1;
     }
 
-    const bool need_eid = p.R != nullptr || p.keep != nullptr || p.use_philox;
-    for_each_edge<VEC>(p, beg, end, c, pv, true, need_eid,
+    const bool need_eid = HAS_R || DROP != DROP_NONE;
+    for_each_edge<VEC, DROP, HAS_R>(p, g, beg, end, pv, true, need_eid,
         [&](int pos, int, const Vec<VEC> &m, const Vec<VEC> &, bool) {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
                 const float x = m.v[v];
-                acc.sum[v] = __fadd_rn(acc.sum[v], x);
-                if constexpr (SQ) acc.sq[v] = __fadd_rn(acc.sq[v], __fmul_rn(x, x));
+                sum[v] = __fadd_rn(sum[v], x);
+                if constexpr (SQ) sq[v] = __fadd_rn(sq[v], __fmul_rn(x, x));
                 if constexpr (MINMAX) {
-                    if (x < acc.mn[v]) { acc.mn[v] = x; acc.amn[v] = pos; }   // strict: first occurrence wins,
-                    if (x > acc.mx[v]) { acc.mx[v] = x; acc.amx[v] = pos; }   // -0.0 == +0.0, NaN never wins
+                    if (x < mn[v]) { mn[v] = x; amn[v] = pos; }   // strict: first occurrence wins,
+                    if (x > mx[v]) { mx[v] = x; amx[v] = pos; }   // -0.0 == +0.0, NaN never wins
                 }
             }
         });
+    if (!g.live) return;
 
     // ---- epilogue: aggregates -> cumulative scalers -> Y[row, t, (s*A+a)*F_in + f] ----
     const int cnt = end - beg;
@@ -200,9 +247,9 @@ __global__ void __launch_bounds__(256) mmconv_fwd_kernel(const __grid_constant__
     Vec<VEC> mean, var;
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
-        mean.v[v] = __fdiv_rn(acc.sum[v], degf);           // sum / count.clamp(min=1)
+        mean.v[v] = __fdiv_rn(sum[v], degf);               // sum / count.clamp(min=1)
         if constexpr (SQ) {
-            const float msq = __fdiv_rn(acc.sq[v], degf);
+            const float msq = __fdiv_rn(sq[v], degf);
             var.v[v] = __fsub_rn(msq, __fmul_rn(mean.v[v], mean.v[v]));   // mma_conv.py:170, no FMA
         } else {
             var.v[v] = 0.0f;
@@ -218,10 +265,10 @@ __global__ void __launch_bounds__(256) mmconv_fwd_kernel(const __grid_constant__
         for (int v = 0; v < VEC; ++v) {
             float x;
             switch (kind) {
-                case MMA_AGGR_SUM: x = acc.sum[v]; break;
+                case MMA_AGGR_SUM: x = sum[v]; break;
                 case MMA_AGGR_MEAN: x = mean.v[v]; break;
-                case MMA_AGGR_MIN: x = MINMAX ? (acc.amn[v] >= 0 ? acc.mn[v] : 0.0f) : 0.0f; break;
-                case MMA_AGGR_MAX: x = MINMAX ? (acc.amx[v] >= 0 ? acc.mx[v] : 0.0f) : 0.0f; break;
+                case MMA_AGGR_MIN: x = amn[v] >= 0 ? mn[v] : 0.0f; break;      // empty row -> 0
+                case MMA_AGGR_MAX: x = amx[v] >= 0 ? mx[v] : 0.0f; break;
                 case MMA_AGGR_VAR: x = var.v[v]; break;
                 default: x = sqrtf(__fadd_rn(fmaxf(var.v[v], 0.0f), 1e-5f)); break;   // STD, mma_conv.py:172
             }
@@ -235,14 +282,14 @@ __global__ void __launch_bounds__(256) mmconv_fwd_kernel(const __grid_constant__
     }
 
     if constexpr (MINMAX) {
-        int32_t amn[VEC], amx[VEC];
+        int32_t o_mn[VEC], o_mx[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-            amn[v] = acc.amn[v] < 0 ? (int32_t)p.E_total : orig_edge_id(p, acc.amn[v]);
-            amx[v] = acc.amx[v] < 0 ? (int32_t)p.E_total : orig_edge_id(p, acc.amx[v]);
+            o_mn[v] = amn[v] < 0 ? (int32_t)p.E_total : orig_edge_id(p, amn[v]);
+            o_mx[v] = amx[v] < 0 ? (int32_t)p.E_total : orig_edge_id(p, amx[v]);
         }
-        if (p.arg_min) st_vec_i32_stream<VEC>(p.arg_min + row * p.F + c, amn);
-        if (p.arg_max) st_vec_i32_stream<VEC>(p.arg_max + row * p.F + c, amx);
+        if (p.arg_min) st_vec_i32_stream<VEC>(p.arg_min + row * p.F + c, o_mn);
+        if (p.arg_max) st_vec_i32_stream<VEC>(p.arg_max + row * p.F + c, o_mx);
     }
     if (p.stat_mean) st_vec_stream<VEC>(p.stat_mean + row * p.F + c, mean);
     if constexpr (SQ) {
@@ -253,79 +300,80 @@ __global__ void __launch_bounds__(256) mmconv_fwd_kernel(const __grid_constant__
 // ----------------------------------------------------------------------------------------
 // backward, destination pass: per-edge gradient rows G and dP
 // ----------------------------------------------------------------------------------------
-template <int VEC, bool NEEDM>
-__global__ void __launch_bounds__(256) mmconv_bwd_dst_kernel(const __grid_constant__ MMConvParams p) {
-    int64_t row;
-    int c;
-    if (!locate(p, row, c, VEC)) return;
+template <int VEC, bool NEEDM, int DROP, bool HAS_R>
+__global__ void __launch_bounds__(256, 3) mmconv_bwd_dst_kernel(const __grid_constant__ MMConvParams p) {
+    GroupCtx g;
+    if (!locate(p, g, VEC)) return;
+    const int64_t row = g.row;
+    const int c = g.c;
     const int beg = __ldg(p.rowptr + row), end = __ldg(p.rowptr + row + 1);
+    const int64_t prow = p.row_map ? (int64_t)__ldg(p.row_map + row) : row;
     const int cnt = end - beg;
     const int degc = cnt > 1 ? cnt : 1;
     const float degf = (float)degc;
 
-    // cumulative scaler factors: block s of Y carries prod_{s'<=s} f_{s'}
-    float fac[MMA_MAX_SCALER];
-    scaler_factors(p, degc, fac);
-    for (int s = 1; s < p.S; ++s) fac[s] *= fac[s - 1];
-
-    Vec<VEC> mean{}, var{};
-    if constexpr (NEEDM) {
-        mean = ld_vec<VEC>(p.c_mean + row * p.F + c);
-        var = ld_vec<VEC>(p.c_var + row * p.F + c);
-    }
-
-    // fold dY over scalers and aggregators into: base (same for every in-edge), gmin / gmax
-    // (routed to the arg edge only) and alpha (coefficient of m_e, from var/std)
-    Vec<VEC> base{}, gmin{}, gmax{}, alpha{};
-    bool has_min = false, has_max = false;
-    const int t = c / p.F_in, f = c - t * p.F_in;
-    const float *dyrow = p.dY + row * p.ldy + (int64_t)t * ((int64_t)p.S * p.A * p.F_in) + f;
-    for (int a = 0; a < p.A; ++a) {
-        Vec<VEC> dz{};
-        for (int s = 0; s < p.S; ++s) {
-            const Vec<VEC> d = ld_vec_stream<VEC>(dyrow + (int64_t)(s * p.A + a) * p.F_in);
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) dz.v[v] += d.v[v] * fac[s];
-        }
-        const int kind = p.akind[a];
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            const float g = dz.v[v];
-            switch (kind) {
-                case MMA_AGGR_SUM: base.v[v] += g; break;
-                case MMA_AGGR_MEAN: base.v[v] += g / degf; break;
-                case MMA_AGGR_MIN: gmin.v[v] += g; break;
-                case MMA_AGGR_MAX: gmax.v[v] += g; break;
-                case MMA_AGGR_VAR: {            // var = E[m^2] - E[m]^2 -> d/dm_e = 2 (m_e - mean) / cnt
-                    const float k = 2.0f * g / degf;
-                    alpha.v[v] += k; base.v[v] -= k * mean.v[v];
-                } break;
-                default: {                      // std = sqrt(relu(var) + 1e-5); relu'(0) = 0
-                    if (var.v[v] > 0.0f) {
-                        const float sd = sqrtf(var.v[v] + 1e-5f);
-                        const float k = g / (sd * degf);
-                        alpha.v[v] += k; base.v[v] -= k * mean.v[v];
-                    }
-                } break;
-            }
-        }
-        has_min |= kind == MMA_AGGR_MIN;
-        has_max |= kind == MMA_AGGR_MAX;
-    }
-
+    Vec<VEC> base{}, gmin{}, gmax{}, alpha{}, pv{};
     int32_t amn[VEC], amx[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) { amn[v] = -1; amx[v] = -1; }
-    if (has_min) ld_vec_i32_as<VEC>(p.c_arg_min + row * p.F + c, amn);
-    if (has_max) ld_vec_i32_as<VEC>(p.c_arg_max + row * p.F + c, amx);
 
-    Vec<VEC> pv{};
-    if (NEEDM && p.P) pv = ld_vec<VEC>(p.P + row * p.ldp + c);
+    if (g.live) {
+        // cumulative scaler factors: block s of Y carries prod_{s'<=s} f_{s'}
+        float fac[MMA_MAX_SCALER];
+        scaler_factors(p, degc, fac);
+        for (int s = 1; s < p.S; ++s) fac[s] *= fac[s - 1];
+
+        Vec<VEC> mean{}, var{};
+        if constexpr (NEEDM) {
+            mean = ld_vec<VEC>(p.c_mean + row * p.F + c);
+            var = ld_vec<VEC>(p.c_var + row * p.F + c);
+        }
+        // fold dY over scalers and aggregators into: base (same for every in-edge), gmin / gmax
+        // (routed to the arg edge only) and alpha (coefficient of m_e, from var/std)
+        bool has_min = false, has_max = false;
+        const int t = c / p.F_in, f = c - t * p.F_in;
+        const float *dyrow = p.dY + row * p.ldy + (int64_t)t * ((int64_t)p.S * p.A * p.F_in) + f;
+        for (int a = 0; a < p.A; ++a) {
+            Vec<VEC> dz{};
+            for (int s = 0; s < p.S; ++s) {
+                const Vec<VEC> d = ld_vec_stream<VEC>(dyrow + (int64_t)(s * p.A + a) * p.F_in);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) dz.v[v] += d.v[v] * fac[s];
+            }
+            const int kind = p.akind[a];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const float gg = dz.v[v];
+                switch (kind) {
+                    case MMA_AGGR_SUM: base.v[v] += gg; break;
+                    case MMA_AGGR_MEAN: base.v[v] += gg / degf; break;
+                    case MMA_AGGR_MIN: gmin.v[v] += gg; break;
+                    case MMA_AGGR_MAX: gmax.v[v] += gg; break;
+                    case MMA_AGGR_VAR: {        // var = E[m^2] - E[m]^2 -> d/dm_e = 2 (m_e - mean) / cnt
+                        const float k = 2.0f * gg / degf;
+                        alpha.v[v] += k; base.v[v] -= k * mean.v[v];
+                    } break;
+                    default: {                  // std = sqrt(relu(var) + 1e-5); relu'(0) = 0
+                        if (var.v[v] > 0.0f) {
+                            const float sd = sqrtf(var.v[v] + 1e-5f);
+                            const float k = gg / (sd * degf);
+                            alpha.v[v] += k; base.v[v] -= k * mean.v[v];
+                        }
+                    } break;
+                }
+            }
+            has_min |= kind == MMA_AGGR_MIN;
+            has_max |= kind == MMA_AGGR_MAX;
+        }
+        if (has_min) ld_vec_i32_as<VEC>(p.c_arg_min + row * p.F + c, amn);
+        if (has_max) ld_vec_i32_as<VEC>(p.c_arg_max + row * p.F + c, amx);
+        if (NEEDM && p.P) pv = ld_vec<VEC>(p.P + prow * p.ldp + c);
+    }
 
     Vec<VEC> dp{};
-    for_each_edge<VEC>(p, beg, end, c, pv, NEEDM, true,
+    for_each_edge<VEC, DROP, (HAS_R && NEEDM)>(p, g, beg, end, pv, NEEDM, true,
         [&](int pos, int eid, const Vec<VEC> &m, const Vec<VEC> &ks, bool has_scale) {
-            Vec<VEC> g;
+            Vec<VEC> gr;
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
                 float x = base.v[v];
@@ -333,22 +381,23 @@ __global__ void __launch_bounds__(256) mmconv_bwd_dst_kernel(const __grid_consta
                 if (eid == amx[v]) x += gmax.v[v];
                 if constexpr (NEEDM) x += alpha.v[v] * m.v[v];
                 if (has_scale) x *= ks.v[v];           // dL/dm_pre = dL/dm * keepscale
-                g.v[v] = x;
+                gr.v[v] = x;
                 dp.v[v] += x;
             }
             if (p.G) {
                 const int64_t slot = p.gslot ? (int64_t)__ldg(p.gslot + pos) : (int64_t)pos;
-                st_vec<VEC>(p.G + slot * p.ldg + c, g);
+                st_vec<VEC>(p.G + slot * p.ldg + c, gr);
             }
         });
-    if (p.dP) st_vec_stream<VEC>(p.dP + row * p.lddp + c, dp);
+    if (p.dP && g.live) st_vec_stream<VEC>(p.dP + prow * p.lddp + c, dp);
 }
 
 // ----------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------
 static int fill_params(MMConvParams &p, const int32_t *rowptr, const int32_t *col, const int32_t *perm,
-                       const int32_t *gid, int64_t E_total, int64_t n_rows, int64_t E, const float *P, int64_t ldp, const float *Q, int64_t ldq,
+                       const int32_t *gid, int64_t E_total, const int32_t *row_map, int64_t n_rows, int64_t E,
+                       const float *P, int64_t ldp, const float *Q, int64_t ldq,
                        const float *R, int64_t ldr, const float *keep, int64_t ldk, float p_drop, uint64_t seed,
                        int T, int F_in, int A, const int32_t *aggr_kinds, int S, const int32_t *scaler_kinds,
                        const float *scale_tab, int64_t tab_stride) {
@@ -360,11 +409,10 @@ static int fill_params(MMConvParams &p, const int32_t *rowptr, const int32_t *co
     if (Q && !col && E > 0) return MMA_ERR_INVALID;
     if (p_drop < 0.0f || p_drop > 1.0f) return MMA_ERR_INVALID;
     p = MMConvParams{};
-    p.rowptr = rowptr; p.col = col; p.perm = perm; p.gid = gid; p.n_rows = n_rows; p.E = E;
+    p.rowptr = rowptr; p.col = col; p.perm = perm; p.gid = gid; p.row_map = row_map; p.n_rows = n_rows; p.E = E;
     p.E_total = gid ? E_total : E;
     p.P = P; p.Q = Q; p.R = R; p.keep = keep; p.ldp = ldp; p.ldq = ldq; p.ldr = ldr; p.ldk = ldk;
     p.drop = make_dropout(p_drop, seed);
-    p.use_philox = (keep == nullptr && p_drop > 0.0f) ? 1 : 0;
     p.T = T; p.F_in = F_in; p.F = T * F_in; p.A = A; p.S = S;
     bool any_scaled = false;
     for (int a = 0; a < A; ++a) {
@@ -387,7 +435,7 @@ static int choose_geometry(MMConvParams &p, bool vec4_ok, int col0, int ncols) {
     vec4_ok = vec4_ok && (col0 % 4 == 0) && (ncols % 4 == 0);
     const int vec = vec4_ok ? 4 : 1;
     const int per_row = (ncols + vec - 1) / vec;     // lanes needed for one row of the window
-    int lg = 0;
+    int lg = 2;                                      // groups of >= 4 lanes (shared index loads / RNG)
     while ((1 << lg) < per_row && lg < 5) ++lg;
     p.lanes_log2 = lg;
     const int lanes = 1 << lg;
@@ -398,12 +446,29 @@ static int choose_geometry(MMConvParams &p, bool vec4_ok, int col0, int ncols) {
 
 static inline bool ok4(const void *ptr, int64_t ld) { return ptr == nullptr || (aligned16(ptr) && (ld % 4) == 0); }
 
+static int drop_mode(const MMConvParams &p, const float *keep, float p_drop, int vec) {
+    if (keep) return DROP_KEEP;
+    if (p_drop <= 0.0f) return DROP_NONE;
+    // the shared generator needs each group's first column on a 16-column block boundary
+    const bool blocks_aligned = (p.col0 % 16 == 0) && (((1 << p.lanes_log2) * 4) % 16 == 0);
+    return (vec == 4 && blocks_aligned) ? DROP_PHILOX_SHARED : DROP_PHILOX_LANE;
+}
+
 }  // namespace mma
 
 using namespace mma;
 
+#define MMA_FOR_DROP(MACRO, ...)                                                \
+    switch (drop) {                                                             \
+        case DROP_NONE: MACRO(__VA_ARGS__, DROP_NONE); break;                   \
+        case DROP_KEEP: MACRO(__VA_ARGS__, DROP_KEEP); break;                   \
+        case DROP_PHILOX_SHARED: MACRO(__VA_ARGS__, DROP_PHILOX_SHARED); break; \
+        default: MACRO(__VA_ARGS__, DROP_PHILOX_LANE); break;                   \
+    }
+
 extern "C" int mmconv_aggregate_fwd(const int32_t *rowptr, const int32_t *col, const int32_t *perm,
-                                    const int32_t *edge_gid, int64_t E_total, int64_t n_rows, int64_t E, const float *P, int64_t ldp,
+                                    const int32_t *edge_gid, int64_t E_total, const int32_t *row_map,
+                                    int64_t n_rows, int64_t E, const float *P, int64_t ldp,
                                     const float *Q, int64_t ldq, const float *R, int64_t ldr,
                                     const float *keep, int64_t ldk, float p_drop, uint64_t seed,
                                     int T, int F_in, int A, const int32_t *aggr_kinds, int S,
@@ -412,8 +477,8 @@ extern "C" int mmconv_aggregate_fwd(const int32_t *rowptr, const int32_t *col, c
                                     float *stat_mean, float *stat_var, int col0, int ncols,
                                     mma_stream_t stream) {
     MMConvParams p;
-    int rc = fill_params(p, rowptr, col, perm, edge_gid, E_total, n_rows, E, P, ldp, Q, ldq, R, ldr, keep, ldk, p_drop, seed,
-                         T, F_in, A, aggr_kinds, S, scaler_kinds, scale_tab, tab_stride);
+    int rc = fill_params(p, rowptr, col, perm, edge_gid, E_total, row_map, n_rows, E, P, ldp, Q, ldq, R, ldr,
+                         keep, ldk, p_drop, seed, T, F_in, A, aggr_kinds, S, scaler_kinds, scale_tab, tab_stride);
     if (rc != MMA_OK) return rc;
     if (!Y) return MMA_ERR_INVALID;
     p.Y = Y; p.ldy = ldy; p.arg_min = arg_min; p.arg_max = arg_max; p.stat_mean = stat_mean; p.stat_var = stat_var;
@@ -427,30 +492,42 @@ extern "C" int mmconv_aggregate_fwd(const int32_t *rowptr, const int32_t *col, c
                     ok4(Y, ldy) && ok4(arg_min, 4) && ok4(arg_max, 4) && ok4(stat_mean, 4) && ok4(stat_var, 4);
     if (col0 < 0 || col0 + (ncols > 0 ? ncols : 0) > p.F) return MMA_ERR_INVALID;
     const int vec = choose_geometry(p, v4, col0, ncols);
+    const int drop = drop_mode(p, keep, p_drop, vec);
     const int64_t threads = p.n_groups << p.lanes_log2;
     const int block = 256;
     const int64_t grid = (threads + block - 1) / block;
     if (grid > INT32_MAX) return MMA_ERR_UNSUPPORTED;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define LAUNCH_FWD(V, MM, SQ) mmconv_fwd_kernel<V, MM, SQ><<<(unsigned)grid, block, 0, st>>>(p)
+#define FWD_V4(MM, SQ, D)                                                                   \
+    do {                                                                                    \
+        if (R) mmconv_fwd_kernel<4, MM, SQ, D, true><<<(unsigned)grid, block, 0, st>>>(p);   \
+        else mmconv_fwd_kernel<4, MM, SQ, D, false><<<(unsigned)grid, block, 0, st>>>(p);    \
+    } while (0)
+    // the scalar path (widths that are not a multiple of 4) is not specialised on the aggregator set
+#define FWD_V1(D)                                                                             \
+    do {                                                                                      \
+        if (R) mmconv_fwd_kernel<1, true, true, D, true><<<(unsigned)grid, block, 0, st>>>(p); \
+        else mmconv_fwd_kernel<1, true, true, D, false><<<(unsigned)grid, block, 0, st>>>(p);  \
+    } while (0)
     if (vec == 4) {
-        if (minmax && sq) LAUNCH_FWD(4, true, true);
-        else if (minmax) LAUNCH_FWD(4, true, false);
-        else if (sq) LAUNCH_FWD(4, false, true);
-        else LAUNCH_FWD(4, false, false);
+        if (minmax && sq) { MMA_FOR_DROP(FWD_V4, true, true) }
+        else if (minmax) { MMA_FOR_DROP(FWD_V4, true, false) }
+        else if (sq) { MMA_FOR_DROP(FWD_V4, false, true) }
+        else { MMA_FOR_DROP(FWD_V4, false, false) }
     } else {
-        if (minmax && sq) LAUNCH_FWD(1, true, true);
-        else if (minmax) LAUNCH_FWD(1, true, false);
-        else if (sq) LAUNCH_FWD(1, false, true);
-        else LAUNCH_FWD(1, false, false);
+        switch (drop) {
+            case DROP_NONE: FWD_V1(DROP_NONE); break;
+            case DROP_KEEP: FWD_V1(DROP_KEEP); break;
+            default: FWD_V1(DROP_PHILOX_LANE); break;
+        }
     }
-#undef LAUNCH_FWD
     MMA_LAUNCH_CHECK();
     return MMA_OK;
 }
 
 extern "C" int mmconv_aggregate_bwd_dst(const int32_t *rowptr, const int32_t *col, const int32_t *perm,
-                                        const int32_t *edge_gid, int64_t E_total, int64_t n_rows, int64_t E, const float *P, int64_t ldp,
+                                        const int32_t *edge_gid, int64_t E_total, const int32_t *row_map,
+                                        int64_t n_rows, int64_t E, const float *P, int64_t ldp,
                                         const float *Q, int64_t ldq, const float *R, int64_t ldr,
                                         const float *keep, int64_t ldk, float p_drop, uint64_t seed,
                                         int T, int F_in, int A, const int32_t *aggr_kinds, int S,
@@ -460,8 +537,8 @@ extern "C" int mmconv_aggregate_bwd_dst(const int32_t *rowptr, const int32_t *co
                                         const int32_t *gslot, float *G, int64_t ldg, float *dP, int64_t lddp,
                                         int col0, int ncols, mma_stream_t stream) {
     MMConvParams p;
-    int rc = fill_params(p, rowptr, col, perm, edge_gid, E_total, n_rows, E, P, ldp, Q, ldq, R, ldr, keep, ldk, p_drop, seed,
-                         T, F_in, A, aggr_kinds, S, scaler_kinds, scale_tab, tab_stride);
+    int rc = fill_params(p, rowptr, col, perm, edge_gid, E_total, row_map, n_rows, E, P, ldp, Q, ldq, R, ldr,
+                         keep, ldk, p_drop, seed, T, F_in, A, aggr_kinds, S, scaler_kinds, scale_tab, tab_stride);
     if (rc != MMA_OK) return rc;
     if (!dY || (!G && !dP && E > 0)) return MMA_ERR_INVALID;
     bool needm = false;
@@ -479,17 +556,30 @@ extern "C" int mmconv_aggregate_bwd_dst(const int32_t *rowptr, const int32_t *co
                     ok4(stat_var, 4) && ok4(G, ldg) && ok4(dP, lddp);
     if (col0 < 0 || col0 + (ncols > 0 ? ncols : 0) > p.F) return MMA_ERR_INVALID;
     const int vec = choose_geometry(p, v4, col0, ncols);
+    const int drop = drop_mode(p, keep, p_drop, vec);
     const int64_t threads = p.n_groups << p.lanes_log2;
     const int block = 256;
     const int64_t grid = (threads + block - 1) / block;
     if (grid > INT32_MAX) return MMA_ERR_UNSUPPORTED;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define BWD_V4(NM, D)                                                                        \
+    do {                                                                                     \
+        if (R && NM) mmconv_bwd_dst_kernel<4, NM, D, true><<<(unsigned)grid, block, 0, st>>>(p); \
+        else mmconv_bwd_dst_kernel<4, NM, D, false><<<(unsigned)grid, block, 0, st>>>(p);     \
+    } while (0)
+#define BWD_V1(D)                                                                                 \
+    do {                                                                                          \
+        if (needm) mmconv_bwd_dst_kernel<1, true, D, true><<<(unsigned)grid, block, 0, st>>>(p);   \
+        else mmconv_bwd_dst_kernel<1, false, D, false><<<(unsigned)grid, block, 0, st>>>(p);       \
+    } while (0)
     if (vec == 4) {
-        if (needm) mmconv_bwd_dst_kernel<4, true><<<(unsigned)grid, block, 0, st>>>(p);
-        else mmconv_bwd_dst_kernel<4, false><<<(unsigned)grid, block, 0, st>>>(p);
+        if (needm) { MMA_FOR_DROP(BWD_V4, true) } else { MMA_FOR_DROP(BWD_V4, false) }
     } else {
-        if (needm) mmconv_bwd_dst_kernel<1, true><<<(unsigned)grid, block, 0, st>>>(p);
-        else mmconv_bwd_dst_kernel<1, false><<<(unsigned)grid, block, 0, st>>>(p);
+        switch (drop) {
+            case DROP_NONE: BWD_V1(DROP_NONE); break;
+            case DROP_KEEP: BWD_V1(DROP_KEEP); break;
+            default: BWD_V1(DROP_PHILOX_LANE); break;
+        }
     }
     MMA_LAUNCH_CHECK();
     return MMA_OK;

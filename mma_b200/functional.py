@@ -74,7 +74,7 @@ class _MMConvAggregate(torch.autograd.Function):
         with _lib.kernel_scope("mmconv_aggregate_fwd", dev):
             _lib.check(_lib.lib().mmconv_aggregate_fwd(
                 _lib.ptr(graph.rowptr), _lib.ptr(graph.col), _lib.ptr(perm), _lib.ptr(graph.gid), graph.E_total,
-                n, graph.E,
+                _lib.ptr(graph.row_map), n, graph.E,
                 _lib.ptr(P), _ld(P), _lib.ptr(Q), _ld(Q), _lib.ptr(R), _ld(R), _lib.ptr(keep), _ld(keep),
                 float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, T, F_in, A, ak, S, sk,
                 _lib.ptr(tab), 0 if tab is None else tab.shape[1],
@@ -119,7 +119,7 @@ class _MMConvAggregate(torch.autograd.Function):
         with _lib.kernel_scope("mmconv_aggregate_bwd_dst", dev):
             _lib.check(l.mmconv_aggregate_bwd_dst(
                 _lib.ptr(graph.rowptr), _lib.ptr(graph.col), _lib.ptr(graph.perm), _lib.ptr(graph.gid),
-                graph.E_total, n, E,
+                graph.E_total, _lib.ptr(graph.row_map), n, E,
                 _lib.ptr(P), _ld(P), _lib.ptr(Q), _ld(Q), _lib.ptr(R), _ld(R), _lib.ptr(keep), _ld(keep),
                 float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, T, F_in, A, ak, S, sk,
                 _lib.ptr(tab), 0 if tab is None else tab.shape[1],
@@ -286,3 +286,123 @@ def nc_aggregate(X: Tensor, PA: Tensor, QA: Tensor, nbr, acts: Sequence[int], co
         raise _lib.MMAError("more than 8 aggregators in one call")
     return _NcAggregate.apply(X, PA, QA, nbr, tuple(int(a) for a in acts), tuple(int(c) for c in combs),
                               keep, float(p_drop), int(seed))
+
+
+# ------------------------------------------------------------------------------------------
+# post-transform with the degree scalers folded into the weights
+# ------------------------------------------------------------------------------------------
+def cumulative_scale_factors(scalers: Sequence[str], avg_deg: Dict[str, float], degrees: Sequence[int]) -> Tensor:
+    """[S, len(degrees)] fp32: block s of MMAConv.aggregate's output is the raw aggregate times
+    prod_{s'<=s} f_{s'}(deg) (cumulative re-assignment, graph_regression/mma_conv.py:181-195, Q4);
+    evaluated on the CPU with the reference's expressions."""
+    deg = torch.tensor(list(degrees), dtype=torch.float32).clamp_(1)
+    cur = torch.ones_like(deg)
+    rows = []
+    for sc in scalers:
+        if sc == "identity":
+            pass
+        elif sc == "amplification":
+            cur = cur * (torch.log(deg + 1) / avg_deg["log"])
+        elif sc == "attenuation":
+            cur = cur * (avg_deg["log"] / torch.log(deg + 1))
+        elif sc == "linear":
+            cur = cur * (deg / avg_deg["lin"])
+        elif sc == "inverse_linear":
+            cur = cur * (avg_deg["lin"] / deg)
+        else:
+            raise ValueError(f'Unknown scaler "{sc}".')
+        rows.append(cur)
+    return torch.stack(rows)
+
+
+class _ScaledPost(torch.autograd.Function):
+    """H[r] = sum_s cum_s(deg_r) * (Z[r] @ W_s^T)  for degree-sorted rows r.
+
+    The reference materialises Y = cat_s(Z * cum_s) [N, S*A*F] and multiplies by the post weight
+    (mma_conv.py:181-196, 132-133).  Rows of equal degree share their S factors, so for a
+    contiguous range of equal-degree rows this is ONE GEMM with the effective weight
+    W_eff(d) = sum_s cum_s(d) W_s: S times fewer flops and no [N, S*A*F] tensor.  Degrees
+    with fewer than `min_rows` nodes (the tail of a skewed distribution) are handled together by
+    the literal formula."""
+
+    @staticmethod
+    def forward(ctx, Z, Wy, cum, ranges, tail_idx, tail_bucket, S: int):
+        n, K = Z.shape
+        Fo = Wy.shape[0]
+        Ws = Wy.view(Fo, S, K)
+        H = torch.empty((n, Fo), dtype=Z.dtype, device=Z.device)
+        big = [b for b, _, _ in ranges]
+        Weff = None
+        if big:
+            cb = cum[:, big]                                                      # [S, B]
+            Weff = torch.einsum("sb,osk->bok", cb, Ws).contiguous()               # [B, Fo, K]
+            for i, (_, lo, hi) in enumerate(ranges):
+                torch.mm(Z[lo:hi], Weff[i].t(), out=H[lo:hi])
+        if tail_idx is not None and tail_idx.numel() > 0:
+            Zt = Z.index_select(0, tail_idx)
+            ct = cum[:, tail_bucket].t()                                          # [nt, S]
+            Yt = (Zt.unsqueeze(1) * ct.unsqueeze(2)).reshape(Zt.shape[0], S * K)
+            H.index_copy_(0, tail_idx, Yt @ Wy.t())
+        ctx.save_for_backward(Z, Wy, cum, Weff, tail_idx, tail_bucket)
+        ctx.ranges, ctx.S = ranges, S
+        return H
+
+    @staticmethod
+    def backward(ctx, dH):
+        Z, Wy, cum, Weff, tail_idx, tail_bucket = ctx.saved_tensors
+        ranges, S = ctx.ranges, ctx.S
+        n, K = Z.shape
+        Fo = Wy.shape[0]
+        dH = dH.contiguous()
+        dZ = torch.empty_like(Z) if ctx.needs_input_grad[0] else None
+        dWy = None
+        if ranges:
+            dWeff = torch.empty_like(Weff) if ctx.needs_input_grad[1] else None
+            for i, (_, lo, hi) in enumerate(ranges):
+                if dZ is not None:
+                    torch.mm(dH[lo:hi], Weff[i], out=dZ[lo:hi])
+                if dWeff is not None:
+                    torch.mm(dH[lo:hi].t(), Z[lo:hi], out=dWeff[i])
+            if dWeff is not None:
+                cb = cum[:, [b for b, _, _ in ranges]]
+                dWy = torch.einsum("sb,bok->osk", cb, dWeff).reshape(Fo, S * K)
+        if tail_idx is not None and tail_idx.numel() > 0:
+            Zt = Z.index_select(0, tail_idx)
+            ct = cum[:, tail_bucket].t()
+            dHt = dH.index_select(0, tail_idx)
+            if dZ is not None:
+                dYt = (dHt @ Wy).view(-1, S, K)
+                dZ.index_copy_(0, tail_idx, (dYt * ct.unsqueeze(2)).sum(dim=1))
+            if ctx.needs_input_grad[1]:
+                Yt = (Zt.unsqueeze(1) * ct.unsqueeze(2)).reshape(Zt.shape[0], S * K)
+                g = dHt.t() @ Yt
+                dWy = g if dWy is None else dWy + g
+        return dZ, dWy, None, None, None, None, None
+
+
+def scaled_post(Z: Tensor, Wy: Tensor, graph: Graph, scalers: Sequence[str], avg_deg: Dict[str, float],
+                min_rows: int = 512) -> Tensor:
+    """Z [n, A*F] (rows in graph.row_map order, raw aggregates) -> H [n, F_out] (same row order)
+    == cat_s(Z * cum_s(deg)) @ Wy^T.  `graph` must have degree-sorted rows (graph.buckets)."""
+    if graph.buckets is None:
+        raise RuntimeError("scaled_post needs a Graph built with sort_rows=True")
+    S = len(scalers)
+    key = (tuple(scalers), float(avg_deg["log"]), float(avg_deg["lin"]), int(min_rows), str(Z.device))
+    plans = graph.__dict__.setdefault("_post_plans", {})
+    plan = plans.get(key)
+    if plan is None:
+        degs = [d for d, _, _ in graph.buckets]
+        cum = cumulative_scale_factors(scalers, avg_deg, degs).to(Z.device)       # [S, n_buckets]
+        ranges, tail_rows, tail_b = [], [], []
+        for b, (d, lo, hi) in enumerate(graph.buckets):
+            if hi - lo >= min_rows:
+                ranges.append((b, lo, hi))
+            else:
+                tail_rows.append(torch.arange(lo, hi, dtype=torch.int64))
+                tail_b.append(torch.full((hi - lo,), b, dtype=torch.int64))
+        tail_idx = torch.cat(tail_rows).to(Z.device) if tail_rows else None
+        tail_bucket = torch.cat(tail_b).to(Z.device) if tail_b else None
+        plan = (cum, tuple(ranges), tail_idx, tail_bucket)
+        plans[key] = plan
+    cum, ranges, tail_idx, tail_bucket = plan
+    return _ScaledPost.apply(Z, Wy, cum, ranges, tail_idx, tail_bucket, S)

@@ -62,12 +62,32 @@ class Graph:
     """
 
     def __init__(self, src: Tensor, dst: Tensor, n_dst: int, n_src: Optional[int] = None,
-                 need_transpose: bool = True):
+                 need_transpose: bool = True, sort_rows: bool = False):
         dev = _lib.require_cuda(src, dst)
         self.device = dev
         self.E = int(dst.numel())
         self.n_dst = int(n_dst)
         self.n_src = int(n_src if n_src is not None else n_dst)
+        self.row_map = None                        # node id of each CSR row (None = identity)
+        self.row_rank = None                       # CSR row of each node (inverse of row_map)
+        self.buckets = None                        # [(degree, row_lo, row_hi)] when rows are degree-sorted
+        if sort_rows and self.n_dst > 0:
+            # CSR rows in order of decreasing in-degree: nodes of equal degree become contiguous row
+            # ranges (the post-transform then needs ONE effective weight per range, see
+            # functional.scaled_post) and long rows are scheduled first.  In-row edge order is
+            # untouched (stable sort by the relabelled destination).
+            deg = torch.bincount(dst, minlength=self.n_dst)
+            order = torch.argsort(deg, descending=True, stable=True)
+            rank = torch.empty_like(order)
+            rank[order] = torch.arange(self.n_dst, device=dev)
+            vals, counts = torch.unique_consecutive(deg.index_select(0, order), return_counts=True)
+            hi = torch.cumsum(counts, 0)
+            vals, counts, hi = vals.tolist(), counts.tolist(), hi.tolist()
+            self.buckets = [(int(d), int(h - c), int(h)) for d, c, h in zip(vals, counts, hi)]
+            self._max_deg_hint = int(vals[0]) if vals else 0
+            self.row_map = order.to(torch.int32).contiguous()
+            self.row_rank = rank
+            dst = rank.index_select(0, dst)
         self.rowptr, self.col, self.perm = csr_build(dst, src, self.n_dst)
         self.gid, self.E_total = None, self.E      # set by the partitioner for a shard
         self._src, self._dst = src, dst
@@ -100,8 +120,9 @@ class Graph:
         return self._max_deg
 
     @staticmethod
-    def from_edge_index(edge_index: Tensor, num_nodes: int, need_transpose: bool = True) -> "Graph":
-        return Graph(edge_index[0], edge_index[1], num_nodes, num_nodes, need_transpose)
+    def from_edge_index(edge_index: Tensor, num_nodes: int, need_transpose: bool = True,
+                        sort_rows: bool = False) -> "Graph":
+        return Graph(edge_index[0], edge_index[1], num_nodes, num_nodes, need_transpose, sort_rows)
 
     @staticmethod
     def from_index(index: Tensor, dim_size: int) -> "Graph":
@@ -113,6 +134,7 @@ class Graph:
         g.n_src = 0
         g.rowptr, g.col, g.perm = csr_build(index, None, g.n_dst)
         g.gid, g.E_total = None, g.E
+        g.row_map = g.row_rank = g.buckets = None
         g._t_built = False
         g.colptr = g.row_t = g.perm_t = g.csr2csc = None
         g._max_deg = None
@@ -124,15 +146,15 @@ _CACHE: "OrderedDict[tuple, Graph]" = OrderedDict()
 _CACHE_SIZE = 16
 
 
-def cached_graph(edge_index: Tensor, num_nodes: int) -> Graph:
+def cached_graph(edge_index: Tensor, num_nodes: int, sort_rows: bool = False) -> Graph:
     """Graph for an `edge_index` tensor, cached on (storage pointer, shape, version, N).
     A tensor mutated in place bumps `_version` and is rebuilt; pass a `Graph`
     explicitly to the layers to bypass the cache altogether."""
     key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes),
-           str(edge_index.device))
+           str(edge_index.device), bool(sort_rows))
     g = _CACHE.get(key)
     if g is None:
-        g = Graph.from_edge_index(edge_index, num_nodes)
+        g = Graph.from_edge_index(edge_index, num_nodes, sort_rows=sort_rows)
         _CACHE[key] = g
         while len(_CACHE) > _CACHE_SIZE:
             _CACHE.popitem(last=False)

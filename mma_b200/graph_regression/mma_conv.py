@@ -105,6 +105,8 @@ class MMAConv(torch.nn.Module):
 
         self.lin = Linear(out_channels, out_channels)
 
+        self.fold_scalers = True             # towers == 1: fold the scalers into the post weight (see _forward_folded)
+        self.fold_min_rows = 512             # degree ranges smaller than this use the literal formula
         self.comm_slices = 4                 # feature windows of the sharded comm/compute pipeline
         self.global_max_deg = None           # sharded runs: global max in-degree (else all-reduced per call)
         self._uid = next(_UID)
@@ -148,12 +150,12 @@ class MMAConv(torch.nn.Module):
             if not aggregator.startswith(ok):
                 raise ValueError(f'Unknown aggregator "{aggregator}".')
 
-    def _graph(self, edge_index, n: int):
+    def _graph(self, edge_index, n: int, sort_rows: bool = False):
         if isinstance(edge_index, (Graph, ShardedGraph)):
             return edge_index
         if not edge_index.is_cuda:
             raise RuntimeError("mma_b200.MMAConv needs CUDA tensors (no CPU fallback)")
-        return cached_graph(edge_index, n)
+        return cached_graph(edge_index, n, sort_rows=sort_rows)
 
     # ------------------------------------------------------------------ forward
     def forward(self, x: Tensor, edge_index, edge_attr: Optional[Tensor] = None) -> Tensor:
@@ -163,6 +165,11 @@ class MMAConv(torch.nn.Module):
         else:
             xt = x.view(-1, 1, F_in)            # towers share x; the repeat (:128) is never materialised
         n = xt.size(0)
+        if T == 1 and self.fold_scalers and self.pre_layers == 1 and self.mask != "no_linear":
+            graph = self._graph(edge_index, n, sort_rows=True)
+            if isinstance(graph, Graph) and graph.buckets is not None:
+                return self._forward_folded(xt[:, 0], graph, edge_attr)
+            edge_index = graph
         out = self.propagate(edge_index, x=xt, edge_attr=edge_attr, size=None)      # [N,T,S*A*F_in]
 
         # post_nns over cat([x, out]) (:132-133) without the cat: split the first Linear's weight
@@ -194,18 +201,11 @@ class MMAConv(torch.nn.Module):
         out = outs[0] if T == 1 else torch.cat(outs, dim=1)
         return self.lin(out)
 
-    def propagate(self, edge_index, size=None, **kwargs):
-        """PyG's propagate for this layer (x_j = x[edge_index[0]], x_i = x[edge_index[1]],
-        segments = edge_index[1]) -- fused when the mask linear is separable."""
-        xt: Tensor = kwargs["x"]
-        edge_attr: Optional[Tensor] = kwargs.get("edge_attr")
-        n = xt.size(0)
-        graph = self._graph(edge_index, n)
+    def _mask_projections(self, xt: Tensor, edge_attr: Optional[Tensor]):
+        """P = X W_i^T + b, Q = X W_j^T (node-level) and R = enc(e) W_e^T (edge-level): the mask
+        linear over cat([x_i, x_j, e]) of mma_conv.py:146-152 / mask_aggr.py:68, split by block."""
         T, F_in = self.towers, self.F_in
-        self._check_names()
-        if self.pre_layers != 1 or self.mask == "no_linear":
-            return self._propagate_materialised(graph, edge_index, xt, edge_attr)
-
+        n = xt.size(0)
         live = [seq[0].live() for seq in self.pre_nns[self.aggregators[-1]]]        # Q2
         W = torch.stack([m.weight for m in live])                                   # [T, F_in, (2|3)F_in]
         b = torch.stack([m.bias for m in live]).reshape(1, T * F_in)
@@ -221,6 +221,46 @@ class MMAConv(torch.nn.Module):
         if edge_attr is not None:
             e = self.edge_encoder(edge_attr)                                        # [E, F_in], :143
             R = F.linear(e, W[:, :, 2 * F_in:].reshape(T * F_in, F_in))             # [E, T*F_in]
+        return P, Q, R
+
+    def _forward_folded(self, x: Tensor, graph: Graph, edge_attr: Optional[Tensor]) -> Tensor:
+        """towers == 1 fast path: K1 emits the RAW aggregates Z [N, A*F_in] in degree-sorted row
+        order; the S cumulative scalers are folded into the post weight per degree range
+        (functional.scaled_post) -- the [N, S*A*F_in] tensor of mma_conv.py:196 and the cat with x
+        (:132) are never materialised."""
+        F_in, n = self.F_in, x.size(0)
+        self._check_names()
+        for s_ in self.scalers:
+            if s_ not in ("identity", "amplification", "attenuation", "linear", "inverse_linear"):
+                raise ValueError(f'Unknown scaler "{s_}".')
+        P, Q, R = self._mask_projections(x.view(n, 1, F_in), edge_attr)
+        keep = self._inject_keep
+        if keep is not None:
+            keep = keep.reshape(graph.E, F_in)
+        Z = MF.mmconv_aggregate(P, Q, R, graph, towers=1, F_in=F_in, aggregators=self.aggregators,
+                                scalers=["identity"], keep=keep, p_drop=self.dropout, seed=self._next_seed())
+        first = self.post_nns[0][0]
+        W = first.weight                                                             # [F_out, (S*A+1)*F_in]
+        Hs = MF.scaled_post(Z.view(n, -1), W[:, F_in:], graph, self.scalers, self.avg_deg,
+                            min_rows=self.fold_min_rows)
+        h = Hs.index_select(0, graph.row_rank) + F.linear(x, W[:, :F_in], first.bias)
+        for m in list(self.post_nns[0])[1:]:
+            h = m(h)
+        return self.lin(h)
+
+    def propagate(self, edge_index, size=None, **kwargs):
+        """PyG's propagate for this layer (x_j = x[edge_index[0]], x_i = x[edge_index[1]],
+        segments = edge_index[1]) -- fused when the mask linear is separable."""
+        xt: Tensor = kwargs["x"]
+        edge_attr: Optional[Tensor] = kwargs.get("edge_attr")
+        n = xt.size(0)
+        graph = self._graph(edge_index, n)
+        T, F_in = self.towers, self.F_in
+        self._check_names()
+        if self.pre_layers != 1 or self.mask == "no_linear":
+            return self._propagate_materialised(graph, edge_index, xt, edge_attr)
+
+        P, Q, R = self._mask_projections(xt, edge_attr)
         if isinstance(graph, ShardedGraph):
             # destination-range shard of one large graph: x holds this rank's rows only
             if T != 1 or R is not None or self._inject_keep is not None:

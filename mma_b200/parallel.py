@@ -198,7 +198,7 @@ class _ShardedAggregate(torch.autograd.Function):
             q_base = Qk.data_ptr() - 4 * s_.start       # virtual base: column c of the window's row j
             with _lib.kernel_scope("mmconv_aggregate_fwd", dev):
                 _lib.check(_lib.lib().mmconv_aggregate_fwd(
-                    _lib.ptr(g.rowptr), _lib.ptr(g.col), _lib.ptr(g.perm), _lib.ptr(g.gid), g.E_total, n, g.E,
+                    _lib.ptr(g.rowptr), _lib.ptr(g.col), _lib.ptr(g.perm), _lib.ptr(g.gid), g.E_total, None, n, g.E,
                     _lib.ptr(P), P.stride(0), q_base, w, None, 0, None, 0,
                     float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, 1, F_in, A, ak, S, sk,
                     _lib.ptr(tab), 0 if tab is None else tab.shape[1], _lib.ptr(Y), Y.stride(0),
@@ -242,7 +242,7 @@ class _ShardedAggregate(torch.autograd.Function):
                 q_base = Qk.data_ptr() - 4 * s_.start
             with _lib.kernel_scope("mmconv_aggregate_bwd_dst", dev):
                 _lib.check(l.mmconv_aggregate_bwd_dst(
-                    _lib.ptr(g.rowptr), _lib.ptr(g.col), _lib.ptr(g.perm), _lib.ptr(g.gid), g.E_total, n, E,
+                    _lib.ptr(g.rowptr), _lib.ptr(g.col), _lib.ptr(g.perm), _lib.ptr(g.gid), g.E_total, None, n, E,
                     _lib.ptr(P), P.stride(0), q_base, w, None, 0, None, 0,
                     float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, 1, F_in, A, ak, S, sk,
                     _lib.ptr(tab), 0 if tab is None else tab.shape[1], _lib.ptr(dY), dY.stride(0),

@@ -220,13 +220,19 @@ def _load_weights(conv, w):
         conv.lin.weight.copy_(w["lin"][0]); conv.lin.bias.copy_(w["lin"][1])
 
 
-@pytest.mark.parametrize("name", ["mmaconv_zinc.pt", "mmaconv_t1_noedge.pt", "mmaconv_divide_prepost2.pt"])
-def test_mmaconv_layer_vs_reference_golden(name):
-    """Whole drop-in layer (fwd + all gradients) against the verbatim reference's outputs."""
+@pytest.mark.parametrize("name,fold", [("mmaconv_zinc.pt", None), ("mmaconv_t1_noedge.pt", 512),
+                                       ("mmaconv_t1_noedge.pt", 2), ("mmaconv_t1_noedge.pt", 0),
+                                       ("mmaconv_divide_prepost2.pt", None)])
+def test_mmaconv_layer_vs_reference_golden(name, fold):
+    """Whole drop-in layer (fwd + all gradients) against the verbatim reference's outputs.
+    fold: towers == 1 only -- 0 = materialised scaler blocks, k = scalers folded into the post weight
+    with degree ranges of >= k rows as one GEMM each (512: everything through the literal tail path)."""
     from mma_b200 import MMAConv
     from oracle import restate
     gd = load_golden(name)
     conv = MMAConv(deg=gd["deg_hist"], **gd["ctor"]).cuda()
+    if fold is not None:
+        conv.fold_scalers, conv.fold_min_rows = fold > 0, max(fold, 1)
     _load_weights(conv, gd["weights"])
     assert conv.avg_deg == gd["weights"]["avg_deg"]
     x = gd["x"].cuda().requires_grad_()
@@ -277,3 +283,47 @@ def test_mmaconv_api_and_errors():
     b = conv(x, ei, ea)
     torch.manual_seed(3); conv._calls = 0; c = conv(x, ei, ea)
     assert not torch.equal(a, b) and torch.equal(a, c)
+
+
+@pytest.mark.parametrize("edge_dim", [None, 6])
+def test_folded_post_transform_vs_oracle(edge_dim):
+    """towers == 1 fast path (raw aggregates in degree-sorted rows + per-degree effective post
+    weight) on a graph with many distinct degrees, vs the op-for-op oracle of the reference."""
+    from mma_b200 import MMAConv
+    from oracle import restate
+    n, E, Fd = 3000, 40000, 32
+    g = torch.Generator().manual_seed(3)
+    src = torch.randint(0, n, (E,), generator=g)
+    dst = (torch.rand(E, generator=g) ** 2 * (n - 5)).long()          # skewed in-degrees, a few empty rows
+    ei = torch.stack([src, dst])
+    hist = restate.degree_histogram(ei, n)
+    torch.manual_seed(0)
+    aggr, scal = ["mean", "sum", "min", "max"], ["identity", "amplification", "attenuation", "linear", "inverse_linear"]
+    conv = MMAConv(Fd, Fd, aggr, scal, hist, edge_dim=edge_dim, towers=1).cuda()
+    conv.fold_min_rows = 16
+    x = torch.randn(n, Fd, generator=g)
+    ea = torch.randn(E, edge_dim, generator=g) if edge_dim else None
+    keep = (torch.rand(E, 1, Fd, generator=g) < 0.5).float() * 2
+    conv._inject_keep = keep.cuda()
+    xg = x.cuda().requires_grad_()
+    eag = None if ea is None else ea.cuda().requires_grad_()
+    y = conv(xg, ei.cuda(), eag)
+    w = restate.weights_from_module(conv)
+    for t in w.tensors():
+        t.requires_grad_()
+    xr = x.clone().requires_grad_()
+    ear = None if ea is None else ea.clone().requires_grad_()
+    yr = restate.mmaconv_forward(w, xr, ei, ear, keep)
+    close(y, yr, what="folded y")
+    gy = torch.randn(n, Fd, generator=g)
+    params = restate.weights_from_module(conv, clone=False).tensors()
+    ins = [xg] + ([eag] if ea is not None else [])
+    insr = [xr] + ([ear] if ea is not None else [])
+    got = torch.autograd.grad(y, ins + params, gy.cuda())
+    ref = torch.autograd.grad(yr, insr + w.tensors(), gy)
+    for i, (a, b) in enumerate(zip(got, ref)):
+        close(a, b, what=f"folded grad {i}")
+    # unfolded path gives the same numbers to fp32 rounding
+    conv.fold_scalers = False
+    y2 = conv(xg, ei.cuda(), eag)
+    close(y2, yr, what="unfolded y")
