@@ -41,19 +41,20 @@ __device__ __forceinline__ Vec<VEC> ld_vec(const float *p) {
     return r;
 }
 
-// gather of a feature row that is touched ~deg times over the whole kernel but
-// far apart in time: keep it out of L1 (no_allocate) so index lines stay resident.
+// gather of a feature row that is touched ~deg times over the whole kernel but far apart in
+// time: ld.global.cg (L2 only) keeps it out of L1 so index lines stay resident.  An intrinsic, not
+// inline asm, so the compiler can predicate it instead of branching around it.
 template <int VEC>
 __device__ __forceinline__ Vec<VEC> ld_vec_stream(const float *p) {
     Vec<VEC> r;
     if constexpr (VEC == 4) {
-        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                     : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "l"(p));
+        const float4 t = __ldcg(reinterpret_cast<const float4 *>(p));
+        r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
     } else if constexpr (VEC == 2) {
-        asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];"
-                     : "=f"(r.v[0]), "=f"(r.v[1]) : "l"(p));
+        const float2 t = __ldcg(reinterpret_cast<const float2 *>(p));
+        r.v[0] = t.x; r.v[1] = t.y;
     } else {
-        asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r.v[0]) : "l"(p));
+        r.v[0] = __ldcg(p);
     }
     return r;
 }

@@ -27,6 +27,8 @@
 namespace mma {
 
 enum { DROP_NONE = 0, DROP_KEEP = 1, DROP_PHILOX_SHARED = 2, DROP_PHILOX_LANE = 3 };
+// which terms make up the message (compile time, so the hot loop carries no null checks)
+enum { MSG_PQ = 0, MSG_PQR = 1, MSG_R = 2, MSG_GENERIC = 3 };
 
 struct MMConvParams {
     const int32_t *rowptr, *col, *perm, *gid, *row_map;
@@ -64,39 +66,51 @@ struct GroupCtx {
     int c;                  // first (global) column of this lane
     int s;                  // lane index inside the group
     int L;                  // group size
-    unsigned mask;          // shuffle mask of the group
-    bool live;              // lane owns real columns (ghost lanes only help with indices / RNG)
+    bool live;              // lane owns real columns of a real row (ghost lanes only help with
+                            // index loads, shuffles and the RNG: every warp runs warp-uniform loops
+                            // so all shuffles use the constant full mask)
+    int beg, deg, wdeg;     // row start, row length, max row length over the warp
 };
 
-__device__ __forceinline__ bool locate(const MMConvParams &p, GroupCtx &g, int vec) {
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ void locate(const MMConvParams &p, GroupCtx &g, int vec) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t group = tid >> p.lanes_log2;
-    if (group >= p.n_groups) return false;                 // whole groups leave together
+    const bool real = group < p.n_groups;
     g.L = 1 << p.lanes_log2;
     g.s = (int)(tid & (g.L - 1));
-    const int lane = threadIdx.x & 31;
-    g.mask = (g.L == 32) ? 0xffffffffu : (((1u << g.L) - 1u) << (lane & ~(g.L - 1)));
-    g.row = group / p.chunks;
-    const int chunk = (int)(group - g.row * p.chunks);
+    g.row = real ? group / p.chunks : 0;
+    const int chunk = real ? (int)(group - g.row * p.chunks) : 0;
     g.c = p.col0 + ((chunk << p.lanes_log2) + g.s) * vec;
-    g.live = g.c < p.col0 + p.ncols;
-    return true;
+    g.live = real && g.c < p.col0 + p.ncols;
+    g.beg = 0; g.deg = 0;
+    if (real) {
+        g.beg = __ldg(p.rowptr + g.row);
+        g.deg = __ldg(p.rowptr + g.row + 1) - g.beg;
+    }
+    g.wdeg = __reduce_max_sync(kFull, g.deg);
 }
 
 // message of one edge for this lane's columns, in the reference's arithmetic order
-template <int VEC>
+// (before the keep-scale): ((P[dst] + Q[src]) + R[e])
+template <int VEC, int MSG>
 __device__ __forceinline__ Vec<VEC> message(const MMConvParams &p, const Vec<VEC> &pv, const Vec<VEC> &q,
-                                            const Vec<VEC> &r, const Vec<VEC> &ks, bool has_scale) {
+                                            const Vec<VEC> &r) {
     Vec<VEC> m;
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
         float x;
-        if (p.P && p.Q) x = __fadd_rn(pv.v[v], q.v[v]);
-        else if (p.P) x = pv.v[v];
-        else if (p.Q) x = q.v[v];
-        else x = r.v[v];
-        if (p.R && (p.P || p.Q)) x = __fadd_rn(x, r.v[v]);
-        if (has_scale) x = __fmul_rn(x, ks.v[v]);     // x * 0 keeps the sign of x, like F.dropout
+        if constexpr (MSG == MSG_PQ) x = __fadd_rn(pv.v[v], q.v[v]);
+        else if constexpr (MSG == MSG_PQR) x = __fadd_rn(__fadd_rn(pv.v[v], q.v[v]), r.v[v]);
+        else if constexpr (MSG == MSG_R) x = r.v[v];
+        else {
+            if (p.P && p.Q) x = __fadd_rn(pv.v[v], q.v[v]);
+            else if (p.P) x = pv.v[v];
+            else if (p.Q) x = q.v[v];
+            else x = r.v[v];
+            if (p.R && (p.P || p.Q)) x = __fadd_rn(x, r.v[v]);
+        }
         m.v[v] = x;
     }
     return m;
@@ -117,47 +131,61 @@ __device__ __forceinline__ uint4 philox_shared_generate(const MMConvParams &p, c
 __device__ __forceinline__ Vec<4> philox_shared_fetch(const MMConvParams &p, const GroupCtx &g, const uint4 &bits,
                                                       int u) {
     const int src = u * (g.L >> 2) + (g.s >> 2);
-    const uint32_t w0 = __shfl_sync(g.mask, bits.x, src, g.L);
-    const uint32_t w1 = __shfl_sync(g.mask, bits.y, src, g.L);
-    const uint32_t w2 = __shfl_sync(g.mask, bits.z, src, g.L);
-    const uint32_t w3 = __shfl_sync(g.mask, bits.w, src, g.L);
+    const uint32_t w0 = __shfl_sync(kFull, bits.x, src, g.L);
+    const uint32_t w1 = __shfl_sync(kFull, bits.y, src, g.L);
+    const uint32_t w2 = __shfl_sync(kFull, bits.z, src, g.L);
+    const uint32_t w3 = __shfl_sync(kFull, bits.w, src, g.L);
     const int wsel = g.s & 3;
     const uint32_t w = wsel == 0 ? w0 : (wsel == 1 ? w1 : (wsel == 2 ? w2 : w3));
     return keep_from_word<4>(p.drop, w, 0);
 }
 
-// Visits the in-edges [beg, end) of the group's row in order, 4 at a time: indices by shuffle,
-// then all gathers of the batch issued, then the edges consumed one by one.
-//   consume(pos, global_edge_id, m, ks, has_scale) is called for live lanes only.
-template <int VEC, int DROP, bool HAS_R, typename Consume>
-__device__ __forceinline__ void for_each_edge(const MMConvParams &p, const GroupCtx &g, int beg, int end,
-                                              const Vec<VEC> &pv, bool need_m, bool need_eid, Consume &&consume) {
-    constexpr bool kHasScale = DROP != DROP_NONE;
+// Visits the in-edges of the group's row in order, 4 at a time: indices by shuffle, then all
+// gathers of the batch issued, then the edges consumed one by one.  Loops run to the warp-wide
+// maximum row length (rows are degree-sorted, so this costs nothing in practice); `valid` masks
+// the edges beyond the group's own row.
+//   consume(valid, pos, global_edge_id, m, ks): m is the message BEFORE the keep-scale.
+template <int VEC, int MSG, int DROP, bool NEED_M, bool NEED_EID, typename Consume>
+__device__ __forceinline__ void for_each_edge(const MMConvParams &p, const GroupCtx &g, const Vec<VEC> &pv,
+                                              Consume &&consume) {
     constexpr bool kShared = DROP == DROP_PHILOX_SHARED && VEC == 4;
-    const bool need_j = need_m && p.Q != nullptr;
-    for (int base = beg; base < end; base += g.L) {
-        const int nb = min(g.L, end - base);
-        int my_j = 0, my_e = base + g.s, my_g;
-        if (g.s < nb) {
-            if (need_j) my_j = __ldg(p.col + base + g.s);
-            if (need_eid && p.perm) my_e = __ldg(p.perm + base + g.s);
+    constexpr bool kNeedQ = NEED_M && MSG != MSG_R;
+    constexpr bool kNeedR = NEED_M && MSG != MSG_PQ;
+    constexpr bool kNeedE = NEED_EID || DROP != DROP_NONE || kNeedR;
+    const bool has_q = kNeedQ && (MSG != MSG_GENERIC || p.Q != nullptr);
+    const bool has_r = kNeedR && (MSG != MSG_GENERIC || p.R != nullptr);
+    const char *Qc = reinterpret_cast<const char *>(p.Q + g.c);
+    const char *Rc = reinterpret_cast<const char *>(p.R + g.c);
+    const char *Kc = reinterpret_cast<const char *>(p.keep + g.c);
+    const uint32_t ldq_b = (uint32_t)p.ldq * 4u, ldr_b = (uint32_t)p.ldr * 4u, ldk_b = (uint32_t)p.ldk * 4u;
+    for (int base = 0; base < g.wdeg; base += g.L) {
+        int my_j = 0, my_e = g.beg + base + g.s, my_g;
+        const bool mine = base + g.s < g.deg;
+        if (mine) {
+            if (has_q) my_j = __ldg(p.col + g.beg + base + g.s);
+            if (kNeedE && p.perm) my_e = __ldg(p.perm + g.beg + base + g.s);
         }
         my_g = my_e;
-        if (g.s < nb && need_eid && p.gid) my_g = __ldg(p.gid + my_e);
-        for (int k = 0; k < nb; k += 4) {
+        if (kNeedE && p.gid && mine) my_g = __ldg(p.gid + my_e);
+        const int nbw = min(g.L, g.wdeg - base);
+        for (int k = 0; k < nbw; k += 4) {
             int ge[4];
             bool ok[4];
-            Vec<VEC> q[4], r[HAS_R ? 4 : 1], kp[DROP == DROP_KEEP ? 4 : 1];
+            Vec<VEC> q[kNeedQ ? 4 : 1], r[kNeedR ? 4 : 1], kp[DROP == DROP_KEEP ? 4 : 1];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                ok[u] = k + u < nb;
-                const int j = need_j ? __shfl_sync(g.mask, my_j, k + u, g.L) : 0;
-                const int e = (need_eid && p.perm) ? __shfl_sync(g.mask, my_e, k + u, g.L) : base + k + u;
-                ge[u] = (need_eid && p.gid) ? __shfl_sync(g.mask, my_g, k + u, g.L) : e;
-                if (g.live && ok[u]) {
-                    if (need_j) q[u] = ld_vec_stream<VEC>(p.Q + (int64_t)j * p.ldq + g.c);
-                    if constexpr (HAS_R) { if (need_m) r[u] = ld_vec_stream<VEC>(p.R + (int64_t)e * p.ldr + g.c); }
-                    if constexpr (DROP == DROP_KEEP) kp[u] = ld_vec_stream<VEC>(p.keep + (int64_t)e * p.ldk + g.c);
+                ok[u] = g.live && (base + k + u < g.deg);
+                const int j = has_q ? __shfl_sync(kFull, my_j, k + u, g.L) : 0;
+                const int e = kNeedE ? __shfl_sync(kFull, my_e, k + u, g.L) : 0;
+                ge[u] = (kNeedE && p.gid) ? __shfl_sync(kFull, my_g, k + u, g.L) : e;
+                if constexpr (kNeedQ) {
+                    if (ok[u] && has_q) q[u] = ld_vec_stream<VEC>(reinterpret_cast<const float *>(Qc + (uint64_t)(uint32_t)j * ldq_b));
+                }
+                if constexpr (kNeedR) {
+                    if (ok[u] && has_r) r[u] = ld_vec_stream<VEC>(reinterpret_cast<const float *>(Rc + (uint64_t)(uint32_t)e * ldr_b));
+                }
+                if constexpr (DROP == DROP_KEEP) {
+                    if (ok[u]) kp[u] = ld_vec_stream<VEC>(reinterpret_cast<const float *>(Kc + (uint64_t)(uint32_t)e * ldk_b));
                 }
             }
             uint4 bits = make_uint4(0u, 0u, 0u, 0u);
@@ -166,17 +194,15 @@ __device__ __forceinline__ void for_each_edge(const MMConvParams &p, const Group
             for (int u = 0; u < 4; ++u) {
                 Vec<VEC> ks{};
                 if constexpr (kShared) {
-                    if constexpr (VEC == 4) ks = philox_shared_fetch(p, g, bits, u);   // every lane of the group takes part
+                    if constexpr (VEC == 4) ks = philox_shared_fetch(p, g, bits, u);   // every lane of the warp takes part
                 } else if constexpr (DROP == DROP_PHILOX_LANE || DROP == DROP_PHILOX_SHARED) {
                     ks = dropout_keep<VEC>(p.drop, (uint32_t)ge[u], g.c, 0u);
                 } else if constexpr (DROP == DROP_KEEP) {
                     ks = kp[u];
                 }
-                if (g.live && ok[u]) {
-                    Vec<VEC> m{};
-                    if (need_m) m = message<VEC>(p, pv, q[u], r[HAS_R ? u : 0], ks, kHasScale);
-                    consume(base + k + u, ge[u], m, ks, kHasScale);
-                }
+                Vec<VEC> m{};
+                if constexpr (NEED_M) m = message<VEC, MSG>(p, pv, q[kNeedQ ? u : 0], r[kNeedR ? u : 0]);
+                consume(ok[u], g.beg + base + k + u, ge[u], m, ks);
             }
         }
     }
@@ -202,17 +228,18 @@ __device__ __forceinline__ void scaler_factors(const MMConvParams &p, int degc, 
 // ----------------------------------------------------------------------------------------
 // forward
 // ----------------------------------------------------------------------------------------
-template <int VEC, bool MINMAX, bool SQ, int DROP, bool HAS_R>
+template <int VEC, int MSG, int DROP, bool MINMAX, bool SQ>
 __global__ void __launch_bounds__(256, 3) mmconv_fwd_kernel(const __grid_constant__ MMConvParams p) {
     GroupCtx g;
-    if (!locate(p, g, VEC)) return;
+    locate(p, g, VEC);
     const int64_t row = g.row;
     const int c = g.c;
-    const int beg = __ldg(p.rowptr + row), end = __ldg(p.rowptr + row + 1);
-    const int64_t prow = p.row_map ? (int64_t)__ldg(p.row_map + row) : row;
 
     Vec<VEC> pv{};
-    if (p.P && g.live) pv = ld_vec<VEC>(p.P + prow * p.ldp + c);
+    if (MSG != MSG_R && g.live && p.P) {
+        const int64_t prow = p.row_map ? (int64_t)__ldg(p.row_map + row) : row;
+        pv = ld_vec<VEC>(p.P + prow * p.ldp + c);
+    }
 
     float sum[VEC], sq[VEC], mn[VEC], mx[VEC];
     int amn[VEC], amx[VEC];
@@ -221,59 +248,50 @@ __global__ void __launch_bounds__(256, 3) mmconv_fwd_kernel(const __grid_constan
         sum[v] = 0.0f; sq[v] = 0.0f; mn[v] = FLT_MAX; mx[v] = -FLT_MAX; amn[v] = -1; amx[v] = -1;
     }
 
-    const bool need_eid = HAS_R || DROP != DROP_NONE;
-    for_each_edge<VEC, DROP, HAS_R>(p, g, beg, end, pv, true, need_eid,
-        [&](int pos, int, const Vec<VEC> &m, const Vec<VEC> &, bool) {
+    for_each_edge<VEC, MSG, DROP, true, false>(p, g, pv,
+        [&](bool ok, int pos, int, const Vec<VEC> &m, const Vec<VEC> &ks) {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
-                const float x = m.v[v];
-                sum[v] = __fadd_rn(sum[v], x);
-                if constexpr (SQ) sq[v] = __fadd_rn(sq[v], __fmul_rn(x, x));
+                float x = m.v[v];
+                if constexpr (DROP != DROP_NONE) x = __fmul_rn(x, ks.v[v]);   // x * 0 keeps the sign of x, like F.dropout
+                if (ok) sum[v] = __fadd_rn(sum[v], x);
+                if constexpr (SQ) { if (ok) sq[v] = __fadd_rn(sq[v], __fmul_rn(x, x)); }
                 if constexpr (MINMAX) {
-                    if (x < mn[v]) { mn[v] = x; amn[v] = pos; }   // strict: first occurrence wins,
-                    if (x > mx[v]) { mx[v] = x; amx[v] = pos; }   // -0.0 == +0.0, NaN never wins
+                    if (ok && x < mn[v]) { mn[v] = x; amn[v] = pos; }   // strict: first occurrence wins,
+                    if (ok && x > mx[v]) { mx[v] = x; amx[v] = pos; }   // -0.0 == +0.0, NaN never wins
                 }
             }
         });
     if (!g.live) return;
 
     // ---- epilogue: aggregates -> cumulative scalers -> Y[row, t, (s*A+a)*F_in + f] ----
-    const int cnt = end - beg;
-    const int degc = cnt > 1 ? cnt : 1;                    // deg.clamp_(1), mma_conv.py:179
+    const int degc = g.deg > 1 ? g.deg : 1;                // deg.clamp_(1), mma_conv.py:179
     const float degf = (float)degc;
     float fac[MMA_MAX_SCALER];
     scaler_factors(p, degc, fac);
 
-    Vec<VEC> mean, var;
+    Vec<VEC> mean, var, sd, vmin, vmax, vsum;
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
+        vsum.v[v] = sum[v];
         mean.v[v] = __fdiv_rn(sum[v], degf);               // sum / count.clamp(min=1)
         if constexpr (SQ) {
             const float msq = __fdiv_rn(sq[v], degf);
-            var.v[v] = __fsub_rn(msq, __fmul_rn(mean.v[v], mean.v[v]));   // mma_conv.py:170, no FMA
+            var.v[v] = __fsub_rn(msq, __fmul_rn(mean.v[v], mean.v[v]));         // mma_conv.py:170, no FMA
+            sd.v[v] = sqrtf(__fadd_rn(fmaxf(var.v[v], 0.0f), 1e-5f));           // mma_conv.py:172
         } else {
-            var.v[v] = 0.0f;
+            var.v[v] = 0.0f; sd.v[v] = 0.0f;
         }
+        vmin.v[v] = (MINMAX && amn[v] >= 0) ? mn[v] : 0.0f;                      // empty row -> 0
+        vmax.v[v] = (MINMAX && amx[v] >= 0) ? mx[v] : 0.0f;
     }
 
     const int t = c / p.F_in, f = c - t * p.F_in;
     float *yrow = p.Y + row * p.ldy + (int64_t)t * ((int64_t)p.S * p.A * p.F_in) + f;
     for (int a = 0; a < p.A; ++a) {
-        Vec<VEC> val;
         const int kind = p.akind[a];
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            float x;
-            switch (kind) {
-                case MMA_AGGR_SUM: x = sum[v]; break;
-                case MMA_AGGR_MEAN: x = mean.v[v]; break;
-                case MMA_AGGR_MIN: x = amn[v] >= 0 ? mn[v] : 0.0f; break;      // empty row -> 0
-                case MMA_AGGR_MAX: x = amx[v] >= 0 ? mx[v] : 0.0f; break;
-                case MMA_AGGR_VAR: x = var.v[v]; break;
-                default: x = sqrtf(__fadd_rn(fmaxf(var.v[v], 0.0f), 1e-5f)); break;   // STD, mma_conv.py:172
-            }
-            val.v[v] = x;
-        }
+        Vec<VEC> val = kind == MMA_AGGR_SUM ? vsum : kind == MMA_AGGR_MEAN ? mean : kind == MMA_AGGR_MIN ? vmin
+                     : kind == MMA_AGGR_MAX ? vmax : kind == MMA_AGGR_VAR ? var : sd;
         for (int s = 0; s < p.S; ++s) {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) val.v[v] = __fmul_rn(val.v[v], fac[s]);     // cumulative (Q4)
@@ -300,16 +318,14 @@ __global__ void __launch_bounds__(256, 3) mmconv_fwd_kernel(const __grid_constan
 // ----------------------------------------------------------------------------------------
 // backward, destination pass: per-edge gradient rows G and dP
 // ----------------------------------------------------------------------------------------
-template <int VEC, bool NEEDM, int DROP, bool HAS_R>
+template <int VEC, int MSG, int DROP, bool NEEDM>
 __global__ void __launch_bounds__(256, 3) mmconv_bwd_dst_kernel(const __grid_constant__ MMConvParams p) {
     GroupCtx g;
-    if (!locate(p, g, VEC)) return;
+    locate(p, g, VEC);
     const int64_t row = g.row;
     const int c = g.c;
-    const int beg = __ldg(p.rowptr + row), end = __ldg(p.rowptr + row + 1);
-    const int64_t prow = p.row_map ? (int64_t)__ldg(p.row_map + row) : row;
-    const int cnt = end - beg;
-    const int degc = cnt > 1 ? cnt : 1;
+    const int64_t prow = (g.live && p.row_map) ? (int64_t)__ldg(p.row_map + row) : row;
+    const int degc = g.deg > 1 ? g.deg : 1;
     const float degf = (float)degc;
 
     Vec<VEC> base{}, gmin{}, gmax{}, alpha{}, pv{};
@@ -344,22 +360,16 @@ __global__ void __launch_bounds__(256, 3) mmconv_bwd_dst_kernel(const __grid_con
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
                 const float gg = dz.v[v];
-                switch (kind) {
-                    case MMA_AGGR_SUM: base.v[v] += gg; break;
-                    case MMA_AGGR_MEAN: base.v[v] += gg / degf; break;
-                    case MMA_AGGR_MIN: gmin.v[v] += gg; break;
-                    case MMA_AGGR_MAX: gmax.v[v] += gg; break;
-                    case MMA_AGGR_VAR: {        // var = E[m^2] - E[m]^2 -> d/dm_e = 2 (m_e - mean) / cnt
-                        const float k = 2.0f * gg / degf;
-                        alpha.v[v] += k; base.v[v] -= k * mean.v[v];
-                    } break;
-                    default: {                  // std = sqrt(relu(var) + 1e-5); relu'(0) = 0
-                        if (var.v[v] > 0.0f) {
-                            const float sd = sqrtf(var.v[v] + 1e-5f);
-                            const float k = gg / (sd * degf);
-                            alpha.v[v] += k; base.v[v] -= k * mean.v[v];
-                        }
-                    } break;
+                if (kind == MMA_AGGR_SUM) base.v[v] += gg;
+                else if (kind == MMA_AGGR_MEAN) base.v[v] += gg / degf;
+                else if (kind == MMA_AGGR_MIN) gmin.v[v] += gg;
+                else if (kind == MMA_AGGR_MAX) gmax.v[v] += gg;
+                else if (kind == MMA_AGGR_VAR) {    // var = E[m^2] - E[m]^2 -> d/dm_e = 2 (m_e - mean) / cnt
+                    const float k = 2.0f * gg / degf;
+                    alpha.v[v] += k; base.v[v] -= k * mean.v[v];
+                } else if (var.v[v] > 0.0f) {       // std = sqrt(relu(var) + 1e-5); relu'(0) = 0
+                    const float k = gg / (sqrtf(var.v[v] + 1e-5f) * degf);
+                    alpha.v[v] += k; base.v[v] -= k * mean.v[v];
                 }
             }
             has_min |= kind == MMA_AGGR_MIN;
@@ -367,26 +377,31 @@ __global__ void __launch_bounds__(256, 3) mmconv_bwd_dst_kernel(const __grid_con
         }
         if (has_min) ld_vec_i32_as<VEC>(p.c_arg_min + row * p.F + c, amn);
         if (has_max) ld_vec_i32_as<VEC>(p.c_arg_max + row * p.F + c, amx);
-        if (NEEDM && p.P) pv = ld_vec<VEC>(p.P + prow * p.ldp + c);
+        if (NEEDM && MSG != MSG_R && p.P) pv = ld_vec<VEC>(p.P + prow * p.ldp + c);
     }
 
     Vec<VEC> dp{};
-    for_each_edge<VEC, DROP, (HAS_R && NEEDM)>(p, g, beg, end, pv, NEEDM, true,
-        [&](int pos, int eid, const Vec<VEC> &m, const Vec<VEC> &ks, bool has_scale) {
+    float *Gc = p.G ? p.G + c : nullptr;
+    for_each_edge<VEC, MSG, DROP, NEEDM, true>(p, g, pv,
+        [&](bool ok, int pos, int eid, const Vec<VEC> &m, const Vec<VEC> &ks) {
             Vec<VEC> gr;
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
                 float x = base.v[v];
                 if (eid == amn[v]) x += gmin.v[v];
                 if (eid == amx[v]) x += gmax.v[v];
-                if constexpr (NEEDM) x += alpha.v[v] * m.v[v];
-                if (has_scale) x *= ks.v[v];           // dL/dm_pre = dL/dm * keepscale
+                if constexpr (NEEDM) {
+                    float mm = m.v[v];
+                    if constexpr (DROP != DROP_NONE) mm = __fmul_rn(mm, ks.v[v]);
+                    x += alpha.v[v] * mm;
+                }
+                if constexpr (DROP != DROP_NONE) x *= ks.v[v];     // dL/dm_pre = dL/dm * keepscale
                 gr.v[v] = x;
-                dp.v[v] += x;
+                if (ok) dp.v[v] += x;
             }
-            if (p.G) {
+            if (ok && Gc) {
                 const int64_t slot = p.gslot ? (int64_t)__ldg(p.gslot + pos) : (int64_t)pos;
-                st_vec<VEC>(p.G + slot * p.ldg + c, gr);
+                st_vec<VEC>(Gc + slot * p.ldg, gr);
             }
         });
     if (p.dP && g.live) st_vec_stream<VEC>(p.dP + prow * p.lddp + c, dp);
@@ -458,13 +473,12 @@ static int drop_mode(const MMConvParams &p, const float *keep, float p_drop, int
 
 using namespace mma;
 
-#define MMA_FOR_DROP(MACRO, ...)                                                \
-    switch (drop) {                                                             \
-        case DROP_NONE: MACRO(__VA_ARGS__, DROP_NONE); break;                   \
-        case DROP_KEEP: MACRO(__VA_ARGS__, DROP_KEEP); break;                   \
-        case DROP_PHILOX_SHARED: MACRO(__VA_ARGS__, DROP_PHILOX_SHARED); break; \
-        default: MACRO(__VA_ARGS__, DROP_PHILOX_LANE); break;                   \
-    }
+static int msg_mode(const float *P, const float *Q, const float *R) {
+    if (P && Q && !R) return MSG_PQ;
+    if (P && Q && R) return MSG_PQR;
+    if (!P && !Q && R) return MSG_R;
+    return MSG_GENERIC;
+}
 
 extern "C" int mmconv_aggregate_fwd(const int32_t *rowptr, const int32_t *col, const int32_t *perm,
                                     const int32_t *edge_gid, int64_t E_total, const int32_t *row_map,
@@ -498,27 +512,36 @@ extern "C" int mmconv_aggregate_fwd(const int32_t *rowptr, const int32_t *col, c
     const int64_t grid = (threads + block - 1) / block;
     if (grid > INT32_MAX) return MMA_ERR_UNSUPPORTED;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define FWD_V4(MM, SQ, D)                                                                   \
-    do {                                                                                    \
-        if (R) mmconv_fwd_kernel<4, MM, SQ, D, true><<<(unsigned)grid, block, 0, st>>>(p);   \
-        else mmconv_fwd_kernel<4, MM, SQ, D, false><<<(unsigned)grid, block, 0, st>>>(p);    \
+    const int msg = msg_mode(P, Q, R);
+    bool launched = false;
+#define FWD(V, M, D, MM, SQ) (mmconv_fwd_kernel<V, M, D, MM, SQ><<<(unsigned)grid, block, 0, st>>>(p), launched = true)
+    // fast kernels: 128-bit path, message mode and dropout mode fixed at compile time
+#define FWD_FAST(M, D)                                       \
+    do {                                                     \
+        if (minmax && sq) FWD(4, M, D, true, true);          \
+        else if (minmax) FWD(4, M, D, true, false);          \
+        else if (sq) FWD(4, M, D, false, true);              \
+        else FWD(4, M, D, false, false);                     \
     } while (0)
-    // the scalar path (widths that are not a multiple of 4) is not specialised on the aggregator set
-#define FWD_V1(D)                                                                             \
-    do {                                                                                      \
-        if (R) mmconv_fwd_kernel<1, true, true, D, true><<<(unsigned)grid, block, 0, st>>>(p); \
-        else mmconv_fwd_kernel<1, true, true, D, false><<<(unsigned)grid, block, 0, st>>>(p);  \
-    } while (0)
-    if (vec == 4) {
-        if (minmax && sq) { MMA_FOR_DROP(FWD_V4, true, true) }
-        else if (minmax) { MMA_FOR_DROP(FWD_V4, true, false) }
-        else if (sq) { MMA_FOR_DROP(FWD_V4, false, true) }
-        else { MMA_FOR_DROP(FWD_V4, false, false) }
-    } else {
-        switch (drop) {
-            case DROP_NONE: FWD_V1(DROP_NONE); break;
-            case DROP_KEEP: FWD_V1(DROP_KEEP); break;
-            default: FWD_V1(DROP_PHILOX_LANE); break;
+    if (vec == 4 && msg != MSG_GENERIC && (drop == DROP_NONE || drop == DROP_PHILOX_SHARED)) {
+        if (msg == MSG_PQ) { if (drop == DROP_NONE) FWD_FAST(MSG_PQ, DROP_NONE); else FWD_FAST(MSG_PQ, DROP_PHILOX_SHARED); }
+        else if (msg == MSG_PQR) { if (drop == DROP_NONE) FWD_FAST(MSG_PQR, DROP_NONE); else FWD_FAST(MSG_PQR, DROP_PHILOX_SHARED); }
+        else { if (drop == DROP_NONE) FWD_FAST(MSG_R, DROP_NONE); else FWD_FAST(MSG_R, DROP_PHILOX_SHARED); }
+    }
+    if (!launched) {    // generic kernels (runtime null checks, all accumulators): test / odd-shape paths
+        if (vec == 4) {
+            switch (drop) {
+                case DROP_NONE: FWD(4, MSG_GENERIC, DROP_NONE, true, true); break;
+                case DROP_KEEP: FWD(4, MSG_GENERIC, DROP_KEEP, true, true); break;
+                case DROP_PHILOX_SHARED: FWD(4, MSG_GENERIC, DROP_PHILOX_SHARED, true, true); break;
+                default: FWD(4, MSG_GENERIC, DROP_PHILOX_LANE, true, true); break;
+            }
+        } else {
+            switch (drop) {
+                case DROP_NONE: FWD(1, MSG_GENERIC, DROP_NONE, true, true); break;
+                case DROP_KEEP: FWD(1, MSG_GENERIC, DROP_KEEP, true, true); break;
+                default: FWD(1, MSG_GENERIC, DROP_PHILOX_LANE, true, true); break;
+            }
         }
     }
     MMA_LAUNCH_CHECK();
@@ -562,23 +585,34 @@ extern "C" int mmconv_aggregate_bwd_dst(const int32_t *rowptr, const int32_t *co
     const int64_t grid = (threads + block - 1) / block;
     if (grid > INT32_MAX) return MMA_ERR_UNSUPPORTED;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define BWD_V4(NM, D)                                                                        \
-    do {                                                                                     \
-        if (R && NM) mmconv_bwd_dst_kernel<4, NM, D, true><<<(unsigned)grid, block, 0, st>>>(p); \
-        else mmconv_bwd_dst_kernel<4, NM, D, false><<<(unsigned)grid, block, 0, st>>>(p);     \
-    } while (0)
-#define BWD_V1(D)                                                                                 \
-    do {                                                                                          \
-        if (needm) mmconv_bwd_dst_kernel<1, true, D, true><<<(unsigned)grid, block, 0, st>>>(p);   \
-        else mmconv_bwd_dst_kernel<1, false, D, false><<<(unsigned)grid, block, 0, st>>>(p);       \
-    } while (0)
-    if (vec == 4) {
-        if (needm) { MMA_FOR_DROP(BWD_V4, true) } else { MMA_FOR_DROP(BWD_V4, false) }
-    } else {
-        switch (drop) {
-            case DROP_NONE: BWD_V1(DROP_NONE); break;
-            case DROP_KEEP: BWD_V1(DROP_KEEP); break;
-            default: BWD_V1(DROP_PHILOX_LANE); break;
+    const int msg = msg_mode(P, Q, R);
+    bool launched = false;
+#define BWD(V, M, D, NM) (mmconv_bwd_dst_kernel<V, M, D, NM><<<(unsigned)grid, block, 0, st>>>(p), launched = true)
+    if (vec == 4 && (drop == DROP_NONE || drop == DROP_PHILOX_SHARED)) {
+        if (!needm) {       // the message itself is not needed: no gather at all
+            if (drop == DROP_NONE) BWD(4, MSG_PQ, DROP_NONE, false); else BWD(4, MSG_PQ, DROP_PHILOX_SHARED, false);
+        } else if (msg == MSG_PQ) {
+            if (drop == DROP_NONE) BWD(4, MSG_PQ, DROP_NONE, true); else BWD(4, MSG_PQ, DROP_PHILOX_SHARED, true);
+        } else if (msg == MSG_PQR) {
+            if (drop == DROP_NONE) BWD(4, MSG_PQR, DROP_NONE, true); else BWD(4, MSG_PQR, DROP_PHILOX_SHARED, true);
+        } else if (msg == MSG_R) {
+            if (drop == DROP_NONE) BWD(4, MSG_R, DROP_NONE, true); else BWD(4, MSG_R, DROP_PHILOX_SHARED, true);
+        }
+    }
+    if (!launched) {
+        if (vec == 4) {
+            switch (drop) {
+                case DROP_NONE: if (needm) BWD(4, MSG_GENERIC, DROP_NONE, true); else BWD(4, MSG_GENERIC, DROP_NONE, false); break;
+                case DROP_KEEP: if (needm) BWD(4, MSG_GENERIC, DROP_KEEP, true); else BWD(4, MSG_GENERIC, DROP_KEEP, false); break;
+                case DROP_PHILOX_SHARED: if (needm) BWD(4, MSG_GENERIC, DROP_PHILOX_SHARED, true); else BWD(4, MSG_GENERIC, DROP_PHILOX_SHARED, false); break;
+                default: if (needm) BWD(4, MSG_GENERIC, DROP_PHILOX_LANE, true); else BWD(4, MSG_GENERIC, DROP_PHILOX_LANE, false); break;
+            }
+        } else {
+            switch (drop) {
+                case DROP_NONE: if (needm) BWD(1, MSG_GENERIC, DROP_NONE, true); else BWD(1, MSG_GENERIC, DROP_NONE, false); break;
+                case DROP_KEEP: if (needm) BWD(1, MSG_GENERIC, DROP_KEEP, true); else BWD(1, MSG_GENERIC, DROP_KEEP, false); break;
+                default: if (needm) BWD(1, MSG_GENERIC, DROP_PHILOX_LANE, true); else BWD(1, MSG_GENERIC, DROP_PHILOX_LANE, false); break;
+            }
         }
     }
     MMA_LAUNCH_CHECK();

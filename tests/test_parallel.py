@@ -1,0 +1,121 @@
+"""Multi-GPU path (mma_b200/parallel.py).
+
+CPU (gloo, world_size 2): the host-side logic -- destination-range bounds, local edge filtering
+with global edge ids, the padded all-gather layout and the reduce-scatter -- checked against a
+single-process recomputation.  The aggregation kernels themselves have no CPU path.
+
+GPU (needs >= 2 devices, NCCL): sharded K1 forward/backward == single-GPU result (min/max
+bit-exact incl. Philox dropout keyed by global edge ids, the rest to fp32 rounding)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _cpu_worker(rank, world, port, n, E):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mma_b200 import parallel as par
+        g = torch.Generator().manual_seed(0)
+        src = torch.randint(0, n, (E,), generator=g)
+        dst = (torch.rand(E, generator=g) ** 2 * n).long().clamp_(max=n - 1)       # skewed
+        for balance in ("nodes", "edges"):
+            sg = par.ShardedGraph(src, dst, n, rank, world, balance=balance)
+            b = sg.bounds
+            assert b[0] == 0 and b[-1] == n and all(b[i] <= b[i + 1] for i in range(world))
+            # every edge lands on exactly one rank, in original order, with its global id
+            cnt = torch.tensor([sg.E]); dist.all_reduce(cnt); assert int(cnt) == E
+            assert torch.equal(src[sg._gid], src[(dst >= sg.lo) & (dst < sg.hi)])
+            assert torch.all(sg._gid[1:] > sg._gid[:-1])
+            assert torch.equal(sg._dst_local + sg.lo, dst[sg._gid])
+            # padded source addressing: gathering rank-major padded rows reproduces global rows
+            F = 3
+            X = torch.arange(n * F, dtype=torch.float32).view(n, F)
+            allx = par.all_gather_rows(X[sg.lo:sg.hi], sg.max_rows)
+            assert torch.equal(allx[sg.src_padded], X[src[sg._gid]])
+            # reduce-scatter of partial per-source sums == global per-source sum of my rows
+            part = torch.zeros(world * sg.max_rows, F).index_add_(0, sg.src_padded, torch.ones(sg.E, F))
+            mine = par.reduce_scatter_rows(part, sg.max_rows, sg.rows)
+            ref = torch.zeros(n, F).index_add_(0, src, torch.ones(E, F))[sg.lo:sg.hi]
+            assert torch.equal(mine, ref)
+            if balance == "edges":
+                per = [int(((dst >= b[r]) & (dst < b[r + 1])).sum()) for r in range(world)]
+                assert max(per) <= 0.75 * E, per                                    # balanced by edges, not nodes
+        # data-parallel gradient all-reduce
+        p = torch.nn.Parameter(torch.ones(4)); p.grad = torch.full((4,), float(rank + 1))
+        par.allreduce_grads([p]); assert torch.equal(p.grad, torch.full((4,), float(sum(range(1, world + 1)))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_partition_and_collectives_gloo_world2():
+    mp.spawn(_cpu_worker, args=(2, _free_port(), 500, 6000), nprocs=2, join=True)
+
+
+def test_partition_bounds_single_process():
+    from mma_b200.parallel import partition_bounds, _slices
+    dst = torch.cat([torch.zeros(900, dtype=torch.long), torch.arange(100)])
+    assert partition_bounds(dst, 100, 4, "nodes") == [0, 25, 50, 75, 100]
+    b = partition_bounds(dst, 100, 4, "edges")
+    assert b[0] == 0 and b[-1] == 100 and b[1] == 1           # the hub row alone fills the first shard
+    assert partition_bounds(torch.zeros(0, dtype=torch.long), 10, 3, "edges") == [0, 4, 8, 10]
+    sl = _slices(128, 4)
+    assert [(s.start, s.stop) for s in sl] == [(0, 32), (32, 64), (64, 96), (96, 128)]
+    assert [(s.start, s.stop) for s in _slices(75, 4)] == [(0, 75)]
+    assert sum(s.stop - s.start for s in _slices(100, 3)) == 100
+
+
+def _gpu_worker(rank, world, port, n, E, Fd, p_drop):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import mma_b200
+        from mma_b200 import parallel as par
+        from oracle import restate
+        g = torch.Generator().manual_seed(1)
+        src = torch.randint(0, n, (E,), generator=g)
+        dst = torch.randint(0, n - 3, (E,), generator=g)
+        P, Q = torch.randn(n, Fd, generator=g), torch.randn(n, Fd, generator=g)
+        P[torch.rand(n, Fd, generator=g) < 0.3] = 0; Q[torch.rand(n, Fd, generator=g) < 0.3] = 0
+        gy = torch.randn(n, 1, 4 * 5 * Fd, generator=g)
+        aggr, scal = ["mean", "sum", "min", "max", "std"], ["identity", "amplification", "attenuation", "linear"]
+        avg = restate.avg_deg_from_hist(torch.bincount(torch.bincount(dst, minlength=n)))
+        # single-GPU reference on this rank's device
+        full = mma_b200.Graph(src.to(dev), dst.to(dev), n)
+        Pf, Qf = P.to(dev).requires_grad_(), Q.to(dev).requires_grad_()
+        Yf = mma_b200.mmconv_aggregate(Pf, Qf, None, full, towers=1, F_in=Fd, aggregators=aggr, scalers=scal,
+                                       avg_deg=avg, p_drop=p_drop, seed=77)
+        gPf, gQf = torch.autograd.grad(Yf, [Pf, Qf], gy.to(dev))
+        for balance, slices in (("nodes", 1), ("edges", 4)):
+            sg = par.ShardedGraph(src.to(dev), dst.to(dev), n, rank, world, balance=balance)
+            Pl = P[sg.lo:sg.hi].to(dev).requires_grad_(); Ql = Q[sg.lo:sg.hi].to(dev).requires_grad_()
+            Yl = par.sharded_mmconv_aggregate(Pl, Ql, sg, F_in=Fd, aggregators=aggr, scalers=scal, avg_deg=avg,
+                                              p_drop=p_drop, seed=77, n_slices=slices, max_deg=full.max_deg)
+            gPl, gQl = torch.autograd.grad(Yl, [Pl, Ql], gy[sg.lo:sg.hi].to(dev))
+            ref = Yf[sg.lo:sg.hi]
+            Yv, Rv = Yl.view(sg.rows, 4, 5, Fd), ref.view(sg.rows, 4, 5, Fd)
+            assert torch.equal(Yv[:, :, 2:4], Rv[:, :, 2:4]), "min/max must be bit-identical across shardings"
+            assert torch.equal(Yv, Rv), "same kernel, same per-row order: sharded forward is bit-identical"
+            assert torch.equal(gPl, gPf[sg.lo:sg.hi])
+            scale = gQf.abs().max().item()
+            assert (gQl - gQf[sg.lo:sg.hi]).abs().max().item() <= 1e-5 * scale      # reduce-scatter sum order
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("p_drop", [0.0, 0.5])
+def test_sharded_aggregate_matches_single_gpu(p_drop):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    mp.spawn(_gpu_worker, args=(2, _free_port(), 4000, 60000, 128, p_drop), nprocs=2, join=True)
