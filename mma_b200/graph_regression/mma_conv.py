@@ -107,7 +107,7 @@ class MMAConv(torch.nn.Module):
 
         self.fold_scalers = True             # towers == 1: fold the scalers into the post weight (see _forward_folded)
         self.fold_min_rows = 512             # degree ranges smaller than this use the literal formula
-        self.comm_slices = 4                 # feature windows of the sharded comm/compute pipeline
+        self.comm_slices = 2                 # feature windows of the sharded comm/compute pipeline
         self.global_max_deg = None           # sharded runs: global max in-degree (else all-reduced per call)
         self._uid = next(_UID)
         self._calls = 0
@@ -167,7 +167,8 @@ class MMAConv(torch.nn.Module):
         n = xt.size(0)
         if T == 1 and self.fold_scalers and self.pre_layers == 1 and self.mask != "no_linear":
             graph = self._graph(edge_index, n, sort_rows=True)
-            if isinstance(graph, Graph) and graph.buckets is not None:
+            local = graph.local if isinstance(graph, ShardedGraph) else graph
+            if local.buckets is not None and not (isinstance(graph, ShardedGraph) and edge_attr is not None):
                 return self._forward_folded(xt[:, 0], graph, edge_attr)
             edge_index = graph
         out = self.propagate(edge_index, x=xt, edge_attr=edge_attr, size=None)      # [N,T,S*A*F_in]
@@ -234,11 +235,20 @@ class MMAConv(torch.nn.Module):
             if s_ not in ("identity", "amplification", "attenuation", "linear", "inverse_linear"):
                 raise ValueError(f'Unknown scaler "{s_}".')
         P, Q, R = self._mask_projections(x.view(n, 1, F_in), edge_attr)
-        keep = self._inject_keep
-        if keep is not None:
-            keep = keep.reshape(graph.E, F_in)
-        Z = MF.mmconv_aggregate(P, Q, R, graph, towers=1, F_in=F_in, aggregators=self.aggregators,
-                                scalers=["identity"], keep=keep, p_drop=self.dropout, seed=self._next_seed())
+        if isinstance(graph, ShardedGraph):     # destination-range shard: x holds this rank's rows only
+            if self._inject_keep is not None:
+                raise RuntimeError("explicit keep masks are not supported on the sharded path")
+            Z = sharded_mmconv_aggregate(P, Q, graph, F_in=F_in, aggregators=self.aggregators,
+                                         scalers=["identity"], p_drop=self.dropout, seed=self._next_seed(),
+                                         n_slices=self.comm_slices, sorted_rows=True)
+            graph = graph.local
+        else:
+            keep = self._inject_keep
+            if keep is not None:
+                keep = keep.reshape(graph.E, F_in)
+            Z = MF.mmconv_aggregate(P, Q, R, graph, towers=1, F_in=F_in, aggregators=self.aggregators,
+                                    scalers=["identity"], keep=keep, p_drop=self.dropout,
+                                    seed=self._next_seed())
         first = self.post_nns[0][0]
         W = first.weight                                                             # [F_out, (S*A+1)*F_in]
         Hs = MF.scaled_post(Z.view(n, -1), W[:, F_in:], graph, self.scalers, self.avg_deg,

@@ -82,7 +82,11 @@ class ShardedGraph:
         self.src_padded = self.to_padded(s)
         self.local: Optional[Graph] = None
         if src.is_cuda:
-            g = Graph(self.src_padded, d, self.rows, world * self.max_rows, need_transpose=False)
+            # local rows in order of decreasing in-degree (row_map addresses P / dP): equal-degree
+            # rows are contiguous for the scaler-folded post GEMM, and the 4 or 8 rows that share a
+            # warp in a narrow feature window have (almost) equal length
+            g = Graph(self.src_padded, d, self.rows, world * self.max_rows, need_transpose=False,
+                      sort_rows=True)
             g.gid = gid.to(torch.int32).contiguous()
             g.E_total = self.E_total
             self.local = g
@@ -198,7 +202,7 @@ class _ShardedAggregate(torch.autograd.Function):
             q_base = Qk.data_ptr() - 4 * s_.start       # virtual base: column c of the window's row j
             with _lib.kernel_scope("mmconv_aggregate_fwd", dev):
                 _lib.check(_lib.lib().mmconv_aggregate_fwd(
-                    _lib.ptr(g.rowptr), _lib.ptr(g.col), _lib.ptr(g.perm), _lib.ptr(g.gid), g.E_total, None, n, g.E,
+                    _lib.ptr(g.rowptr), _lib.ptr(g.col), _lib.ptr(g.perm), _lib.ptr(g.gid), g.E_total, _lib.ptr(g.row_map), n, g.E,
                     _lib.ptr(P), P.stride(0), q_base, w, None, 0, None, 0,
                     float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, 1, F_in, A, ak, S, sk,
                     _lib.ptr(tab), 0 if tab is None else tab.shape[1], _lib.ptr(Y), Y.stride(0),
@@ -242,7 +246,7 @@ class _ShardedAggregate(torch.autograd.Function):
                 q_base = Qk.data_ptr() - 4 * s_.start
             with _lib.kernel_scope("mmconv_aggregate_bwd_dst", dev):
                 _lib.check(l.mmconv_aggregate_bwd_dst(
-                    _lib.ptr(g.rowptr), _lib.ptr(g.col), _lib.ptr(g.perm), _lib.ptr(g.gid), g.E_total, None, n, E,
+                    _lib.ptr(g.rowptr), _lib.ptr(g.col), _lib.ptr(g.perm), _lib.ptr(g.gid), g.E_total, _lib.ptr(g.row_map), n, E,
                     _lib.ptr(P), P.stride(0), q_base, w, None, 0, None, 0,
                     float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, 1, F_in, A, ak, S, sk,
                     _lib.ptr(tab), 0 if tab is None else tab.shape[1], _lib.ptr(dY), dY.stride(0),
@@ -281,10 +285,13 @@ def _comm_stream(dev) -> torch.cuda.Stream:
 def sharded_mmconv_aggregate(P_loc: Tensor, Q_loc: Tensor, sg: ShardedGraph, *, F_in: int,
                              aggregators: Sequence[str], scalers: Sequence[str],
                              avg_deg: Optional[Dict[str, float]] = None, p_drop: float = 0.0, seed: int = 0,
-                             n_slices: int = 4, max_deg: Optional[int] = None) -> Tensor:
+                             n_slices: int = 2, max_deg: Optional[int] = None,
+                             sorted_rows: bool = False) -> Tensor:
     """Sharded K1 (single tower): P_loc/Q_loc are this rank's rows [rows, F_in]; returns this
-    rank's Y [rows, 1, S*A*F_in].  `max_deg` must be the GLOBAL maximum in-degree when scalers are
-    used (the lookup table is then identical on all ranks); default: all-reduce(max)."""
+    rank's Y [rows, 1, S*A*F_in] in node order (sorted_rows=True: in the shard's degree-sorted row
+    order, sg.local.row_map, without the extra un-permute).  `max_deg` must be the GLOBAL maximum
+    in-degree when scalers are used (the lookup table is then identical on all ranks); default:
+    all-reduce(max)."""
     for a in aggregators:
         if a not in _lib.AGGR_KINDS:
             raise ValueError(f'Unknown aggregator "{a}".')
@@ -300,5 +307,8 @@ def sharded_mmconv_aggregate(P_loc: Tensor, Q_loc: Tensor, sg: ShardedGraph, *, 
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=sg.group)
             max_deg = int(t.item())
         tab = MF.scale_table(avg_deg, max(max_deg, 1), P_loc.device)
-    return _ShardedAggregate.apply(P_loc, Q_loc, sg, F_in, akinds, skinds, tab, float(p_drop), int(seed),
-                                   int(n_slices))
+    Y = _ShardedAggregate.apply(P_loc, Q_loc, sg, F_in, akinds, skinds, tab, float(p_drop), int(seed),
+                                int(n_slices))
+    if sorted_rows or sg.local.row_rank is None:
+        return Y
+    return Y.index_select(0, sg.local.row_rank)
