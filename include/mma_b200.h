@@ -202,6 +202,51 @@ int mma_nc_aggregate_bwd_src(const int32_t *colptr, const int32_t *row, const in
 int mma_dropout_keep_scale(float p_drop, uint64_t seed, uint32_t stream_id,
                            int64_t E, int F, float *out, int64_t ldo, mma_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * G1-G4: the dense projections on the tcgen05 tensor cores, fp32-accurate by
+ * 3xTF32 operand splitting (x = hi + lo; hi*hi + hi*lo + lo*hi, fp32 accumulate
+ * in TMEM).  They replace the reference's fp32 Linears: the mask projection
+ * (mask_aggr.py:68), the post-transform over cat([x, out]) and `lin`
+ * (mma_conv.py:132-136), GraphConvolution's x @ W (layers.py:40) -- and their
+ * autograd backward.  All operands fp32 row-major, 16-byte aligned, leading
+ * dimensions multiples of 4.
+ * ------------------------------------------------------------------------ */
+
+/* hi = w with the low 13 mantissa bits cleared (exact TF32), lo = w - hi. */
+int mma_tf32_split(const float *w, float *hi, float *lo, int64_t n, mma_stream_t stream);
+
+/* C[out_row(r), 0:N] = [A0 | A1][r, :] . B[b_off + 0:N, :]^T (+ bias) (+ add[out_row(r), 0:N])
+ *   A0 [M, K0], A1 [M, K1] (optional second source concatenated along K; K0 % 32 == 0 then);
+ *   Bhi/Blo [b_rows, K0+K1] pre-split weight(s) (mma_tf32_split);
+ *   tile_tab (optional) int32 [n_tiles_m][4] = {row0, row_end, b_off, 0}: 128-row tiles of a
+ *     GROUPED GEMM -- rows [row0, row_end) use the weight rows b_off .. b_off+N (degree ranges
+ *     with scaler-folded weights); null = plain GEMM over M rows, b_off = 0;
+ *   out_map (optional) int32 [M]: output row of input row r (row scatter fused in the epilogue);
+ *   bias [N], add (indexed like C, may alias C) optional.
+ *   mode 0 = 3xTF32 (hi written back), 1 = 3xTF32 (raw operand as hi), 2 = plain TF32 (not fp32-accurate).
+ *   max_ctas <= 0: one persistent CTA per SM. */
+int mma_linear_tf32x3(const float *A0, int64_t lda0, int K0, const float *A1, int64_t lda1, int K1,
+                      const float *Bhi, const float *Blo, int64_t ldb, int64_t b_rows,
+                      int64_t M, int N, const int32_t *tile_tab, int64_t n_tiles_m,
+                      float *C, int64_t ldc, const int32_t *out_map, const float *bias,
+                      const float *add, int64_t ldadd, int mode, int max_ctas, mma_stream_t stream);
+
+/* Weight gradient: part[slot][n][k] = sum_{m in slab} [G0 | G1][m, n] * A[m, k].
+ *   slab_tab int32 [n_slabs][4] = {row0, row_end, slot, 0} (row0 % 32 == 0 is not required;
+ *   slabs may end anywhere: rows >= row_end are masked); part [slots][N0+N1][K].
+ *   Sum the slots in a fixed order with mma_reduce_slabs (no atomics). */
+int mma_wgrad_tf32x3(const float *G0, int64_t ldg0, int N0, const float *G1, int64_t ldg1, int N1,
+                     const float *A, int64_t lda, int K, int64_t M, const int32_t *slab_tab,
+                     int64_t n_slabs, float *part, int mode, int max_ctas, mma_stream_t stream);
+
+/* out[i] = sum_s coef[s] * part[s][i], s ascending (coef optional), i < n, n % 4 == 0. */
+int mma_reduce_slabs(const float *part, const float *coef, int64_t n_slots, int64_t n, float *out,
+                     mma_stream_t stream);
+
+/* out[g][i] = sum of part[s][i] for s in [seg_ptr[g], seg_ptr[g+1]), ascending s; out [n_segs][n]. */
+int mma_reduce_slabs_segmented(const float *part, const int32_t *seg_ptr, int64_t n_segs, int64_t n,
+                               float *out, mma_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,6 +43,13 @@ _SIGS = {
     "mma_nc_aggregate_bwd_src": ([_vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32,
                                   _vp, _vp, _f32, _u64, _vp, _vp, _i64, _vp, _i64, _vp], C.c_int),
     "mma_dropout_keep_scale": ([_f32, _u64, _u32, _i64, _i32, _vp, _i64, _vp], C.c_int),
+    "mma_tf32_split": ([_vp, _vp, _vp, _i64, _vp], C.c_int),
+    "mma_linear_tf32x3": ([_vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _i64,
+                           _vp, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _vp], C.c_int),
+    "mma_wgrad_tf32x3": ([_vp, _i64, _i32, _vp, _i64, _i32, _vp, _i64, _i32, _i64, _vp, _i64, _vp, _i32, _i32, _vp],
+                         C.c_int),
+    "mma_reduce_slabs": ([_vp, _vp, _i64, _i64, _vp, _vp], C.c_int),
+    "mma_reduce_slabs_segmented": ([_vp, _vp, _i64, _i64, _vp, _vp], C.c_int),
 }
 EXPORTS = tuple(_SIGS)
 

@@ -1,0 +1,650 @@
+// G1-G4: the dense projections of the MultiMaskConv layer on the 5th-gen tensor cores.
+//
+// Replaces (reference paths relative to /root/reference/graph_regression):
+//   mask_aggr.py:68        the mask projection Linear          -> P, Q = X W_i^T + b, X W_j^T
+//   mma_conv.py:132-136    cat([x, out]) -> post_nns -> lin    -> grouped GEMM over degree ranges + lin
+// and their autograd backward (dgrad: same kernel with the transposed weight; wgrad: gemm_wgrad below).
+//
+// The reference computes these in fp32 and parity is judged at 1e-5, so plain TF32 (10-bit mantissa)
+// is not acceptable.  Every fp32 operand is split as x = hi + lo with hi exactly representable in
+// TF32 and lo = x - hi; D += A_lo B_hi + A_hi B_lo + A_hi B_hi (3xTF32) recovers the fp32 product to
+// ~2^-21 with fp32 accumulation in TMEM.  Weights (small) are pre-split on the host side of the
+// call; activations are split INSIDE the kernel by a converter warpgroup working on the TMA-filled
+// shared-memory tile, so no extra pass over HBM is needed.
+//
+// One persistent CTA per SM, 320 threads, warp-specialised:
+//   warp 0      TMA producer     A tile [128 x 32] fp32 (+ pre-split B_hi/B_lo tiles [128 x 32]) per stage
+//   warp 1      MMA issuer       one thread issues 12 tcgen05.mma.kind::tf32 (M=128,N=128,K=8) per stage
+//   warps 2-5   converter        A -> (A_hi in place, A_lo) in shared memory, fence.proxy.async
+//   warps 6-9   epilogue         TMEM -> registers -> swizzled smem transpose -> coalesced global stores
+//                                with optional bias, row-indexed addend and output-row scatter
+// Pipelines: smem full/conv/empty (3 stages) and TMEM full/empty (2 accumulators of 128 columns),
+// so the epilogue of tile i overlaps the main loop of tile i+1.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace mma {
+namespace gemm {
+
+using namespace tc;
+
+constexpr int BM = 128, BN = 128, BK = 32;
+constexpr int STAGES = 3;
+constexpr int A_BYTES = BM * BK * 4;                      // 16 KB
+constexpr int B_BYTES = BN * BK * 4;                      // 16 KB
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;    // A, A_lo, B_hi, B_lo
+constexpr int EPI_BYTES = 4 * 32 * 32 * 4;                // one 32x32 fp32 transpose buffer per epilogue warp
+constexpr int BAR_BYTES = 256;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;   // + alignment slack
+constexpr int THREADS = 320;
+constexpr int TMEM_COLS = 512;   // 2 tiles in flight x (main + correction) accumulators of 128 columns
+
+struct alignas(64) NtParams {
+    CUtensorMap map_a0, map_a1, map_bhi, map_blo;
+    int kb_split, num_kb;       // k-blocks [0,kb_split) read map_a0, [kb_split,num_kb) read map_a1
+    int n_tiles_n;
+    int mode;                   // 0: 3xTF32, hi written back explicitly; 1: 3xTF32, raw A as hi; 2: 1xTF32
+    int64_t M, n_tiles_m;
+    int N;
+    const int32_t *tile_tab;    // [n_tiles_m][4] = row0, row_end, b_row_off, -   (null: plain GEMM)
+    float *C;
+    int64_t ldc;
+    const int32_t *out_map;     // output row of tile row r (null: r)
+    const float *bias;          // [N]
+    const float *add;           // indexed like C
+    int64_t ldadd;
+};
+
+struct Tile { int64_t row0, row_end; int b_off, n0; };
+
+__device__ __forceinline__ Tile locate_tile(const NtParams &p, int64_t t) {
+    Tile tl;
+    const int64_t m = t / p.n_tiles_n;
+    tl.n0 = (int)(t - m * p.n_tiles_n) * BN;
+    if (p.tile_tab) {
+        const int4 e = __ldg(reinterpret_cast<const int4 *>(p.tile_tab) + m);
+        tl.row0 = e.x; tl.row_end = e.y; tl.b_off = e.z;
+    } else {
+        tl.row0 = m * BM; tl.row_end = p.M; tl.b_off = 0;
+    }
+    return tl;
+}
+
+// main + correction accumulator chunk (32 lanes x 32 columns) -> registers
+__device__ __forceinline__ void load_acc(uint32_t taddr, bool with_corr, uint32_t (&r)[32]) {
+    tmem_ld_32x32(taddr, r);
+    if (with_corr) {
+        uint32_t c[32];
+        tmem_ld_32x32(taddr + BN, c);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(c[i]));
+    } else {
+        tmem_ld_wait();
+    }
+}
+
+// One 32-row x 32-column accumulator chunk held row-per-thread (thread = row) -> global memory.
+// The chunk is transposed through a swizzled 4 KB staging buffer (16-byte chunk index XOR row%8:
+// conflict-free both ways) so that every store instruction writes 4 rows x 128 B of full lines.
+__device__ __forceinline__ void store_chunk(float *stg, const uint32_t (&r)[32], int lane, int64_t row0, int64_t row_end,
+                                            int col0, int n_cols, float *C, int64_t ldc, const int32_t *out_map,
+                                            const float *bias, const float *add, int64_t ldadd) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                     __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        *reinterpret_cast<float4 *>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = v;
+    }
+    __syncwarp();
+    const int ch = lane & 7;
+    const int col = col0 + ch * 4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + (lane >> 3);
+        const int64_t grow = row0 + rr;
+        if (grow < row_end && col < n_cols) {
+            float4 v = *reinterpret_cast<const float4 *>(stg + rr * 32 + ((ch ^ (rr & 7)) << 2));
+            const int64_t orow = out_map ? (int64_t)__ldg(out_map + grow) : grow;
+            if (bias) {
+                const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + col));
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+            }
+            if (add) {
+                const float4 a = __ldcs(reinterpret_cast<const float4 *>(add + orow * ldadd + col));
+                v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+            }
+            __stcs(reinterpret_cast<float4 *>(C + orow * ldc + col), v);
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_constant__ NtParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t epi_base = smem_base + STAGES * STAGE_BYTES;
+    const uint32_t bar_base = epi_base + EPI_BYTES;
+    // barriers: full[3], conv[3], empty[3], tfull[2], tempty[2], then the TMEM base address word
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto conv_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+    auto tfull_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + b); };
+    auto tempty_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + 2 + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (3 * STAGES + 4);
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem + (tmem_slot - smem_base));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n_tiles = p.n_tiles_m * p.n_tiles_n;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.map_a0); tma_prefetch_desc(&p.map_a1);
+        tma_prefetch_desc(&p.map_bhi); tma_prefetch_desc(&p.map_blo);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(conv_bar(s), 4); mbar_init(empty_bar(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const Tile tl = locate_tile(p, t);
+                for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1u;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    const uint32_t sa = smem_base + s * STAGE_BYTES;
+                    mbar_expect_tx(full_bar(s), A_BYTES + (p.mode == 2 ? 1 : 2) * B_BYTES);
+                    if (kb < p.kb_split) tma_load_2d(sa, &p.map_a0, full_bar(s), kb * BK, (int)tl.row0);
+                    else tma_load_2d(sa, &p.map_a1, full_bar(s), (kb - p.kb_split) * BK, (int)tl.row0);
+                    tma_load_2d(sa + 2 * A_BYTES, &p.map_bhi, full_bar(s), kb * BK, tl.b_off + tl.n0);
+                    if (p.mode != 2) tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &p.map_blo, full_bar(s), kb * BK, tl.b_off + tl.n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(BM, BN, 0, 0);
+            uint32_t it = 0, ti = 0;
+            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+                const uint32_t buf = ti & 1u;
+                mbar_wait(tempty_bar(buf), ((ti >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * 2 * BN;      // main accumulator; correction at +BN
+                for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1u;
+                    mbar_wait(full_bar(s), ph);
+                    if (p.mode != 2) mbar_wait(conv_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + s * STAGE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k) {
+                        const uint64_t a_hi = umma_desc_sw128(sa + k * 32, 16, 1024);
+                        const uint64_t a_lo = umma_desc_sw128(sa + A_BYTES + k * 32, 16, 1024);
+                        const uint64_t b_hi = umma_desc_sw128(sa + 2 * A_BYTES + k * 32, 16, 1024);
+                        const uint64_t b_lo = umma_desc_sw128(sa + 2 * A_BYTES + B_BYTES + k * 32, 16, 1024);
+                        const uint32_t first = (kb | k) != 0;
+                        // The tensor core truncates when it adds into the fp32 accumulator, a bias that grows
+                        // with the length of the accumulation chain.  The two small cross terms go to their
+                        // own accumulator (2^-11 of the magnitude, so their truncation is negligible) and the
+                        // main chain is 1 MMA per K step instead of 3; the epilogue adds the two.
+                        if (p.mode != 2) {
+                            umma_tf32_ss(d_tmem + BN, a_lo, b_hi, idesc, first);
+                            umma_tf32_ss(d_tmem + BN, a_hi, b_lo, idesc, 1u);
+                        }
+                        umma_tf32_ss(d_tmem, a_hi, b_hi, idesc, first);
+                    }
+                    tc_commit(empty_bar(s));            // smem stage reusable once these MMAs retire
+                }
+                tc_commit(tfull_bar(buf));              // accumulator complete
+            }
+        }
+    } else if (warp < 6) {
+        // ===================================================================== converter (A -> hi, lo)
+        if (p.mode != 2) {
+            const int ct = threadIdx.x - 64;            // 0..127
+            uint32_t it = 0;
+            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1u;
+                    mbar_wait(full_bar(s), ph);
+                    float4 *a = reinterpret_cast<float4 *>(smem + s * STAGE_BYTES);
+                    float4 *alo = reinterpret_cast<float4 *>(smem + s * STAGE_BYTES + A_BYTES);
+#pragma unroll
+                    for (int i = 0; i < A_BYTES / 16 / 128; ++i) {
+                        const float4 v = a[i * 128 + ct];
+                        if (p.mode == 0) {
+                            const float4 h = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+                            alo[i * 128 + ct] = make_float4(tf32_rna(v.x - h.x), tf32_rna(v.y - h.y), tf32_rna(v.z - h.z),
+                                                            tf32_rna(v.w - h.w));
+                            a[i * 128 + ct] = h;
+                        } else {        // the tensor core ignores the low 13 mantissa bits: raw A acts as trunc(A)
+                            const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+                            alo[i * 128 + ct] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                        }
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(conv_bar(s));
+                }
+            }
+        }
+    } else {
+        // ===================================================================== epilogue
+        const int wq = warp & 3;                        // TMEM lane quarter this warp may access
+        float *stg = reinterpret_cast<float *>(smem + (epi_base - smem_base) + (warp - 6) * 4096);
+        uint32_t ti = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+            const Tile tl = locate_tile(p, t);
+            const uint32_t buf = ti & 1u;
+            mbar_wait(tfull_bar(buf), (ti >> 1) & 1u);
+            tc_fence_after();
+            const int n_chunks = min(4, (p.N - tl.n0 + 31) / 32);
+            for (int c = 0; c < n_chunks; ++c) {
+                uint32_t r[32];
+                load_acc(tmem_base + buf * 2 * BN + c * 32 + ((uint32_t)(wq * 32) << 16), p.mode != 2, r);
+                if (c == n_chunks - 1) {                // accumulator fully read: hand the buffer back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar(buf));
+                }
+                store_chunk(stg, r, lane, tl.row0 + wq * 32, tl.row_end, tl.n0 + c * 32, p.N, p.C, p.ldc, p.out_map,
+                            p.bias, p.add, p.ldadd);
+                __syncwarp();
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------
+// wgrad: dW[n, k] = sum_m G[m, n] * A[m, k]   (G = dL/dY [M, N], A = layer input [M, K])
+//
+// Both operands are "MN-major" for the tensor core (the reduction index m is the ROW of both
+// row-major matrices): a stage holds 32 reduction rows as 4 + 4 TMA boxes of [32 rows x 32 columns]
+// (TMA swizzle 128B_ATOM_32B), i.e. canonical MN-major SWIZZLE_128B_BASE32B atoms -- the only MN-major
+// layout the tensor core accepts for 32-bit operands -- with LBO = 4096 B between 32-column groups and
+// SBO = 512 B between groups of 4 reduction rows; one tcgen05.mma (K = 8) consumes 8 rows = 1024 B.  Both operands are activations, so the converter warps split both tiles; rows beyond the
+// slab's end (slabs may end inside a 32-row block when they follow degree ranges) are zeroed there.
+// The reduction over M is cut into slabs; a work unit = (slab, 128x128 output tile) writes its partial
+// tile to part[slab_slot][N][K]; a fixed-order second pass sums the slabs (no atomics).
+// ------------------------------------------------------------------------------------------
+struct alignas(64) WgParams {
+    CUtensorMap map_g0, map_g1, map_a;
+    int n_split;                // output rows n < n_split come from map_g0, the rest from map_g1 (at n - n_split)
+    int tiles_n, tiles_k, mode;
+    int N, K;
+    int64_t n_slabs;
+    const int32_t *slab_tab;    // [n_slabs][4] = row0, row_end, out_slot, -
+    float *part;                // [slots][N][K]
+};
+
+__global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_constant__ WgParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t epi_base = smem_base + STAGES * STAGE_BYTES;
+    const uint32_t bar_base = epi_base + EPI_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto conv_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+    auto tfull_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + b); };
+    auto tempty_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + 2 + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (3 * STAGES + 4);
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem + (tmem_slot - smem_base));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles = p.tiles_n * p.tiles_k;
+    const int64_t n_units = p.n_slabs * tiles;
+    // stage layout: G [4 x 4 KB] | G_lo | A [4 x 4 KB] | A_lo
+    struct Unit { int row0, row_end, slot, n0, k0; };
+    auto locate = [&](int64_t u) {
+        Unit x;
+        const int64_t sl = u / tiles;
+        const int tile = (int)(u - sl * tiles);
+        const int4 e = __ldg(reinterpret_cast<const int4 *>(p.slab_tab) + sl);
+        x.row0 = e.x; x.row_end = e.y; x.slot = e.z;
+        x.n0 = (tile / p.tiles_k) * BM;
+        x.k0 = (tile % p.tiles_k) * BN;
+        return x;
+    };
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.map_g0); tma_prefetch_desc(&p.map_g1); tma_prefetch_desc(&p.map_a);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(conv_bar(s), 4); mbar_init(empty_bar(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const Unit x = locate(u);
+                const CUtensorMap *mg = x.n0 < p.n_split ? &p.map_g0 : &p.map_g1;
+                const int gc0 = x.n0 < p.n_split ? x.n0 : x.n0 - p.n_split;
+                for (int r = x.row0; r < x.row_end; r += BK, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1u;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    const uint32_t sa = smem_base + s * STAGE_BYTES;
+                    mbar_expect_tx(full_bar(s), A_BYTES + B_BYTES);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        tma_load_2d(sa + g * 4096, mg, full_bar(s), gc0 + g * 32, r);
+                        tma_load_2d(sa + 2 * A_BYTES + g * 4096, &p.map_a, full_bar(s), x.k0 + g * 32, r);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(BM, BN, 1, 1);
+            uint32_t it = 0, ti = 0;
+            for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++ti) {
+                const Unit x = locate(u);
+                const uint32_t buf = ti & 1u;
+                mbar_wait(tempty_bar(buf), ((ti >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * 2 * BN;
+                uint32_t acc = 0;
+                for (int r = x.row0; r < x.row_end; r += BK, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1u;
+                    mbar_wait(full_bar(s), ph);
+                    mbar_wait(conv_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + s * STAGE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k) {
+                        const uint64_t g_hi = umma_desc(sa + k * 1024, 4096, 512, 1);
+                        const uint64_t g_lo = umma_desc(sa + A_BYTES + k * 1024, 4096, 512, 1);
+                        const uint64_t a_hi = umma_desc(sa + 2 * A_BYTES + k * 1024, 4096, 512, 1);
+                        const uint64_t a_lo = umma_desc(sa + 2 * A_BYTES + B_BYTES + k * 1024, 4096, 512, 1);
+                        if (p.mode != 2) {
+                            umma_tf32_ss(d_tmem + BN, g_lo, a_hi, idesc, acc);
+                            umma_tf32_ss(d_tmem + BN, g_hi, a_lo, idesc, 1u);
+                        }
+                        umma_tf32_ss(d_tmem, g_hi, a_hi, idesc, acc);
+                        acc = 1u;
+                    }
+                    tc_commit(empty_bar(s));
+                }
+                tc_commit(tfull_bar(buf));
+            }
+        }
+    } else if (warp < 6) {
+        const int ct = threadIdx.x - 64;
+        uint32_t it = 0;
+        for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const Unit x = locate(u);
+            for (int r = x.row0; r < x.row_end; r += BK, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1u;
+                const int valid = x.row_end - r;            // rows of this block inside the slab (>= 32: all)
+                mbar_wait(full_bar(s), ph);
+#pragma unroll
+                for (int op = 0; op < 2; ++op) {
+                    float4 *a = reinterpret_cast<float4 *>(smem + s * STAGE_BYTES + op * 2 * A_BYTES);
+                    float4 *alo = a + A_BYTES / 16;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int idx = i * 128 + ct;       // 16-byte chunk; box g = idx/256, row = (idx/8) % 32
+                        float4 v = a[idx];
+                        const bool dead = ((idx >> 3) & 31) >= valid;
+                        if (dead) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.mode == 0) {
+                            const float4 h = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+                            alo[idx] = make_float4(tf32_rna(v.x - h.x), tf32_rna(v.y - h.y), tf32_rna(v.z - h.z),
+                                                   tf32_rna(v.w - h.w));
+                            a[idx] = h;
+                        } else {
+                            const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+                            if (p.mode != 2) alo[idx] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                            if (valid < BK) a[idx] = h;
+                        }
+                    }
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(conv_bar(s));
+            }
+        }
+    } else {
+        const int wq = warp & 3;
+        float *stg = reinterpret_cast<float *>(smem + (epi_base - smem_base) + (warp - 6) * 4096);
+        uint32_t ti = 0;
+        for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++ti) {
+            const Unit x = locate(u);
+            const uint32_t buf = ti & 1u;
+            mbar_wait(tfull_bar(buf), (ti >> 1) & 1u);
+            tc_fence_after();
+            float *out = p.part + (int64_t)x.slot * p.N * p.K;
+            const int n_chunks = min(4, (p.K - x.k0 + 31) / 32);
+            for (int c = 0; c < n_chunks; ++c) {
+                uint32_t r[32];
+                load_acc(tmem_base + buf * 2 * BN + c * 32 + ((uint32_t)(wq * 32) << 16), p.mode != 2, r);
+                if (c == n_chunks - 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar(buf));
+                }
+                store_chunk(stg, r, lane, x.n0 + wq * 32, p.N, x.k0 + c * 32, p.K, out, p.K, nullptr, nullptr, nullptr, 0);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// out[i] = sum_s coef[s] * part[s][i] in slab order (coef null: 1)
+__global__ void reduce_slabs_kernel(const float *__restrict__ part, const float *__restrict__ coef, int64_t n_slots,
+                                    int64_t n4, float *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t s = 0; s < n_slots; ++s) {
+        const float4 v = __ldcs(reinterpret_cast<const float4 *>(part) + s * n4 + i);
+        const float c = coef ? __ldg(coef + s) : 1.0f;
+        acc.x += c * v.x; acc.y += c * v.y; acc.z += c * v.z; acc.w += c * v.w;
+    }
+    reinterpret_cast<float4 *>(out)[i] = acc;
+}
+
+// out[g][i] = sum over slots s in [seg_ptr[g], seg_ptr[g+1]) of part[s][i], ascending s
+__global__ void reduce_slabs_seg_kernel(const float *__restrict__ part, const int32_t *__restrict__ seg_ptr,
+                                        int64_t n4, float *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const int g = blockIdx.y;
+    const int s0 = __ldg(seg_ptr + g), s1 = __ldg(seg_ptr + g + 1);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = s0; s < s1; ++s) {
+        const float4 v = __ldcs(reinterpret_cast<const float4 *>(part) + (int64_t)s * n4 + i);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    reinterpret_cast<float4 *>(out)[(int64_t)g * n4 + i] = acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// weight pre-split
+// ------------------------------------------------------------------------------------------
+__global__ void split_tf32_kernel(const float *__restrict__ w, float *__restrict__ hi, float *__restrict__ lo, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float x = w[i];
+        const float h = tf32_rna(x);
+        hi[i] = h;
+        lo[i] = tf32_rna(x - h);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: tensor maps
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            ptr = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(ptr);
+    }();
+    return fn;
+}
+
+// 2-D fp32 row-major tensor [rows, cols] with leading dimension ld (elements); box = [box_rows x box_cols],
+// 128-byte swizzle (box_cols * 4 must be 128).  Out-of-bounds elements are zero-filled.
+int make_map_2d(CUtensorMap *m, const float *base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols,
+                CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return MMA_ERR_CUDA;
+    if (!aligned16(base) || (ld % 4) != 0 || rows < 1 || cols < 1) return MMA_ERR_INVALID;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? MMA_OK : MMA_ERR_INVALID;
+}
+
+}  // namespace gemm
+}  // namespace mma
+
+using namespace mma;
+using namespace mma::gemm;
+
+extern "C" int mma_tf32_split(const float *w, float *hi, float *lo, int64_t n, mma_stream_t stream) {
+    if (n < 0 || (n > 0 && (!w || !hi || !lo))) return MMA_ERR_INVALID;
+    if (n == 0) return MMA_OK;
+    split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(w, hi, lo, n);
+    MMA_LAUNCH_CHECK();
+    return MMA_OK;
+}
+
+extern "C" int mma_linear_tf32x3(const float *A0, int64_t lda0, int K0, const float *A1, int64_t lda1, int K1,
+                                 const float *Bhi, const float *Blo, int64_t ldb, int64_t b_rows,
+                                 int64_t M, int N, const int32_t *tile_tab, int64_t n_tiles_m,
+                                 float *C, int64_t ldc, const int32_t *out_map, const float *bias,
+                                 const float *add, int64_t ldadd, int mode, int max_ctas, mma_stream_t stream) {
+    if (!A0 || !Bhi || !Blo || !C || M < 0 || N < 1 || K0 < 1 || K1 < 0 || b_rows < 1) return MMA_ERR_INVALID;
+    if (mode < 0 || mode > 2) return MMA_ERR_INVALID;
+    if ((N % 4) != 0 || (ldc % 4) != 0 || !aligned16(C) || !aligned16(bias) || !aligned16(add) || (ldadd % 4) != 0)
+        return MMA_ERR_UNSUPPORTED;
+    if (K1 > 0 && (!A1 || (K0 % BK) != 0)) return MMA_ERR_INVALID;
+    if (M >= INT32_MAX || b_rows >= INT32_MAX) return MMA_ERR_UNSUPPORTED;
+    if (M == 0) return MMA_OK;
+    NtParams p;
+    memset(&p, 0, sizeof(p));
+    int rc;
+    if ((rc = make_map_2d(&p.map_a0, A0, M, K0, lda0, BM, BK)) != MMA_OK) return rc;
+    if (K1 > 0) { if ((rc = make_map_2d(&p.map_a1, A1, M, K1, lda1, BM, BK)) != MMA_OK) return rc; }
+    else p.map_a1 = p.map_a0;
+    if ((rc = make_map_2d(&p.map_bhi, Bhi, b_rows, K0 + K1, ldb, BN, BK)) != MMA_OK) return rc;
+    if ((rc = make_map_2d(&p.map_blo, Blo, b_rows, K0 + K1, ldb, BN, BK)) != MMA_OK) return rc;
+    p.kb_split = K1 > 0 ? K0 / BK : (K0 + BK - 1) / BK;
+    p.num_kb = p.kb_split + (K1 + BK - 1) / BK;
+    p.n_tiles_n = (N + BN - 1) / BN;
+    p.mode = mode;
+    p.M = M; p.N = N;
+    p.tile_tab = tile_tab;
+    p.n_tiles_m = tile_tab ? n_tiles_m : (M + BM - 1) / BM;
+    if (p.n_tiles_m < 1) return tile_tab ? MMA_OK : MMA_ERR_INVALID;
+    p.C = C; p.ldc = ldc; p.out_map = out_map; p.bias = bias; p.add = add; p.ldadd = ldadd;
+    MMA_CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    int sms = 0, dev = 0;
+    MMA_CUDA_CHECK(cudaGetDevice(&dev));
+    MMA_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
+    const int64_t n_tiles = p.n_tiles_m * p.n_tiles_n;
+    const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
+    gemm_nt_kernel<<<grid, THREADS, SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    MMA_LAUNCH_CHECK();
+    return MMA_OK;
+}
+
+extern "C" int mma_wgrad_tf32x3(const float *G0, int64_t ldg0, int N0, const float *G1, int64_t ldg1, int N1,
+                                const float *A, int64_t lda, int K, int64_t M, const int32_t *slab_tab,
+                                int64_t n_slabs, float *part, int mode, int max_ctas, mma_stream_t stream) {
+    if (!G0 || !A || !part || !slab_tab || M < 1 || N0 < 1 || N1 < 0 || K < 1 || n_slabs < 0) return MMA_ERR_INVALID;
+    if (mode < 0 || mode > 2) return MMA_ERR_INVALID;
+    if (N1 > 0 && (!G1 || (N0 % BM) != 0)) return MMA_ERR_INVALID;
+    if ((K % 4) != 0 || !aligned16(part) || M >= INT32_MAX) return MMA_ERR_UNSUPPORTED;
+    if (n_slabs == 0) return MMA_OK;
+    WgParams p;
+    memset(&p, 0, sizeof(p));
+    int rc;
+    if ((rc = make_map_2d(&p.map_g0, G0, M, N0, ldg0, BK, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != MMA_OK) return rc;
+    if (N1 > 0) { if ((rc = make_map_2d(&p.map_g1, G1, M, N1, ldg1, BK, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != MMA_OK) return rc; }
+    else p.map_g1 = p.map_g0;
+    if ((rc = make_map_2d(&p.map_a, A, M, K, lda, BK, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != MMA_OK) return rc;
+    p.N = N0 + N1; p.K = K;
+    p.n_split = N1 > 0 ? N0 : INT32_MAX;
+    p.tiles_n = (p.N + BM - 1) / BM;
+    p.tiles_k = (K + BN - 1) / BN;
+    p.mode = mode;
+    p.n_slabs = n_slabs; p.slab_tab = slab_tab; p.part = part;
+    MMA_CUDA_CHECK(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    int sms = 0, dev = 0;
+    MMA_CUDA_CHECK(cudaGetDevice(&dev));
+    MMA_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
+    const int64_t n_units = n_slabs * p.tiles_n * p.tiles_k;
+    const unsigned grid = (unsigned)(n_units < sms ? n_units : sms);
+    gemm_wgrad_kernel<<<grid, THREADS, SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    MMA_LAUNCH_CHECK();
+    return MMA_OK;
+}
+
+extern "C" int mma_reduce_slabs(const float *part, const float *coef, int64_t n_slots, int64_t n, float *out,
+                                mma_stream_t stream) {
+    if (!part || !out || n_slots < 1 || n < 0 || (n % 4) != 0 || !aligned16(part) || !aligned16(out))
+        return MMA_ERR_INVALID;
+    if (n == 0) return MMA_OK;
+    const int64_t n4 = n / 4;
+    reduce_slabs_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        part, coef, n_slots, n4, out);
+    MMA_LAUNCH_CHECK();
+    return MMA_OK;
+}
+
+extern "C" int mma_reduce_slabs_segmented(const float *part, const int32_t *seg_ptr, int64_t n_segs, int64_t n,
+                                          float *out, mma_stream_t stream) {
+    if (!part || !seg_ptr || !out || n_segs < 0 || n < 0 || (n % 4) != 0 || !aligned16(part) || !aligned16(out))
+        return MMA_ERR_INVALID;
+    if (n == 0 || n_segs == 0) return MMA_OK;
+    if (n_segs > 65535) return MMA_ERR_UNSUPPORTED;
+    const int64_t n4 = n / 4;
+    dim3 grid((unsigned)((n4 + 255) / 256), (unsigned)n_segs);
+    reduce_slabs_seg_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(part, seg_ptr, n4, out);
+    MMA_LAUNCH_CHECK();
+    return MMA_OK;
+}

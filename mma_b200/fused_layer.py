@@ -1,0 +1,239 @@
+"""The whole MultiMaskConv layer (towers == 1) as ONE autograd node over the C-ABI kernels.
+
+reference (graph_regression/mma_conv.py)                  here, all rows in degree-sorted node order
+--------------------------------------------------------  ------------------------------------------------
+x.view(-1,1,F).repeat(1,T,1)                (:128)        x_s = x[node_perm]                      (row gather)
+mask Linear over cat([x_i,x_j])   (:146-152, mask_aggr)   [P|Q|XW] = x_s [W_i;W_j;W_x]^T + [b;0;b_post]  (G1, tcgen05)
+dropout + A scatters + degree     (:157-179)              Z = K1(P, Q)      raw aggregates [N, A*F]
+S cumulative scalers, cat, post Linear (:181-196,132-133) H = Z W_eff(deg)^T + XW   (G2: grouped tcgen05 GEMM,
+                                                            one effective weight per equal-degree row range)
+lin                                (:136)                  out[node_perm[r]] = H[r] W_lin^T + b   (G3, row scatter fused
+                                                            in the epilogue)
+autograd backward                  (mma.py:157)            dgrad = same GEMM kernel on transposed weights, wgrad =
+                                                            split-K tcgen05 kernel + fixed-order slab reduction,
+                                                            K1 destination pass + transpose-CSR pass (no atomics)
+
+cat([x, out]) @ W_post^T is split as x W_x^T + Y W_y^T, and x W_x^T rides along in G1 (x is read once).
+The GEMMs are 3xTF32 (fp32-accurate, see csrc/gemm_tf32x3.cu).  No CPU path.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from . import tc_gemm as tg
+from .functional import cumulative_scale_factors
+from .graph import Graph
+
+
+class PostPlan:
+    """Row ranges of equal in-degree (graph.buckets) -> tile / slab tables of the grouped GEMMs."""
+
+    def __init__(self, graph: Graph, scalers: Sequence[str], avg_deg: Dict[str, float], min_rows: int, Fo: int, K: int):
+        dev = graph.device
+        degs = [d for d, _, _ in graph.buckets]
+        self.S = len(scalers)
+        self.cum = cumulative_scale_factors(scalers, avg_deg, degs).to(dev)           # [S, n_buckets]
+        big, tiles, tiles_t, slabs, seg_ptr, tail_rows, tail_b = [], [], [], [], [0], [], []
+        for b, (_, lo, hi) in enumerate(graph.buckets):
+            if hi - lo >= min_rows:
+                i = len(big)
+                big.append(b)
+                for r in range(lo, hi, tg.BM):
+                    tiles.append((r, hi, i * Fo, 0))
+                    tiles_t.append((r, hi, i * K, 0))
+                for r in range(lo, hi, tg.MAX_SLAB_ROWS):
+                    slabs.append((r, min(hi, r + tg.MAX_SLAB_ROWS), len(slabs), 0))
+                seg_ptr.append(len(slabs))
+            else:
+                tail_rows.append(torch.arange(lo, hi, dtype=torch.int64))
+                tail_b.append(torch.full((hi - lo,), b, dtype=torch.int64))
+        i32 = lambda rows: torch.tensor(rows, dtype=torch.int32, device=dev).reshape(-1, 4)
+        self.big = big
+        self.cum_big = self.cum[:, big].contiguous() if big else None                 # [S, B]
+        self.tile_tab, self.tile_tab_t, self.slabs = i32(tiles), i32(tiles_t), i32(slabs)
+        self.seg_ptr = torch.tensor(seg_ptr, dtype=torch.int32, device=dev)
+        self.tail_idx = torch.cat(tail_rows).to(dev) if tail_rows else None
+        self.tail_bucket = torch.cat(tail_b).to(dev) if tail_b else None
+
+
+def post_plan(graph: Graph, scalers, avg_deg, min_rows: int, Fo: int, K: int) -> PostPlan:
+    key = ("tc", tuple(scalers), float(avg_deg["log"]), float(avg_deg["lin"]), int(min_rows), int(Fo), int(K))
+    plans = graph.__dict__.setdefault("_post_plans", {})
+    p = plans.get(key)
+    if p is None:
+        p = plans[key] = PostPlan(graph, scalers, avg_deg, min_rows, Fo, K)
+    return p
+
+
+def _k1_fwd(graph: Graph, P: Tensor, Q: Tensor, R: Optional[Tensor], keep: Optional[Tensor], F: int,
+            akinds: Tuple[int, ...], p_drop: float, seed: int):
+    dev = P.device
+    n, A = graph.n_dst, len(akinds)
+    Z = torch.empty((n, A * F), dtype=torch.float32, device=dev)
+    has_min, has_max = 2 in akinds, 3 in akinds
+    need_sq = 4 in akinds or 5 in akinds
+    arg_min = torch.empty((n, F), dtype=torch.int32, device=dev) if has_min else None
+    arg_max = torch.empty((n, F), dtype=torch.int32, device=dev) if has_max else None
+    mean = torch.empty((n, F), dtype=torch.float32, device=dev) if need_sq else None
+    var = torch.empty((n, F), dtype=torch.float32, device=dev) if need_sq else None
+    ak, sk = _lib.i32_array(akinds), _lib.i32_array((0,))
+    with _lib.kernel_scope("mmconv_aggregate_fwd", dev):
+        _lib.check(_lib.lib().mmconv_aggregate_fwd(
+            _lib.ptr(graph.rowptr), _lib.ptr(graph.col), _lib.ptr(graph.perm), _lib.ptr(graph.gid), graph.E_total,
+            None, n, graph.E, _lib.ptr(P), P.stride(0), _lib.ptr(Q), Q.stride(0),
+            _lib.ptr(R), 0 if R is None else R.stride(0), _lib.ptr(keep), 0 if keep is None else keep.stride(0),
+            float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, 1, F, A, ak, 1, sk, None, 0,
+            _lib.ptr(Z), Z.stride(0), _lib.ptr(arg_min), _lib.ptr(arg_max), _lib.ptr(mean), _lib.ptr(var), 0, 0,
+            _lib.stream_ptr(dev)), "mmconv_aggregate_fwd")
+    return Z, arg_min, arg_max, mean, var
+
+
+def _k1_bwd(graph: Graph, P, Q, R, keep, F, akinds, p_drop, seed, dZ, arg_min, arg_max, mean, var,
+            dPQ: Tensor, need_R: bool):
+    """dP -> dPQ[:, :F], dQ -> dPQ[:, F:2F]; returns dR (or None)."""
+    dev = dZ.device
+    n, E, A = graph.n_dst, graph.E, len(akinds)
+    if E == 0:
+        dPQ.zero_()
+        return torch.zeros_like(R) if need_R else None
+    graph.build_transpose()
+    G = torch.empty((E, F), dtype=torch.float32, device=dev)
+    gslot = graph.perm if need_R else graph.csr2csc
+    ak, sk = _lib.i32_array(akinds), _lib.i32_array((0,))
+    l = _lib.lib()
+    dP, dQ = dPQ[:, :F], dPQ[:, F:2 * F]
+    with _lib.kernel_scope("mmconv_aggregate_bwd_dst", dev):
+        _lib.check(l.mmconv_aggregate_bwd_dst(
+            _lib.ptr(graph.rowptr), _lib.ptr(graph.col), _lib.ptr(graph.perm), _lib.ptr(graph.gid), graph.E_total,
+            None, n, E, _lib.ptr(P), P.stride(0), _lib.ptr(Q), Q.stride(0),
+            _lib.ptr(R), 0 if R is None else R.stride(0), _lib.ptr(keep), 0 if keep is None else keep.stride(0),
+            float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, 1, F, A, ak, 1, sk, None, 0,
+            _lib.ptr(dZ), dZ.stride(0), _lib.ptr(arg_min), _lib.ptr(arg_max), _lib.ptr(mean), _lib.ptr(var),
+            _lib.ptr(gslot), _lib.ptr(G), F, _lib.ptr(dP), dPQ.stride(0), 0, 0, _lib.stream_ptr(dev)),
+            "mmconv_aggregate_bwd_dst")
+    idx = graph.perm_t if need_R else None
+    with _lib.kernel_scope("mma_segment_sum_rows", dev):
+        _lib.check(l.mma_segment_sum_rows(_lib.ptr(graph.colptr), _lib.ptr(idx), None, graph.n_src, _lib.ptr(G), F, F,
+                                          _lib.ptr(dQ), dPQ.stride(0), _lib.stream_ptr(dev)), "mma_segment_sum_rows")
+    return G if need_R else None
+
+
+class _FusedMMAConv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, W1, b1, Wy, Wlin, blin, R, keep, graph: Graph, plan: PostPlan, cfg):
+        F, Fo, akinds, p_drop, seed = cfg
+        dev = _lib.require_cuda(x, W1, Wy, Wlin)
+        n = graph.n_dst
+        A, S = len(akinds), plan.S
+        K = A * F
+        x_s = x.index_select(0, graph.node_perm)
+        W1hi, W1lo = tg.split_weight(W1)
+        PQX = tg.linear(x_s, W1hi, W1lo, 2 * F + Fo, bias=b1, name="gemm_mask_proj")              # [n, 2F+Fo]
+        P, Q, XW = PQX[:, :F], PQX[:, F:2 * F], PQX[:, 2 * F:]
+        Z, arg_min, arg_max, mean, var = _k1_fwd(graph, P, Q, R, keep, F, akinds, p_drop, seed)
+        H = torch.empty((n, Fo), dtype=torch.float32, device=dev)
+        Ws = Wy.view(Fo, S, K)
+        Weff = None
+        if plan.big:
+            Weff = torch.einsum("sb,osk->bok", plan.cum_big, Ws).contiguous()                       # [B, Fo, K]
+            hi, lo = tg.split_weight(Weff.view(-1, K))
+            tg.linear(Z, hi, lo, Fo, tile_tab=plan.tile_tab, out=H, add=XW, name="gemm_post_grouped")
+        if plan.tail_idx is not None:
+            Zt = Z.index_select(0, plan.tail_idx)
+            ct = plan.cum[:, plan.tail_bucket].t()                                                  # [nt, S]
+            Yt = (Zt.unsqueeze(1) * ct.unsqueeze(2)).reshape(Zt.shape[0], S * K)
+            H.index_copy_(0, plan.tail_idx, Yt @ Wy.t() + XW.index_select(0, plan.tail_idx))
+        lhi, llo = tg.split_weight(Wlin)
+        out = torch.empty((n, Wlin.shape[0]), dtype=torch.float32, device=dev)
+        tg.linear(H, lhi, llo, Wlin.shape[0], bias=blin, out=out, out_map=graph.node_perm32, name="gemm_lin")
+        ctx.graph, ctx.plan, ctx.cfg = graph, plan, cfg
+        ctx.has_R = R is not None
+        ctx.save_for_backward(x_s, PQX, Z, H, W1, Wy, Wlin, Weff, R, keep, arg_min, arg_max, mean, var)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x_s, PQX, Z, H, W1, Wy, Wlin, Weff, R, keep, arg_min, arg_max, mean, var = ctx.saved_tensors
+        graph, plan = ctx.graph, ctx.plan
+        F, Fo, akinds, p_drop, seed = ctx.cfg
+        dev = d_out.device
+        n = graph.n_dst
+        A, S = len(akinds), plan.S
+        K = A * F
+        P, Q, XW = PQX[:, :F], PQX[:, F:2 * F], PQX[:, 2 * F:]
+        d_out = d_out.contiguous()
+        d_out_s = d_out.index_select(0, graph.node_perm)
+        # ---- lin
+        thi, tlo = tg.split_weight(Wlin.t())
+        dH = tg.linear(d_out_s, thi, tlo, Wlin.shape[1], name="gemm_lin_dgrad")                     # [n, Fo]
+        dWlin = tg.wgrad(d_out_s, H, name="gemm_lin_wgrad")
+        dblin = d_out.sum(0)
+        # ---- grouped post transform
+        dZ = torch.empty((n, K), dtype=torch.float32, device=dev)
+        dWy = None
+        if plan.big:
+            WeffT = Weff.transpose(1, 2).contiguous()                                               # [B, K, Fo]
+            hi, lo = tg.split_weight(WeffT.view(-1, Fo))
+            tg.linear(dH, hi, lo, K, tile_tab=plan.tile_tab_t, out=dZ, name="gemm_post_dgrad")
+            part = tg.wgrad_partials(dH, Z, plan.slabs, plan.slabs.shape[0], name="gemm_post_wgrad")
+            dWeff = tg.reduce_slabs_segmented(part, plan.seg_ptr)                                   # [B, Fo, K]
+            dWy = torch.einsum("sb,bok->osk", plan.cum_big, dWeff).reshape(Fo, S * K)
+        if plan.tail_idx is not None:
+            ti = plan.tail_idx
+            Zt = Z.index_select(0, ti)
+            ct = plan.cum[:, plan.tail_bucket].t()
+            dHt = dH.index_select(0, ti)
+            dYt = (dHt @ Wy).view(-1, S, K)
+            dZ.index_copy_(0, ti, (dYt * ct.unsqueeze(2)).sum(dim=1))
+            Yt = (Zt.unsqueeze(1) * ct.unsqueeze(2)).reshape(Zt.shape[0], S * K)
+            g = dHt.t() @ Yt
+            dWy = g if dWy is None else dWy + g
+        # ---- K1 backward: dP, dQ (and dR)
+        dPQ = torch.empty((n, 2 * F), dtype=torch.float32, device=dev)
+        need_R = ctx.has_R and ctx.needs_input_grad[6]
+        dR = _k1_bwd(graph, P, Q, R, keep, F, akinds, p_drop, seed, dZ, arg_min, arg_max, mean, var, dPQ, need_R)
+        del dZ
+        # ---- mask projection: dx (scattered back to node order), dW1, db1
+        w1hi, w1lo = tg.split_weight(W1.t())
+        dx = torch.empty((n, W1.shape[1]), dtype=torch.float32, device=dev)
+        if (2 * F) % 128 == 0:
+            tg.linear(dPQ, w1hi, w1lo, W1.shape[1], A1=dH, out=dx, out_map=graph.node_perm32, name="gemm_mask_dgrad")
+            dW1 = tg.wgrad(dPQ, x_s, G1=dH, name="gemm_mask_wgrad")
+        else:
+            dPQX = torch.cat([dPQ, dH], dim=1)
+            tg.linear(dPQX, w1hi, w1lo, W1.shape[1], out=dx, out_map=graph.node_perm32, name="gemm_mask_dgrad")
+            dW1 = tg.wgrad(dPQX, x_s, name="gemm_mask_wgrad")
+        db1 = torch.cat([dPQ.sum(0), dH.sum(0)])
+        return dx, dW1, db1, dWy, dWlin, dblin, dR, None, None, None, None
+
+
+def supported(F_in: int, F_out: int, out_channels: int) -> bool:
+    """Shapes the TMA-fed GEMMs accept (16-byte aligned rows); anything else uses the torch.mm path."""
+    return F_in % 4 == 0 and F_out % 4 == 0 and out_channels % 4 == 0
+
+
+def fused_mmaconv(x: Tensor, graph: Graph, *, W_mask: Tensor, b_mask: Optional[Tensor], W_post: Tensor,
+                  b_post: Optional[Tensor], W_lin: Tensor, b_lin: Optional[Tensor], R: Optional[Tensor],
+                  keep: Optional[Tensor], aggregators: Sequence[str], scalers: Sequence[str],
+                  avg_deg: Dict[str, float], p_drop: float, seed: int, min_rows: int) -> Tensor:
+    """x [N, F] (node order) -> MMAConv output [N, out] for towers == 1, pre_layers == post_layers == 1.
+    W_mask [F, 2F or 3F] (the live mask Linear, Q2), W_post [Fo, (S*A+1)*F], W_lin [out, Fo]."""
+    if graph.node_perm is None or graph.buckets is None:
+        raise RuntimeError("fused_mmaconv needs a Graph built with sort_rows=True, relabel=True")
+    F = x.shape[1]
+    Fo = W_post.shape[0]
+    akinds = tuple(_lib.AGGR_KINDS[a] for a in aggregators)
+    dev = x.device
+    zeros = lambda k: torch.zeros(k, dtype=torch.float32, device=dev)
+    W1 = torch.cat([W_mask[:, :F], W_mask[:, F:2 * F], W_post[:, :F]], dim=0)                        # [2F+Fo, F]
+    b1 = torch.cat([b_mask if b_mask is not None else zeros(F), zeros(F),
+                    b_post if b_post is not None else zeros(Fo)])
+    Wy = W_post[:, F:]
+    plan = post_plan(graph, scalers, avg_deg, min_rows, Fo, len(akinds) * F)
+    blin = b_lin if b_lin is not None else zeros(W_lin.shape[0])
+    return _FusedMMAConv.apply(x, W1, b1, Wy.contiguous(), W_lin, blin, R, keep, graph, plan,
+                               (F, Fo, akinds, float(p_drop), int(seed)))

@@ -37,6 +37,7 @@ from torch import Tensor
 from torch.nn import ModuleList, ReLU, Sequential
 
 from .. import functional as MF
+from .. import fused_layer
 from ..graph import Graph, cached_graph
 from ..parallel import ShardedGraph, sharded_mmconv_aggregate
 from ..linear import Linear, reset
@@ -105,6 +106,7 @@ class MMAConv(torch.nn.Module):
 
         self.lin = Linear(out_channels, out_channels)
 
+        self.use_tensor_cores = True         # towers == 1: whole layer as one autograd node over tcgen05 GEMMs + K1
         self.fold_scalers = True             # towers == 1: fold the scalers into the post weight (see _forward_folded)
         self.fold_min_rows = 512             # degree ranges smaller than this use the literal formula
         self.comm_slices = 2                 # feature windows of the sharded comm/compute pipeline
@@ -150,12 +152,12 @@ class MMAConv(torch.nn.Module):
             if not aggregator.startswith(ok):
                 raise ValueError(f'Unknown aggregator "{aggregator}".')
 
-    def _graph(self, edge_index, n: int, sort_rows: bool = False):
+    def _graph(self, edge_index, n: int, sort_rows: bool = False, relabel: bool = False):
         if isinstance(edge_index, (Graph, ShardedGraph)):
             return edge_index
         if not edge_index.is_cuda:
             raise RuntimeError("mma_b200.MMAConv needs CUDA tensors (no CPU fallback)")
-        return cached_graph(edge_index, n, sort_rows=sort_rows)
+        return cached_graph(edge_index, n, sort_rows=sort_rows, relabel=relabel)
 
     # ------------------------------------------------------------------ forward
     def forward(self, x: Tensor, edge_index, edge_attr: Optional[Tensor] = None) -> Tensor:
@@ -166,7 +168,11 @@ class MMAConv(torch.nn.Module):
             xt = x.view(-1, 1, F_in)            # towers share x; the repeat (:128) is never materialised
         n = xt.size(0)
         if T == 1 and self.fold_scalers and self.pre_layers == 1 and self.mask != "no_linear":
-            graph = self._graph(edge_index, n, sort_rows=True)
+            fused_ok = (self.use_tensor_cores and self.post_layers == 1 and
+                        fused_layer.supported(F_in, self.F_out, self.out_channels))
+            graph = self._graph(edge_index, n, sort_rows=True, relabel=fused_ok)
+            if fused_ok and isinstance(graph, Graph) and graph.node_perm is not None:
+                return self._forward_fused(xt[:, 0], graph, edge_attr)
             local = graph.local if isinstance(graph, ShardedGraph) else graph
             if local.buckets is not None and not (isinstance(graph, ShardedGraph) and edge_attr is not None):
                 return self._forward_folded(xt[:, 0], graph, edge_attr)
@@ -223,6 +229,29 @@ class MMAConv(torch.nn.Module):
             e = self.edge_encoder(edge_attr)                                        # [E, F_in], :143
             R = F.linear(e, W[:, :, 2 * F_in:].reshape(T * F_in, F_in))             # [E, T*F_in]
         return P, Q, R
+
+    def _forward_fused(self, x: Tensor, graph: Graph, edge_attr: Optional[Tensor]) -> Tensor:
+        """towers == 1 on a relabelled (degree-sorted) graph: the whole layer is one autograd node --
+        three tcgen05 3xTF32 GEMMs around K1, rows permuted only at entry and exit (fused_layer.py)."""
+        F_in = self.F_in
+        self._check_names()
+        for s_ in self.scalers:
+            if s_ not in ("identity", "amplification", "attenuation", "linear", "inverse_linear"):
+                raise ValueError(f'Unknown scaler "{s_}".')
+        live = self.pre_nns[self.aggregators[-1]][0][0].live()                      # Q2
+        R = None
+        if edge_attr is not None:
+            e = self.edge_encoder(edge_attr)                                        # [E, F_in], :143
+            R = F.linear(e, live.weight[:, 2 * F_in:])
+        keep = self._inject_keep
+        if keep is not None:
+            keep = keep.reshape(graph.E, F_in)
+        first = self.post_nns[0][0]
+        return fused_layer.fused_mmaconv(
+            x.contiguous(), graph, W_mask=live.weight, b_mask=live.bias, W_post=first.weight, b_post=first.bias,
+            W_lin=self.lin.weight, b_lin=self.lin.bias, R=R, keep=keep, aggregators=self.aggregators,
+            scalers=self.scalers, avg_deg=self.avg_deg, p_drop=self.dropout, seed=self._next_seed(),
+            min_rows=self.fold_min_rows)
 
     def _forward_folded(self, x: Tensor, graph: Graph, edge_attr: Optional[Tensor]) -> Tensor:
         """towers == 1 fast path: K1 emits the RAW aggregates Z [N, A*F_in] in degree-sorted row

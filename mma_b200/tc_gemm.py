@@ -1,0 +1,150 @@
+"""Thin wrappers over the tcgen05 3xTF32 GEMM entry points of the C ABI (include/mma_b200.h:
+mma_tf32_split, mma_linear_tf32x3, mma_wgrad_tf32x3, mma_reduce_slabs).
+
+They stand in for the reference's fp32 Linears (mask_aggr.py:68, mma_conv.py:132-136) and their
+autograd backward.  No CPU path: CPU tensors raise.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+BM = BN = 128
+BK = 32
+MODE = 0            # 0: 3xTF32 with the hi part written back (safe); 1: raw operand as hi; 2: plain TF32
+
+
+def usable(*mats: Optional[Tensor]) -> bool:
+    """TMA needs 16-byte aligned bases and row strides; everything else falls back to torch.mm."""
+    for t in mats:
+        if t is None:
+            continue
+        if (not t.is_cuda or t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1 or t.stride(0) % 4 != 0
+                or t.data_ptr() % 16 != 0 or t.shape[0] < 1 or t.shape[1] < 1):
+            return False
+    return True
+
+
+def split_weight(W: Tensor) -> Tuple[Tensor, Tensor]:
+    """(hi, lo) of a weight matrix, hi exactly representable in TF32."""
+    dev = _lib.require_cuda(W)
+    W = W.detach().contiguous()
+    hi, lo = torch.empty_like(W), torch.empty_like(W)
+    with _lib.kernel_scope("mma_tf32_split", dev):
+        _lib.check(_lib.lib().mma_tf32_split(_lib.ptr(W), _lib.ptr(hi), _lib.ptr(lo), W.numel(),
+                                             _lib.stream_ptr(dev)), "mma_tf32_split")
+    return hi, lo
+
+
+def linear(A0: Tensor, Whi: Tensor, Wlo: Tensor, n_out: int, *, A1: Optional[Tensor] = None,
+           tile_tab: Optional[Tensor] = None, out: Optional[Tensor] = None, out_map: Optional[Tensor] = None,
+           bias: Optional[Tensor] = None, add: Optional[Tensor] = None, mode: Optional[int] = None,
+           max_ctas: int = 0, name: str = "mma_linear_tf32x3") -> Tensor:
+    """out[out_map[r]] = [A0|A1][r] @ W[b_off : b_off + n_out].T (+ bias) (+ add[out_map[r]]).
+
+    Whi/Wlo: [b_rows, K0+K1] (stacked weights for a grouped GEMM; `tile_tab` int32 [tiles, 4] =
+    (row0, row_end, b_off, 0) selects the weight per 128-row tile)."""
+    dev = _lib.require_cuda(A0, Whi, Wlo)
+    M, K0 = A0.shape
+    K1 = 0 if A1 is None else A1.shape[1]
+    if not usable(A0, A1, Whi, Wlo, out, add):
+        raise RuntimeError("mma_linear_tf32x3: operands must be fp32, row-major, 16-byte aligned with ld % 4 == 0")
+    if Whi.shape != Wlo.shape or Whi.shape[1] != K0 + K1 or Whi.stride(0) != Wlo.stride(0):
+        raise RuntimeError(f"weight halves {tuple(Whi.shape)}/{tuple(Wlo.shape)} do not match K = {K0 + K1}")
+    if out is None:
+        out = torch.empty((M, n_out), dtype=torch.float32, device=dev)
+    if tile_tab is not None and (tile_tab.dtype != torch.int32 or tile_tab.dim() != 2 or tile_tab.shape[1] != 4
+                                 or not tile_tab.is_contiguous()):
+        raise RuntimeError("tile_tab must be a contiguous int32 [tiles, 4] tensor")
+    with _lib.kernel_scope(name, dev):
+        _lib.check(_lib.lib().mma_linear_tf32x3(
+            _lib.ptr(A0), A0.stride(0), K0, _lib.ptr(A1), 0 if A1 is None else A1.stride(0), K1,
+            _lib.ptr(Whi), _lib.ptr(Wlo), Whi.stride(0), Whi.shape[0], M, n_out,
+            _lib.ptr(tile_tab), 0 if tile_tab is None else tile_tab.shape[0],
+            _lib.ptr(out), out.stride(0), _lib.ptr(out_map), _lib.ptr(bias), _lib.ptr(add),
+            0 if add is None else add.stride(0), MODE if mode is None else mode, max_ctas,
+            _lib.stream_ptr(dev)), name)
+    return out
+
+
+MAX_SLAB_ROWS = 1024    # the tensor core truncates on accumulate: keep accumulation chains short (128 MMAs)
+
+
+def make_slabs(M: int, tiles: int, device, sms: int = 148, waves: int = 2, max_rows: int = MAX_SLAB_ROWS) -> Tensor:
+    """Cuts the reduction rows [0, M) into slabs (multiples of 32 rows, at most `max_rows`) so that
+    slabs x tiles fills at least `waves` waves of persistent CTAs; int32 [n_slabs, 4] = (row0, row_end, slot, 0)."""
+    n_slabs = max(1, min((sms * waves + tiles - 1) // tiles, (M + BK - 1) // BK))
+    rows = min(((M + n_slabs - 1) // n_slabs + BK - 1) // BK * BK, max_rows)
+    tab = []
+    r = 0
+    while r < M:
+        tab.append((r, min(M, r + rows), len(tab), 0))
+        r += rows
+    return torch.tensor(tab, dtype=torch.int32, device=device)
+
+
+def wgrad_partials(G0: Tensor, A: Tensor, slabs: Tensor, n_slots: int, *, G1: Optional[Tensor] = None,
+                   mode: Optional[int] = None, max_ctas: int = 0, name: str = "mma_wgrad_tf32x3") -> Tensor:
+    """part[slot] = [G0|G1][rows of the slab].T @ A[rows of the slab]  -> [n_slots, N0+N1, K]."""
+    dev = _lib.require_cuda(G0, A, slabs)
+    M, N0 = G0.shape
+    N1 = 0 if G1 is None else G1.shape[1]
+    K = A.shape[1]
+    if not usable(G0, G1, A) or A.shape[0] != M or K % 4 != 0:
+        raise RuntimeError("mma_wgrad_tf32x3: operands must be fp32, row-major, 16-byte aligned with ld % 4 == 0")
+    part = torch.empty((n_slots, N0 + N1, K), dtype=torch.float32, device=dev)
+    with _lib.kernel_scope(name, dev):
+        _lib.check(_lib.lib().mma_wgrad_tf32x3(
+            _lib.ptr(G0), G0.stride(0), N0, _lib.ptr(G1), 0 if G1 is None else G1.stride(0), N1,
+            _lib.ptr(A), A.stride(0), K, M, _lib.ptr(slabs), slabs.shape[0], _lib.ptr(part),
+            MODE if mode is None else mode, max_ctas, _lib.stream_ptr(dev)), name)
+    return part
+
+
+def reduce_slabs(part: Tensor, coef: Optional[Tensor] = None) -> Tensor:
+    dev = _lib.require_cuda(part)
+    n_slots = part.shape[0]
+    out = torch.empty(part.shape[1:], dtype=torch.float32, device=dev)
+    with _lib.kernel_scope("mma_reduce_slabs", dev):
+        _lib.check(_lib.lib().mma_reduce_slabs(_lib.ptr(part), _lib.ptr(coef), n_slots, out.numel(), _lib.ptr(out),
+                                               _lib.stream_ptr(dev)), "mma_reduce_slabs")
+    return out
+
+
+def reduce_slabs_segmented(part: Tensor, seg_ptr: Tensor) -> Tensor:
+    """out[g] = sum of part[seg_ptr[g] : seg_ptr[g+1]] (fixed ascending order) -> [n_segs, *part.shape[1:]]."""
+    dev = _lib.require_cuda(part, seg_ptr)
+    n_segs = seg_ptr.numel() - 1
+    out = torch.empty((n_segs,) + tuple(part.shape[1:]), dtype=torch.float32, device=dev)
+    n = part[0].numel() if part.shape[0] else 0
+    with _lib.kernel_scope("mma_reduce_slabs", dev):
+        _lib.check(_lib.lib().mma_reduce_slabs_segmented(_lib.ptr(part), _lib.ptr(seg_ptr), n_segs, n, _lib.ptr(out),
+                                                         _lib.stream_ptr(dev)), "mma_reduce_slabs_segmented")
+    return out
+
+
+_SLAB_CACHE = {}
+
+
+def cached_slabs(M: int, tiles: int, device) -> Tensor:
+    key = (int(M), int(tiles), str(device))
+    t = _SLAB_CACHE.get(key)
+    if t is None:
+        if len(_SLAB_CACHE) > 64:
+            _SLAB_CACHE.clear()
+        t = _SLAB_CACHE[key] = make_slabs(M, tiles, device)
+    return t
+
+
+def wgrad(G0: Tensor, A: Tensor, *, G1: Optional[Tensor] = None, mode: Optional[int] = None,
+          name: str = "mma_wgrad_tf32x3") -> Tensor:
+    """dW [N0+N1, K] = [G0|G1].T @ A  (split-K over slabs + fixed-order reduction)."""
+    N = G0.shape[1] + (0 if G1 is None else G1.shape[1])
+    tiles = ((N + BM - 1) // BM) * ((A.shape[1] + BN - 1) // BN)
+    slabs = cached_slabs(G0.shape[0], tiles, G0.device)
+    part = wgrad_partials(G0, A, slabs, slabs.shape[0], G1=G1, mode=mode, name=name)
+    return reduce_slabs(part)

@@ -220,10 +220,11 @@ def _load_weights(conv, w):
         conv.lin.weight.copy_(w["lin"][0]); conv.lin.bias.copy_(w["lin"][1])
 
 
-@pytest.mark.parametrize("name,fold", [("mmaconv_zinc.pt", None), ("mmaconv_t1_noedge.pt", 512),
-                                       ("mmaconv_t1_noedge.pt", 2), ("mmaconv_t1_noedge.pt", 0),
-                                       ("mmaconv_divide_prepost2.pt", None)])
-def test_mmaconv_layer_vs_reference_golden(name, fold):
+@pytest.mark.parametrize("name,fold,tc", [("mmaconv_zinc.pt", None, False), ("mmaconv_t1_noedge.pt", 512, False),
+                                          ("mmaconv_t1_noedge.pt", 2, False), ("mmaconv_t1_noedge.pt", 0, False),
+                                          ("mmaconv_t1_noedge.pt", 512, True), ("mmaconv_t1_noedge.pt", 1, True),
+                                          ("mmaconv_divide_prepost2.pt", None, False)])
+def test_mmaconv_layer_vs_reference_golden(name, fold, tc):
     """Whole drop-in layer (fwd + all gradients) against the verbatim reference's outputs.
     fold: towers == 1 only -- 0 = materialised scaler blocks, k = scalers folded into the post weight
     with degree ranges of >= k rows as one GEMM each (512: everything through the literal tail path)."""
@@ -233,6 +234,7 @@ def test_mmaconv_layer_vs_reference_golden(name, fold):
     conv = MMAConv(deg=gd["deg_hist"], **gd["ctor"]).cuda()
     if fold is not None:
         conv.fold_scalers, conv.fold_min_rows = fold > 0, max(fold, 1)
+    conv.use_tensor_cores = tc      # tc: the whole layer as one autograd node over the tcgen05 3xTF32 GEMMs
     _load_weights(conv, gd["weights"])
     assert conv.avg_deg == gd["weights"]["avg_deg"]
     x = gd["x"].cuda().requires_grad_()
@@ -285,8 +287,8 @@ def test_mmaconv_api_and_errors():
     assert not torch.equal(a, b) and torch.equal(a, c)
 
 
-@pytest.mark.parametrize("edge_dim", [None, 6])
-def test_folded_post_transform_vs_oracle(edge_dim):
+@pytest.mark.parametrize("edge_dim,tc", [(None, False), (6, False), (None, True), (6, True)])
+def test_folded_post_transform_vs_oracle(edge_dim, tc):
     """towers == 1 fast path (raw aggregates in degree-sorted rows + per-degree effective post
     weight) on a graph with many distinct degrees, vs the op-for-op oracle of the reference."""
     from mma_b200 import MMAConv
@@ -301,6 +303,7 @@ def test_folded_post_transform_vs_oracle(edge_dim):
     aggr, scal = ["mean", "sum", "min", "max"], ["identity", "amplification", "attenuation", "linear", "inverse_linear"]
     conv = MMAConv(Fd, Fd, aggr, scal, hist, edge_dim=edge_dim, towers=1).cuda()
     conv.fold_min_rows = 16
+    conv.use_tensor_cores = tc
     x = torch.randn(n, Fd, generator=g)
     ea = torch.randn(E, edge_dim, generator=g) if edge_dim else None
     keep = (torch.rand(E, 1, Fd, generator=g) < 0.5).float() * 2
