@@ -226,6 +226,11 @@ def fused_mmaconv(x: Tensor, graph: Graph, *, W_mask: Tensor, b_mask: Optional[T
         raise RuntimeError("fused_mmaconv needs a Graph built with sort_rows=True, relabel=True")
     F = x.shape[1]
     Fo = W_post.shape[0]
+    for a in aggregators:                       # aggregate(), mma_conv.py:164-177: exact names only
+        if a not in _lib.AGGR_KINDS:
+            raise ValueError(f'Unknown aggregator "{a}".')
+    if len(aggregators) > _lib.MAX_AGGR or len(scalers) > _lib.MAX_SCALER:
+        raise _lib.MMAError("more than 8 aggregators or scalers in one call")
     akinds = tuple(_lib.AGGR_KINDS[a] for a in aggregators)
     dev = x.device
     zeros = lambda k: torch.zeros(k, dtype=torch.float32, device=dev)
