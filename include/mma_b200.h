@@ -91,18 +91,26 @@ int mma_invert_perm(const int32_t *perm, int64_t E, int32_t *inv, mma_stream_t s
  *                       the CSR rows are a permutation of the nodes (degree-sorted rows for the
  *                       bucketed post-transform); all other per-row tensors are in CSR row order.
  *                       NULL = identity.
+ *   rng_row [n_rows], rng_row0 : id of CSR row r in the dropout stream = rng_row0 + (rng_row ? rng_row[r] : r);
+ *                       pass the GLOBAL destination node id (row permutation / relabelling / shard
+ *                       offset undone) and the stream does not depend on how the rows are laid out.
  *   P [n_rows, F] ld ldp | Q [n_src, F] ld ldq | R [E, F] ld ldr, ORIGINAL edge order | any may be NULL
  *   keep [E, F] ld ldk : explicit keep-scale (0 or 1/(1-p)), original edge order, or NULL
  *   p_drop, seed      : if keep == NULL and p_drop > 0: in-kernel Philox4x32-10 dropout keyed by
- *                       (seed, original edge id, column) -- identical in fwd/bwd and across shards;
- *                       p is quantised to round(256 p)/256 (exact for the reference's 0.5 / 0.75)
+ *                       (seed, row id, position of the edge in the row's in-edge list, column) --
+ *                       identical in fwd/bwd and across shards (the CSR sort is stable, so the in-row
+ *                       position is layout-invariant); p is quantised to round(256 p)/256 (exact for
+ *                       the reference's 0.5 / 0.75); p = 0.5 consumes one random bit per element,
+ *                       any other p one byte (mma_dropout_keep_scale_rows materialises the stream)
  *   aggr_kinds (host) [A], scaler_kinds (host) [S]
  *   scale_tab [4, tab_stride] : factor of scaler kind k (1..4) at clamped degree d is
  *                       scale_tab[(k-1)*tab_stride + d], d <= tab_stride-1 (built by the
  *                       caller with the reference's own expression, mma_conv.py:185-191);
  *                       may be NULL when all scalers are identity
  *   Y [n_rows, T, S*A*F_in] ld ldy
- *   arg_min/arg_max [n_rows, F] int32 : ORIGINAL edge id of the selected edge (E if none); NULL ok
+ *   arg_min/arg_max [n_rows, F] int32 : ORIGINAL (global) edge id of the selected edge (E_total if
+ *                       none); with MMA_K1_ARGS_LOCAL in `flags`: its CSR slot instead (what the
+ *                       backward of the same graph needs; saves the perm lookups).  NULL ok
  *   stat_mean/stat_var [n_rows, F] : saved for the var/std backward; NULL ok
  *   col0, ncols : process only the column window [col0, col0+ncols) of F (ncols <= 0: all columns).
  *                       Every tensor is still addressed with GLOBAL column indices, so windows of one
@@ -110,8 +118,11 @@ int mma_invert_perm(const int32_t *perm, int64_t E, int32_t *inv, mma_stream_t s
  *                       and produce exactly the unsliced result (the dropout stream is keyed by the
  *                       global column).
  * ---------------------------------------------------------------------- */
+#define MMA_K1_ARGS_LOCAL 1   /* flags: arg_min/arg_max hold CSR slots, not original edge ids */
+
 int mmconv_aggregate_fwd(const int32_t *rowptr, const int32_t *col, const int32_t *perm,
                          const int32_t *edge_gid, int64_t E_total, const int32_t *row_map,
+                         const int32_t *rng_row, int64_t rng_row0,
                          int64_t n_rows, int64_t E,
                          const float *P, int64_t ldp, const float *Q, int64_t ldq,
                          const float *R, int64_t ldr, const float *keep, int64_t ldk,
@@ -120,7 +131,8 @@ int mmconv_aggregate_fwd(const int32_t *rowptr, const int32_t *col, const int32_
                          int S, const int32_t *scaler_kinds,
                          const float *scale_tab, int64_t tab_stride,
                          float *Y, int64_t ldy, int32_t *arg_min, int32_t *arg_max,
-                         float *stat_mean, float *stat_var, int col0, int ncols, mma_stream_t stream);
+                         float *stat_mean, float *stat_var, int col0, int ncols, int flags,
+                         mma_stream_t stream);
 
 /* K1 backward, destination pass (replaces autograd of mma_conv.py:157-196):
  *   G[gslot(pos), c] = dL/dm_pre[e, c]   for every edge (row of the per-edge gradient),
@@ -129,7 +141,8 @@ int mmconv_aggregate_fwd(const int32_t *rowptr, const int32_t *col, const int32_
  * original edge order == dL/dR).  arg_min/arg_max/stat_* are the forward's outputs. */
 int mmconv_aggregate_bwd_dst(const int32_t *rowptr, const int32_t *col, const int32_t *perm,
                              const int32_t *edge_gid, int64_t E_total, const int32_t *row_map,
-                         int64_t n_rows, int64_t E,
+                             const int32_t *rng_row, int64_t rng_row0,
+                             int64_t n_rows, int64_t E,
                              const float *P, int64_t ldp, const float *Q, int64_t ldq,
                              const float *R, int64_t ldr, const float *keep, int64_t ldk,
                              float p_drop, uint64_t seed,
@@ -140,7 +153,7 @@ int mmconv_aggregate_bwd_dst(const int32_t *rowptr, const int32_t *col, const in
                              const int32_t *arg_min, const int32_t *arg_max,
                              const float *stat_mean, const float *stat_var,
                              const int32_t *gslot, float *G, int64_t ldg,
-                             float *dP, int64_t lddp, int col0, int ncols, mma_stream_t stream);
+                             float *dP, int64_t lddp, int col0, int ncols, int flags, mma_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * K3 / transpose pass: deterministic segmented row sum (CSR SpMM)
@@ -196,11 +209,17 @@ int mma_nc_aggregate_bwd_src(const int32_t *colptr, const int32_t *row, const in
                              const float *gS, float *dQA, int64_t lddqa, float *dXnbr, int64_t lddx,
                              mma_stream_t stream);
 
-/* Materialises the in-kernel Philox dropout keep-scale (0 or 1/(1-p)) for
- * `stream_id` (0 for K1; the aggregator slot a for K2) as [E, F] floats, so that
- * tests can inject the identical mask into the CPU oracle. */
+/* Materialises K2's in-kernel Philox dropout keep-scale (0 or 1/(1-p)), keyed by (edge id,
+ * column, stream_id = aggregator slot a), as [E, F] floats, so that tests can inject the
+ * identical mask into the CPU oracle. */
 int mma_dropout_keep_scale(float p_drop, uint64_t seed, uint32_t stream_id,
                            int64_t E, int F, float *out, int64_t ldo, mma_stream_t stream);
+
+/* The same for K1's row-keyed stream (see mmconv_aggregate_fwd): out[perm[k], c] for every CSR slot k
+ * of the destination CSR (rowptr, perm; perm NULL = identity), i.e. [E, F] in ORIGINAL edge order. */
+int mma_dropout_keep_scale_rows(const int32_t *rowptr, const int32_t *perm, const int32_t *rng_row,
+                                int64_t rng_row0, int64_t n_rows, int64_t E, float p_drop, uint64_t seed,
+                                int F, float *out, int64_t ldo, mma_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * G1-G4: the dense projections on the tcgen05 tensor cores, fp32-accurate by

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libmma_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_WORKSPACE = 0, -1, -2, -3, -4
 MAX_AGGR, MAX_SCALER = 8, 8
+K1_ARGS_LOCAL = 1        # flags of mmconv_aggregate_fwd / _bwd_dst: arg indices are CSR slots
 AGGR_KINDS = {"sum": 0, "mean": 1, "min": 2, "max": 3, "var": 4, "std": 5}
 SCALER_KINDS = {"identity": 0, "amplification": 1, "attenuation": 2, "linear": 3, "inverse_linear": 4}
 NC_COMBINE = {"sum": 0, "mean": 1, "max": 2, "min": 3, "none": 4}
@@ -29,12 +30,13 @@ _SIGS = {
     "mma_csr_build_workspace_bytes": ([_i64, _i64, C.POINTER(C.c_size_t)], C.c_int),
     "mma_csr_build": ([_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, C.c_size_t, _vp], C.c_int),
     "mma_invert_perm": ([_vp, _i64, _vp, _vp], C.c_int),
-    "mmconv_aggregate_fwd": ([_vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64,
-                              _f32, _u64, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _i64,
-                              _vp, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _vp], C.c_int),
-    "mmconv_aggregate_bwd_dst": ([_vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64,
-                                  _f32, _u64, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _i64,
-                                  _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i32, _i32, _vp], C.c_int),
+    "mmconv_aggregate_fwd": ([_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64,
+                              _vp, _i64, _f32, _u64, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _i64,
+                              _vp, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp], C.c_int),
+    "mmconv_aggregate_bwd_dst": ([_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64,
+                                  _vp, _i64, _f32, _u64, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _i64,
+                                  _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp],
+                                 C.c_int),
     "mma_segment_sum_rows": ([_vp, _vp, _vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp], C.c_int),
     "mma_nc_aggregate_fwd": ([_vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32,
                               _vp, _vp, _vp, _f32, _u64, _vp, _vp, _vp], C.c_int),
@@ -43,6 +45,7 @@ _SIGS = {
     "mma_nc_aggregate_bwd_src": ([_vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32,
                                   _vp, _vp, _f32, _u64, _vp, _vp, _i64, _vp, _i64, _vp], C.c_int),
     "mma_dropout_keep_scale": ([_f32, _u64, _u32, _i64, _i32, _vp, _i64, _vp], C.c_int),
+    "mma_dropout_keep_scale_rows": ([_vp, _vp, _vp, _i64, _i64, _i64, _f32, _u64, _i32, _vp, _i64, _vp], C.c_int),
     "mma_tf32_split": ([_vp, _vp, _vp, _i64, _vp], C.c_int),
     "mma_linear_tf32x3": ([_vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _i64,
                            _vp, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _vp], C.c_int),

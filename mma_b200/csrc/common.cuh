@@ -165,6 +165,46 @@ __device__ __forceinline__ Vec<VEC> dropout_keep(const Dropout &d, uint32_t eid,
     return keep_from_word<VEC>(d, w, c & 3);
 }
 
+// ---------------------------------------------------------------------------
+// K1's dropout stream is keyed by (destination node id, position of the edge inside that node's
+// in-edge list, column): the CSR is a STABLE sort by destination, so the in-row position of an edge
+// does not depend on how rows are permuted, relabelled or sharded -- forward, backward and every
+// shard regenerate the same bits, and a lane that owns 4 columns of a row generates exactly the bits
+// it consumes (no exchange between lanes).
+//   p == 0.5 (thr == 128, the reference's constant): ONE BIT per element.  Philox counter
+//     (row id, pos >> 5, column >> 2, 0): word v <-> column 4*(c>>2) + v, bit (pos & 31) <-> edge.
+//     keep iff the bit is set.  One call covers 32 edges x 4 columns.
+//   any other p: one BYTE per element.  Counter (row id, pos >> 2, column >> 2, 1): word v <-> column,
+//     byte (pos & 3) <-> edge; drop iff byte < thr.  One call covers 4 edges x 4 columns.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool dropout_one_bit(const Dropout &d) { return d.thr == 128u; }
+
+__device__ __forceinline__ uint4 row_rng_bits1(const Dropout &d, uint32_t row_id, uint32_t pos, uint32_t c) {
+    return philox4x32_10(make_uint4(row_id, pos >> 5, c >> 2, 0u), make_uint2(d.k0, d.k1));
+}
+__device__ __forceinline__ uint4 row_rng_bits8(const Dropout &d, uint32_t row_id, uint32_t pos, uint32_t c) {
+    return philox4x32_10(make_uint4(row_id, pos >> 2, c >> 2, 1u), make_uint2(d.k0, d.k1));
+}
+
+// keep-scale of VEC consecutive columns starting at c for in-row edge `pos` of row `row_id`
+// (slow per-edge form for the generic kernels; the fast kernels amortise the Philox call).
+template <int VEC>
+__device__ __forceinline__ Vec<VEC> dropout_keep_row(const Dropout &d, uint32_t row_id, uint32_t pos, int c) {
+    Vec<VEC> r;
+    const bool one = dropout_one_bit(d);
+    const uint4 b = one ? row_rng_bits1(d, row_id, pos, (uint32_t)c) : row_rng_bits8(d, row_id, pos, (uint32_t)c);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        const int ws = (c + v) & 3;                     // VEC > 1 implies c % VEC == 0: same Philox call
+        const uint32_t w = ws == 0 ? b.x : (ws == 1 ? b.y : (ws == 2 ? b.z : b.w));
+        bool keep;
+        if (one) keep = (w >> (pos & 31u)) & 1u;
+        else keep = ((w >> (8u * (pos & 3u))) & 0xFFu) >= d.thr;
+        r.v[v] = keep ? d.scale : 0.0f;
+    }
+    return r;
+}
+
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace mma

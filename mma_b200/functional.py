@@ -47,6 +47,45 @@ def _c(t: Optional[Tensor]) -> Optional[Tensor]:
 def _ld(t: Optional[Tensor]) -> int:
     return 0 if t is None else t.stride(0)
 
+def k1_forward(graph: Graph, P, Q, R, keep, *, T: int, F_in: int, akinds, skinds, tab, p_drop: float, seed: int,
+               Y: Tensor, arg_min, arg_max, mean, var, col0: int = 0, ncols: int = 0, local_args: bool = False,
+               q_ptr: Optional[int] = None, ldq: Optional[int] = None) -> None:
+    """One launch of mmconv_aggregate_fwd (include/mma_b200.h) on `graph`'s destination CSR.
+    q_ptr / ldq override Q's base pointer and leading dimension (column-window pipeline of the
+    sharded path: a narrow gathered window addressed with global column indices)."""
+    dev = graph.device
+    ak, sk = _lib.i32_array(akinds), _lib.i32_array(skinds)
+    with _lib.kernel_scope("mmconv_aggregate_fwd", dev):
+        _lib.check(_lib.lib().mmconv_aggregate_fwd(
+            _lib.ptr(graph.rowptr), _lib.ptr(graph.col), _lib.ptr(graph.perm), _lib.ptr(graph.gid), graph.E_total,
+            _lib.ptr(graph.row_map), _lib.ptr(graph.rng_row), int(graph.rng_row0), graph.n_dst, graph.E,
+            _lib.ptr(P), _ld(P), (_lib.ptr(Q) if q_ptr is None else q_ptr), (_ld(Q) if ldq is None else ldq),
+            _lib.ptr(R), _ld(R), _lib.ptr(keep), _ld(keep),
+            float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, T, F_in, len(akinds), ak, len(skinds), sk,
+            _lib.ptr(tab), 0 if tab is None else tab.shape[1],
+            _lib.ptr(Y), Y.stride(0), _lib.ptr(arg_min), _lib.ptr(arg_max), _lib.ptr(mean), _lib.ptr(var),
+            col0, ncols, _lib.K1_ARGS_LOCAL if local_args else 0, _lib.stream_ptr(dev)), "mmconv_aggregate_fwd")
+
+
+def k1_backward_dst(graph: Graph, P, Q, R, keep, *, T: int, F_in: int, akinds, skinds, tab, p_drop: float,
+                    seed: int, dY: Tensor, arg_min, arg_max, mean, var, gslot, G, ldg: int, dP, lddp: int,
+                    col0: int = 0, ncols: int = 0, local_args: bool = False, q_ptr: Optional[int] = None,
+                    ldq: Optional[int] = None) -> None:
+    """One launch of mmconv_aggregate_bwd_dst (destination pass of K1's backward)."""
+    dev = graph.device
+    ak, sk = _lib.i32_array(akinds), _lib.i32_array(skinds)
+    with _lib.kernel_scope("mmconv_aggregate_bwd_dst", dev):
+        _lib.check(_lib.lib().mmconv_aggregate_bwd_dst(
+            _lib.ptr(graph.rowptr), _lib.ptr(graph.col), _lib.ptr(graph.perm), _lib.ptr(graph.gid), graph.E_total,
+            _lib.ptr(graph.row_map), _lib.ptr(graph.rng_row), int(graph.rng_row0), graph.n_dst, graph.E,
+            _lib.ptr(P), _ld(P), (_lib.ptr(Q) if q_ptr is None else q_ptr), (_ld(Q) if ldq is None else ldq),
+            _lib.ptr(R), _ld(R), _lib.ptr(keep), _ld(keep),
+            float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, T, F_in, len(akinds), ak, len(skinds), sk,
+            _lib.ptr(tab), 0 if tab is None else tab.shape[1],
+            _lib.ptr(dY), dY.stride(0), _lib.ptr(arg_min), _lib.ptr(arg_max), _lib.ptr(mean), _lib.ptr(var),
+            _lib.ptr(gslot), _lib.ptr(G), ldg, _lib.ptr(dP), lddp, col0, ncols,
+            _lib.K1_ARGS_LOCAL if local_args else 0, _lib.stream_ptr(dev)), "mmconv_aggregate_bwd_dst")
+
 
 class _MMConvAggregate(torch.autograd.Function):
     """Y = fused gather + mask-add + dropout + multi-aggregate + cumulative scalers (K1)."""
@@ -69,17 +108,8 @@ class _MMConvAggregate(torch.autograd.Function):
         arg_max = torch.empty((n, F), dtype=torch.int32, device=dev) if has_max else None
         stat_mean = torch.empty((n, F), dtype=torch.float32, device=dev) if need_sq else None
         stat_var = torch.empty((n, F), dtype=torch.float32, device=dev) if need_sq else None
-        ak, sk = _lib.i32_array(akinds), _lib.i32_array(skinds)
-        perm = None if graph.perm is None else graph.perm
-        with _lib.kernel_scope("mmconv_aggregate_fwd", dev):
-            _lib.check(_lib.lib().mmconv_aggregate_fwd(
-                _lib.ptr(graph.rowptr), _lib.ptr(graph.col), _lib.ptr(perm), _lib.ptr(graph.gid), graph.E_total,
-                _lib.ptr(graph.row_map), n, graph.E,
-                _lib.ptr(P), _ld(P), _lib.ptr(Q), _ld(Q), _lib.ptr(R), _ld(R), _lib.ptr(keep), _ld(keep),
-                float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, T, F_in, A, ak, S, sk,
-                _lib.ptr(tab), 0 if tab is None else tab.shape[1],
-                _lib.ptr(Y), Y.stride(0), _lib.ptr(arg_min), _lib.ptr(arg_max),
-                _lib.ptr(stat_mean), _lib.ptr(stat_var), 0, 0, _lib.stream_ptr(dev)), "mmconv_aggregate_fwd")
+        k1_forward(graph, P, Q, R, keep, T=T, F_in=F_in, akinds=akinds, skinds=skinds, tab=tab, p_drop=p_drop,
+                   seed=seed, Y=Y, arg_min=arg_min, arg_max=arg_max, mean=stat_mean, var=stat_var)
         ctx.graph, ctx.cfg = graph, (T, F_in, akinds, skinds, p_drop, seed)
         ctx.has = (P is not None, Q is not None, R is not None)
         ctx.save_for_backward(P, Q, R, keep, tab, arg_min, arg_max, stat_mean, stat_var)
@@ -114,18 +144,10 @@ class _MMConvAggregate(torch.autograd.Function):
             graph.build_transpose()
             G = torch.empty((E, F), dtype=torch.float32, device=dev)
             gslot = graph.csr2csc
-        ak, sk = _lib.i32_array(akinds), _lib.i32_array(skinds)
         l = _lib.lib()
-        with _lib.kernel_scope("mmconv_aggregate_bwd_dst", dev):
-            _lib.check(l.mmconv_aggregate_bwd_dst(
-                _lib.ptr(graph.rowptr), _lib.ptr(graph.col), _lib.ptr(graph.perm), _lib.ptr(graph.gid),
-                graph.E_total, _lib.ptr(graph.row_map), n, E,
-                _lib.ptr(P), _ld(P), _lib.ptr(Q), _ld(Q), _lib.ptr(R), _ld(R), _lib.ptr(keep), _ld(keep),
-                float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, T, F_in, A, ak, S, sk,
-                _lib.ptr(tab), 0 if tab is None else tab.shape[1],
-                _lib.ptr(dY), dY.stride(0), _lib.ptr(arg_min), _lib.ptr(arg_max),
-                _lib.ptr(stat_mean), _lib.ptr(stat_var), _lib.ptr(gslot), _lib.ptr(G), F,
-                _lib.ptr(dP), F, 0, 0, _lib.stream_ptr(dev)), "mmconv_aggregate_bwd_dst")
+        k1_backward_dst(graph, P, Q, R, keep, T=T, F_in=F_in, akinds=akinds, skinds=skinds, tab=tab, p_drop=p_drop,
+                        seed=seed, dY=dY, arg_min=arg_min, arg_max=arg_max, mean=stat_mean, var=stat_var,
+                        gslot=gslot, G=G, ldg=F, dP=dP, lddp=F)
         dQ = None
         if need_Q:
             graph.build_transpose()
@@ -206,10 +228,22 @@ def segment_sum_rows(src: Tensor, ptr: Tensor, idx: Optional[Tensor], val: Optio
     return _SegmentSumRows.apply(src, ptr, idx, val, n_rows, ptr_t, idx_t, val_t)
 
 
-def dropout_keep_scale(p: float, seed: int, E: int, F: int, device, stream_id: int = 0) -> Tensor:
-    """The keep-scale tensor [E,F] (0 or 1/(1-p)) that the kernels generate on the fly for
-    (seed, stream_id) -- for injecting the identical dropout into the CPU oracle in tests."""
+def dropout_keep_scale(p: float, seed: int, E: int, F: int, device, stream_id: int = 0,
+                       graph: Optional[Graph] = None) -> Tensor:
+    """The keep-scale tensor [E,F] (0 or 1/(1-p), original edge order) that the kernels generate on
+    the fly -- for injecting the identical dropout into the CPU oracle in tests.  With `graph`: K1's
+    stream (keyed by destination row and in-row position); without: K2's stream for aggregator slot
+    `stream_id` (keyed by edge id)."""
     out = torch.empty((E, F), dtype=torch.float32, device=device)
+    if graph is not None:
+        if graph.E != E:
+            raise RuntimeError("graph has a different number of edges")
+        with torch.cuda.device(device):
+            _lib.check(_lib.lib().mma_dropout_keep_scale_rows(
+                _lib.ptr(graph.rowptr), _lib.ptr(graph.perm), _lib.ptr(graph.rng_row), int(graph.rng_row0),
+                graph.n_dst, E, float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, F, _lib.ptr(out), F,
+                _lib.stream_ptr(out.device)), "mma_dropout_keep_scale_rows")
+        return out
     with torch.cuda.device(device):
         _lib.check(_lib.lib().mma_dropout_keep_scale(float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream_id),
                                                      E, F, _lib.ptr(out), F, _lib.stream_ptr(out.device)),

@@ -25,6 +25,7 @@ from torch import Tensor
 
 from . import _lib
 from . import tc_gemm as tg
+from . import functional as MF
 from .functional import cumulative_scale_factors
 from .graph import Graph
 
@@ -80,15 +81,8 @@ def _k1_fwd(graph: Graph, P: Tensor, Q: Tensor, R: Optional[Tensor], keep: Optio
     arg_max = torch.empty((n, F), dtype=torch.int32, device=dev) if has_max else None
     mean = torch.empty((n, F), dtype=torch.float32, device=dev) if need_sq else None
     var = torch.empty((n, F), dtype=torch.float32, device=dev) if need_sq else None
-    ak, sk = _lib.i32_array(akinds), _lib.i32_array((0,))
-    with _lib.kernel_scope("mmconv_aggregate_fwd", dev):
-        _lib.check(_lib.lib().mmconv_aggregate_fwd(
-            _lib.ptr(graph.rowptr), _lib.ptr(graph.col), _lib.ptr(graph.perm), _lib.ptr(graph.gid), graph.E_total,
-            None, n, graph.E, _lib.ptr(P), P.stride(0), _lib.ptr(Q), Q.stride(0),
-            _lib.ptr(R), 0 if R is None else R.stride(0), _lib.ptr(keep), 0 if keep is None else keep.stride(0),
-            float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, 1, F, A, ak, 1, sk, None, 0,
-            _lib.ptr(Z), Z.stride(0), _lib.ptr(arg_min), _lib.ptr(arg_max), _lib.ptr(mean), _lib.ptr(var), 0, 0,
-            _lib.stream_ptr(dev)), "mmconv_aggregate_fwd")
+    MF.k1_forward(graph, P, Q, R, keep, T=1, F_in=F, akinds=akinds, skinds=(0,), tab=None, p_drop=p_drop, seed=seed,
+                  Y=Z, arg_min=arg_min, arg_max=arg_max, mean=mean, var=var, local_args=True)
     return Z, arg_min, arg_max, mean, var
 
 
@@ -103,18 +97,11 @@ def _k1_bwd(graph: Graph, P, Q, R, keep, F, akinds, p_drop, seed, dZ, arg_min, a
     graph.build_transpose()
     G = torch.empty((E, F), dtype=torch.float32, device=dev)
     gslot = graph.perm if need_R else graph.csr2csc
-    ak, sk = _lib.i32_array(akinds), _lib.i32_array((0,))
     l = _lib.lib()
     dP, dQ = dPQ[:, :F], dPQ[:, F:2 * F]
-    with _lib.kernel_scope("mmconv_aggregate_bwd_dst", dev):
-        _lib.check(l.mmconv_aggregate_bwd_dst(
-            _lib.ptr(graph.rowptr), _lib.ptr(graph.col), _lib.ptr(graph.perm), _lib.ptr(graph.gid), graph.E_total,
-            None, n, E, _lib.ptr(P), P.stride(0), _lib.ptr(Q), Q.stride(0),
-            _lib.ptr(R), 0 if R is None else R.stride(0), _lib.ptr(keep), 0 if keep is None else keep.stride(0),
-            float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, 1, F, A, ak, 1, sk, None, 0,
-            _lib.ptr(dZ), dZ.stride(0), _lib.ptr(arg_min), _lib.ptr(arg_max), _lib.ptr(mean), _lib.ptr(var),
-            _lib.ptr(gslot), _lib.ptr(G), F, _lib.ptr(dP), dPQ.stride(0), 0, 0, _lib.stream_ptr(dev)),
-            "mmconv_aggregate_bwd_dst")
+    MF.k1_backward_dst(graph, P, Q, R, keep, T=1, F_in=F, akinds=akinds, skinds=(0,), tab=None, p_drop=p_drop,
+                       seed=seed, dY=dZ, arg_min=arg_min, arg_max=arg_max, mean=mean, var=var, gslot=gslot, G=G,
+                       ldg=F, dP=dP, lddp=dPQ.stride(0), local_args=True)
     idx = graph.perm_t if need_R else None
     with _lib.kernel_scope("mma_segment_sum_rows", dev):
         _lib.check(l.mma_segment_sum_rows(_lib.ptr(graph.colptr), _lib.ptr(idx), None, graph.n_src, _lib.ptr(G), F, F,

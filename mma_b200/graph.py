@@ -69,6 +69,7 @@ class Graph:
         self.n_dst = int(n_dst)
         self.n_src = int(n_src if n_src is not None else n_dst)
         self.node_perm = self.node_perm32 = self.node_rank = None
+        self.rng_row, self.rng_row0 = None, 0      # id of CSR row r in K1's dropout stream: rng_row0 + rng_row[r]
         self.row_map = None                        # node id of each CSR row (None = identity)
         self.row_rank = None                       # CSR row of each node (inverse of row_map)
         self.buckets = None                        # [(degree, row_lo, row_hi)] when rows are degree-sorted
@@ -87,6 +88,7 @@ class Graph:
             self.buckets = [(int(d), int(h - c), int(h)) for d, c, h in zip(vals, counts, hi)]
             self._max_deg_hint = int(vals[0]) if vals else 0
             self.row_map = order.to(torch.int32).contiguous()
+            self.rng_row = self.row_map                # stream keyed by the ORIGINAL node id: layout-invariant
             self.row_rank = rank
             dst = rank.index_select(0, dst)
             if relabel:
@@ -149,6 +151,7 @@ class Graph:
         g.gid, g.E_total = None, g.E
         g.row_map = g.row_rank = g.buckets = None
         g.node_perm = g.node_perm32 = g.node_rank = None
+        g.rng_row, g.rng_row0 = None, 0
         g._t_built = False
         g.colptr = g.row_t = g.perm_t = g.csr2csc = None
         g._max_deg = None

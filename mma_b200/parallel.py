@@ -89,6 +89,7 @@ class ShardedGraph:
                       sort_rows=True)
             g.gid = gid.to(torch.int32).contiguous()
             g.E_total = self.E_total
+            g.rng_row0 = self.lo                      # dropout stream keyed by the GLOBAL destination node id
             self.local = g
         self._dst_local, self._gid = d, gid
 
@@ -200,14 +201,9 @@ class _ShardedAggregate(torch.autograd.Function):
             w = s_.stop - s_.start
             Qk = gathered[k]
             q_base = Qk.data_ptr() - 4 * s_.start       # virtual base: column c of the window's row j
-            with _lib.kernel_scope("mmconv_aggregate_fwd", dev):
-                _lib.check(_lib.lib().mmconv_aggregate_fwd(
-                    _lib.ptr(g.rowptr), _lib.ptr(g.col), _lib.ptr(g.perm), _lib.ptr(g.gid), g.E_total, _lib.ptr(g.row_map), n, g.E,
-                    _lib.ptr(P), P.stride(0), q_base, w, None, 0, None, 0,
-                    float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, 1, F_in, A, ak, S, sk,
-                    _lib.ptr(tab), 0 if tab is None else tab.shape[1], _lib.ptr(Y), Y.stride(0),
-                    _lib.ptr(arg_min), _lib.ptr(arg_max), _lib.ptr(mean), _lib.ptr(var),
-                    s_.start, w, _lib.stream_ptr(dev)), "mmconv_aggregate_fwd")
+            MF.k1_forward(g, P, None, None, None, T=1, F_in=F_in, akinds=akinds, skinds=skinds, tab=tab,
+                          p_drop=p_drop, seed=seed, Y=Y, arg_min=arg_min, arg_max=arg_max, mean=mean, var=var,
+                          col0=s_.start, ncols=w, q_ptr=q_base, ldq=w)
             Qk.record_stream(cur)
         ctx.sg, ctx.cfg = sg, (F_in, akinds, skinds, p_drop, seed, n_slices)
         ctx.save_for_backward(P, Q, tab, arg_min, arg_max, mean, var)
@@ -244,15 +240,10 @@ class _ShardedAggregate(torch.autograd.Function):
                 cur.wait_stream(comm)
                 Qk.record_stream(cur)
                 q_base = Qk.data_ptr() - 4 * s_.start
-            with _lib.kernel_scope("mmconv_aggregate_bwd_dst", dev):
-                _lib.check(l.mmconv_aggregate_bwd_dst(
-                    _lib.ptr(g.rowptr), _lib.ptr(g.col), _lib.ptr(g.perm), _lib.ptr(g.gid), g.E_total, _lib.ptr(g.row_map), n, E,
-                    _lib.ptr(P), P.stride(0), q_base, w, None, 0, None, 0,
-                    float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, 1, F_in, A, ak, S, sk,
-                    _lib.ptr(tab), 0 if tab is None else tab.shape[1], _lib.ptr(dY), dY.stride(0),
-                    _lib.ptr(arg_min), _lib.ptr(arg_max), _lib.ptr(mean), _lib.ptr(var),
-                    _lib.ptr(g.csr2csc), _lib.ptr(G), F_in, _lib.ptr(dP), F_in, s_.start, w,
-                    _lib.stream_ptr(dev)), "mmconv_aggregate_bwd_dst")
+            MF.k1_backward_dst(g, P, None, None, None, T=1, F_in=F_in, akinds=akinds, skinds=skinds, tab=tab,
+                               p_drop=p_drop, seed=seed, dY=dY, arg_min=arg_min, arg_max=arg_max, mean=mean, var=var,
+                               gslot=g.csr2csc, G=G, ldg=F_in, dP=dP, lddp=F_in, col0=s_.start, ncols=w,
+                               q_ptr=q_base, ldq=w)
             part = torch.empty((g.n_src, w), dtype=torch.float32, device=dev)
             with _lib.kernel_scope("mma_segment_sum_rows", dev):
                 _lib.check(l.mma_segment_sum_rows(_lib.ptr(g.colptr), None, None, g.n_src,

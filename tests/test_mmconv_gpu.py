@@ -159,7 +159,7 @@ def test_philox_dropout_matches_injected_mask():
     P, Q = torch.randn(n, F), torch.randn(n, F)
     g = mma_b200.Graph(src.cuda(), dst.cuda(), n)
     seed = 1234567
-    keep = mma_b200.dropout_keep_scale(p, seed, E, F, "cuda")
+    keep = mma_b200.dropout_keep_scale(p, seed, E, F, "cuda", graph=g)
     frac = (keep > 0).float().mean().item()
     assert abs(frac - (1 - p)) < 0.01 and set(keep.unique().tolist()) == {0.0, 2.0}
     Pg, Qg = P.cuda().requires_grad_(), Q.cuda().requires_grad_()
@@ -174,9 +174,9 @@ def test_philox_dropout_matches_injected_mask():
     b = torch.autograd.grad(ref, [Pr, Qr], gy)
     close(a[0], b[0], what="philox dP"); close(a[1], b[1], what="philox dQ")
     # different seeds / p
-    k2 = mma_b200.dropout_keep_scale(p, seed + 1, E, F, "cuda")
+    k2 = mma_b200.dropout_keep_scale(p, seed + 1, E, F, "cuda", graph=g)
     assert not torch.equal(keep, k2)
-    k3 = mma_b200.dropout_keep_scale(0.75, seed, E, F, "cuda")
+    k3 = mma_b200.dropout_keep_scale(0.75, seed, E, F, "cuda", graph=g)
     assert abs((k3 > 0).float().mean().item() - 0.25) < 0.01 and k3.max().item() == 4.0
 
 
