@@ -94,6 +94,11 @@ int mma_invert_perm(const int32_t *perm, int64_t E, int32_t *inv, mma_stream_t s
  *   rng_row [n_rows], rng_row0 : id of CSR row r in the dropout stream = rng_row0 + (rng_row ? rng_row[r] : r);
  *                       pass the GLOBAL destination node id (row permutation / relabelling / shard
  *                       offset undone) and the stream does not depend on how the rows are laid out.
+ *   row_chunks [n_chunks+1], n_chunks : optional work partition for the persistent kernels: chunk i
+ *                       is the CSR rows [row_chunks[i], row_chunks[i+1]) (ascending, row_chunks[0] = 0,
+ *                       row_chunks[n_chunks] = n_rows), chunks of about equal cost (edges + ~6 per row),
+ *                       many more chunks than SMs x 16 warps; they are dealt round-robin to the warps.
+ *                       NULL: one chunk per warp found by a binary search over rowptr (poorer balance).
  *   P [n_rows, F] ld ldp | Q [n_src, F] ld ldq | R [E, F] ld ldr, ORIGINAL edge order | any may be NULL
  *   keep [E, F] ld ldk : explicit keep-scale (0 or 1/(1-p)), original edge order, or NULL
  *   p_drop, seed      : if keep == NULL and p_drop > 0: in-kernel Philox4x32-10 dropout keyed by
@@ -123,6 +128,7 @@ int mma_invert_perm(const int32_t *perm, int64_t E, int32_t *inv, mma_stream_t s
 int mmconv_aggregate_fwd(const int32_t *rowptr, const int32_t *col, const int32_t *perm,
                          const int32_t *edge_gid, int64_t E_total, const int32_t *row_map,
                          const int32_t *rng_row, int64_t rng_row0,
+                         const int32_t *row_chunks, int64_t n_chunks,
                          int64_t n_rows, int64_t E,
                          const float *P, int64_t ldp, const float *Q, int64_t ldq,
                          const float *R, int64_t ldr, const float *keep, int64_t ldk,
@@ -142,6 +148,7 @@ int mmconv_aggregate_fwd(const int32_t *rowptr, const int32_t *col, const int32_
 int mmconv_aggregate_bwd_dst(const int32_t *rowptr, const int32_t *col, const int32_t *perm,
                              const int32_t *edge_gid, int64_t E_total, const int32_t *row_map,
                              const int32_t *rng_row, int64_t rng_row0,
+                             const int32_t *row_chunks, int64_t n_chunks,
                              int64_t n_rows, int64_t E,
                              const float *P, int64_t ldp, const float *Q, int64_t ldq,
                              const float *R, int64_t ldr, const float *keep, int64_t ldk,

@@ -22,6 +22,9 @@
 //     shuffle, instead of every lane running Philox for every edge;
 //   * the gathered rows Q[src] (and R[e], keep[e]) are fetched with 128-bit loads, 4 edges
 //     (4 x 512 B per warp at F=128) in flight per group before any is consumed.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace mma {
@@ -32,9 +35,11 @@ enum { FD_NONE = 0, FD_BIT = 1, FD_BYTE = 2 };              // fast kernels: no 
 enum { MSG_PQ = 0, MSG_PQR = 1, MSG_R = 2, MSG_GENERIC = 3 };
 
 struct MMConvParams {
-    const int32_t *rowptr, *col, *perm, *gid, *row_map, *rng_row;
-    int64_t n_rows, E, E_total, rng_row0;
+    const int32_t *rowptr, *col, *perm, *gid, *row_map, *rng_row, *row_chunks;
+    int64_t n_rows, E, E_total, rng_row0, n_chunks;
     int use_rng, args_local;
+    int simple_out;          // S == 1 and every aggregator kind at most once: zoff[kind] = its column offset in a Y row (-1: absent)
+    int zoff[6];
     const float *P, *Q, *R, *keep;
     int64_t ldp, ldq, ldr, ldk;
     Dropout drop;
@@ -781,12 +786,14 @@ __global__ void __launch_bounds__(256, 2) mmconv_bwd_fast(const __grid_constant_
     if (p.dP && g.live) st_vec_stream<4>(p.dP + prow * p.lddp + c, dp);
 }
 
+#include "mmconv_stream.cuh"
+
 // ----------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------
 static int fill_params(MMConvParams &p, const int32_t *rowptr, const int32_t *col, const int32_t *perm,
                        const int32_t *gid, int64_t E_total, const int32_t *row_map, const int32_t *rng_row,
-                       int64_t rng_row0, int64_t n_rows, int64_t E,
+                       int64_t rng_row0, const int32_t *row_chunks, int64_t n_chunks, int64_t n_rows, int64_t E,
                        const float *P, int64_t ldp, const float *Q, int64_t ldq,
                        const float *R, int64_t ldr, const float *keep, int64_t ldk, float p_drop, uint64_t seed,
                        int T, int F_in, int A, const int32_t *aggr_kinds, int S, const int32_t *scaler_kinds,
@@ -802,6 +809,8 @@ static int fill_params(MMConvParams &p, const int32_t *rowptr, const int32_t *co
     p = MMConvParams{};
     p.rowptr = rowptr; p.col = col; p.perm = perm; p.gid = gid; p.row_map = row_map; p.n_rows = n_rows; p.E = E;
     p.rng_row = rng_row; p.rng_row0 = rng_row0;
+    if (row_chunks && n_chunks < 1) return MMA_ERR_INVALID;
+    p.row_chunks = row_chunks; p.n_chunks = row_chunks ? n_chunks : 0;
     p.E_total = gid ? E_total : E;
     p.P = P; p.Q = Q; p.R = R; p.keep = keep; p.ldp = ldp; p.ldq = ldq; p.ldr = ldr; p.ldk = ldk;
     p.drop = make_dropout(p_drop, seed);
@@ -820,6 +829,12 @@ static int fill_params(MMConvParams &p, const int32_t *rowptr, const int32_t *co
     }
     if (any_scaled && (!scale_tab || tab_stride < 2)) return MMA_ERR_INVALID;
     p.scale_tab = scale_tab; p.tab_stride = tab_stride > 0 ? tab_stride : 1;
+    p.simple_out = (S == 1 && !any_scaled) ? 1 : 0;
+    for (int k = 0; k < 6; ++k) p.zoff[k] = -1;
+    for (int a = 0; a < A; ++a) {
+        if (p.zoff[p.akind[a]] >= 0) p.simple_out = 0;
+        p.zoff[p.akind[a]] = a * F_in;
+    }
     return MMA_OK;
 }
 
@@ -857,6 +872,54 @@ static int msg_mode(const float *P, const float *Q, const float *R) {
     return MSG_GENERIC;
 }
 
+// ---- stream kernels: launch geometry ----
+struct StreamCfg { int nst, warps; };
+static StreamCfg stream_cfg() {                 // ring stages x warps per CTA; MMA_K1_STREAM = "0" (off) | "8x12" | "4x16": tuning aid
+    static StreamCfg cfg = [] {
+        StreamCfg c{6, 16};
+        const char *e = getenv("MMA_K1_STREAM");
+        if (e) {
+            if (e[0] == '0') c = StreamCfg{0, 0};
+            else if (!strcmp(e, "8x12")) c = StreamCfg{8, 12};
+            else if (!strcmp(e, "4x16")) c = StreamCfg{4, 16};
+        }
+        return c;
+    }();
+    return cfg;
+}
+static int sm_count() {
+    static int n = [] { int dev = 0, v = kSMs; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); return v; }();
+    return n;
+}
+template <typename K>
+static cudaError_t launch_stream(K kernel, const MMConvParams &p, int nst, int warps, cudaStream_t st) {
+    const int smem = warps * nst * 4 * p.ncols * 4;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    kernel<<<sm_count(), warps * 32, smem, st>>>(p);
+    return cudaSuccess;
+}
+template <int NST, int WARPS, int DROP>
+static cudaError_t launch_fwd_stream(const MMConvParams &p, bool minmax, bool sq, cudaStream_t st) {
+    if (minmax && sq) return launch_stream(stream::mmconv_fwd_stream<NST, WARPS, DROP, true, true>, p, NST, WARPS, st);
+    if (minmax) return launch_stream(stream::mmconv_fwd_stream<NST, WARPS, DROP, true, false>, p, NST, WARPS, st);
+    if (sq) return launch_stream(stream::mmconv_fwd_stream<NST, WARPS, DROP, false, true>, p, NST, WARPS, st);
+    return launch_stream(stream::mmconv_fwd_stream<NST, WARPS, DROP, false, false>, p, NST, WARPS, st);
+}
+template <int NST, int WARPS, int DROP>
+static cudaError_t launch_bwd_stream(const MMConvParams &p, bool needm, cudaStream_t st) {
+    if (needm) {
+        if (p.args_local) return launch_stream(stream::mmconv_bwd_stream<NST, WARPS, DROP, true, true>, p, NST, WARPS, st);
+        return launch_stream(stream::mmconv_bwd_stream<NST, WARPS, DROP, true, false>, p, NST, WARPS, st);
+    }
+    if (p.args_local) return launch_stream(stream::mmconv_bwd_stream<NST, WARPS, DROP, false, true>, p, NST, WARPS, st);
+    return launch_stream(stream::mmconv_bwd_stream<NST, WARPS, DROP, false, false>, p, NST, WARPS, st);
+}
+// the stream kernels take: 128-bit columns, one warp per row window (<= 128 columns), message P + Q
+static bool stream_ok(const MMConvParams &p, int vec, const float *keep) {
+    return stream_cfg().nst > 0 && vec == 4 && !keep && p.chunks == 1 && p.ncols <= 128 && p.E > 0;
+}
+
 template <int MSG, int DROP>
 static void launch_fwd_fast(const MMConvParams &p, bool minmax, bool sq, unsigned grid, int block, cudaStream_t st) {
     if (minmax && sq) mmconv_fwd_fast<MSG, DROP, true, true><<<grid, block, 0, st>>>(p);
@@ -879,6 +942,7 @@ static void launch_bwd_fast(const MMConvParams &p, bool needm, unsigned grid, in
 extern "C" int mmconv_aggregate_fwd(const int32_t *rowptr, const int32_t *col, const int32_t *perm,
                                     const int32_t *edge_gid, int64_t E_total, const int32_t *row_map,
                                     const int32_t *rng_row, int64_t rng_row0,
+                                    const int32_t *row_chunks, int64_t n_chunks,
                                     int64_t n_rows, int64_t E, const float *P, int64_t ldp,
                                     const float *Q, int64_t ldq, const float *R, int64_t ldr,
                                     const float *keep, int64_t ldk, float p_drop, uint64_t seed,
@@ -888,7 +952,8 @@ extern "C" int mmconv_aggregate_fwd(const int32_t *rowptr, const int32_t *col, c
                                     float *stat_mean, float *stat_var, int col0, int ncols, int flags,
                                     mma_stream_t stream) {
     MMConvParams p;
-    int rc = fill_params(p, rowptr, col, perm, edge_gid, E_total, row_map, rng_row, rng_row0, n_rows, E, P, ldp,
+    int rc = fill_params(p, rowptr, col, perm, edge_gid, E_total, row_map, rng_row, rng_row0, row_chunks, n_chunks,
+                         n_rows, E, P, ldp,
                          Q, ldq, R, ldr, keep, ldk, p_drop, seed, T, F_in, A, aggr_kinds, S, scaler_kinds,
                          scale_tab, tab_stride, flags);
     if (rc != MMA_OK) return rc;
@@ -911,7 +976,18 @@ extern "C" int mmconv_aggregate_fwd(const int32_t *rowptr, const int32_t *col, c
     const unsigned grid = (unsigned)grid64;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int msg = msg_mode(P, Q, R);
-    if (vec == 4 && !keep && (msg == MSG_PQ || msg == MSG_PQR)) {
+    if (msg == MSG_PQ && stream_ok(p, vec, keep)) {
+        // persistent cp.async-ring kernels (mmconv_stream.cuh)
+        const int fd = fast_drop_mode(p.drop);
+        const StreamCfg sc = stream_cfg();
+        cudaError_t e;
+        if (fd == FD_BIT && minmax && sq && sc.nst == 8) e = launch_fwd_stream<8, 12, FD_BIT>(p, minmax, sq, st);
+        else if (fd == FD_BIT && minmax && sq && sc.nst == 4) e = launch_fwd_stream<4, 16, FD_BIT>(p, minmax, sq, st);
+        else if (fd == FD_NONE) e = launch_fwd_stream<6, 16, FD_NONE>(p, minmax, sq, st);
+        else if (fd == FD_BIT) e = launch_fwd_stream<6, 16, FD_BIT>(p, minmax, sq, st);
+        else e = launch_fwd_stream<6, 16, FD_BYTE>(p, minmax, sq, st);
+        MMA_CUDA_CHECK(e);
+    } else if (vec == 4 && !keep && (msg == MSG_PQ || msg == MSG_PQR)) {
         // fast kernels: 128-bit columns, message and dropout mode fixed at compile time
         const int fd = fast_drop_mode(p.drop);
         if (msg == MSG_PQ) {
@@ -942,6 +1018,7 @@ extern "C" int mmconv_aggregate_fwd(const int32_t *rowptr, const int32_t *col, c
 extern "C" int mmconv_aggregate_bwd_dst(const int32_t *rowptr, const int32_t *col, const int32_t *perm,
                                         const int32_t *edge_gid, int64_t E_total, const int32_t *row_map,
                                         const int32_t *rng_row, int64_t rng_row0,
+                                        const int32_t *row_chunks, int64_t n_chunks,
                                         int64_t n_rows, int64_t E, const float *P, int64_t ldp,
                                         const float *Q, int64_t ldq, const float *R, int64_t ldr,
                                         const float *keep, int64_t ldk, float p_drop, uint64_t seed,
@@ -952,7 +1029,8 @@ extern "C" int mmconv_aggregate_bwd_dst(const int32_t *rowptr, const int32_t *co
                                         const int32_t *gslot, float *G, int64_t ldg, float *dP, int64_t lddp,
                                         int col0, int ncols, int flags, mma_stream_t stream) {
     MMConvParams p;
-    int rc = fill_params(p, rowptr, col, perm, edge_gid, E_total, row_map, rng_row, rng_row0, n_rows, E, P, ldp,
+    int rc = fill_params(p, rowptr, col, perm, edge_gid, E_total, row_map, rng_row, rng_row0, row_chunks, n_chunks,
+                         n_rows, E, P, ldp,
                          Q, ldq, R, ldr, keep, ldk, p_drop, seed, T, F_in, A, aggr_kinds, S, scaler_kinds,
                          scale_tab, tab_stride, flags);
     if (rc != MMA_OK) return rc;
@@ -979,7 +1057,17 @@ extern "C" int mmconv_aggregate_bwd_dst(const int32_t *rowptr, const int32_t *co
     const unsigned grid = (unsigned)grid64;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int msg = msg_mode(P, Q, R);
-    if (vec == 4 && !keep && (!needm || msg == MSG_PQ || msg == MSG_PQR)) {
+    if ((!needm || msg == MSG_PQ) && stream_ok(p, vec, keep)) {
+        const int fd = fast_drop_mode(p.drop);
+        const StreamCfg sc = stream_cfg();
+        cudaError_t e;
+        if (fd == FD_BIT && needm && sc.nst == 8) e = launch_bwd_stream<8, 12, FD_BIT>(p, needm, st);
+        else if (fd == FD_BIT && needm && sc.nst == 4) e = launch_bwd_stream<4, 16, FD_BIT>(p, needm, st);
+        else if (fd == FD_NONE) e = launch_bwd_stream<6, 16, FD_NONE>(p, needm, st);
+        else if (fd == FD_BIT) e = launch_bwd_stream<6, 16, FD_BIT>(p, needm, st);
+        else e = launch_bwd_stream<6, 16, FD_BYTE>(p, needm, st);
+        MMA_CUDA_CHECK(e);
+    } else if (vec == 4 && !keep && (!needm || msg == MSG_PQ || msg == MSG_PQR)) {
         const int fd = fast_drop_mode(p.drop);
         if (needm && msg == MSG_PQR) {
             if (fd == FD_NONE) launch_bwd_fast<MSG_PQR, FD_NONE>(p, needm, grid, block, st);

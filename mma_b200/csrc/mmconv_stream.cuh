@@ -1,0 +1,633 @@
+// K1 "stream" kernels: the HBM-bound configuration of the MultiMaskConv aggregate (128-bit column
+// groups, message P[dst] + Q[src], in-kernel dropout) as a persistent, latency-tolerant pipeline.
+//
+// The register-batch kernels in mmconv_aggregate.cu give every destination row to a fresh warp, which
+// walks a chain of dependent DRAM round trips (rowptr -> col -> Q rows -> next batch) with at most 8
+// gathered rows in flight, and spends ~1000 instructions per row on generic addressing: ncu showed them
+// latency / issue bound at ~50 % of the HBM roofline.  Here
+//   * the rows are cut into cost-balanced CHUNKS (row_chunks, built once per graph; ~50 rows each) that
+//     are dealt round-robin to persistent warps; a chunk's in-edges are one contiguous stream of CSR
+//     slots, so col[] is read with coalesced, prefetched loads and the row boundaries come from rowptr
+//     one row ahead -- no data-dependent index chain;
+//   * the gathered rows Q[src] are copied global -> shared with cp.async (LDGSTS, 16 B per lane: a lane
+//     copies exactly the 4 columns it later consumes, so completion needs no cross-lane barrier) into a
+//     per-warp ring of NST stages x 4 edges that runs NST-1 stages AHEAD of consumption and does not
+//     stop at row boundaries;
+//   * a stage that lies inside one row is consumed by a 4-edge unrolled, branch-free body (12
+//     instructions per element); stages that straddle a row boundary go edge by edge; the row epilogue
+//     keeps running output pointers instead of re-deriving addresses.
+// Same arithmetic, same summation order, same dropout stream as the other K1 kernels (bit-identical
+// results); included by mmconv_aggregate.cu.
+#pragma once
+
+namespace stream {
+
+constexpr int kRowCost = 6;        // a row costs about this many edges (used when no row_chunks are given)
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}"
+                 :: "r"(dst), "l"(src), "r"((int)pred) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+__device__ __forceinline__ Vec<4> lds4(uint32_t addr) {
+    Vec<4> r;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "r"(addr));
+    return r;
+}
+
+// smallest r in [0, n_rows] with rowptr[r] + kRowCost * r >= target
+__device__ __forceinline__ int first_row_at(const int32_t *rowptr, int64_t n_rows, int64_t target) {
+    int64_t lo = 0, hi = n_rows;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)__ldg(rowptr + mid) + kRowCost * mid >= target) hi = mid; else lo = mid + 1;
+    }
+    return (int)lo;
+}
+
+// rows [r0, r1) of chunk i
+__device__ __forceinline__ void chunk_rows(const MMConvParams &p, int64_t i, int64_t n_chunks, int &r0, int &r1) {
+    if (p.row_chunks) {
+        r0 = __ldg(p.row_chunks + i); r1 = __ldg(p.row_chunks + i + 1);
+    } else {
+        const int64_t total = p.E + kRowCost * p.n_rows;
+        r0 = first_row_at(p.rowptr, p.n_rows, (total * i) / n_chunks);
+        r1 = (i + 1 == n_chunks) ? (int)p.n_rows : first_row_at(p.rowptr, p.n_rows, (total * (i + 1)) / n_chunks);
+    }
+}
+
+// Issue side of the pipeline: index chunks + the cp.async ring of one warp.
+template <int NST, bool NQ>
+struct Ring {
+    uint32_t base;             // shared-memory address of this lane's 16 bytes in ring slot 0
+    int rowb;                  // bytes of one gathered row window
+    const char *Qc;            // Q + this lane's column
+    uint32_t ldq_b;
+    const int32_t *colp;       // col + first CSR slot of the stream
+    int len, lane;
+    bool live;
+    int idx_cur, idx_nxt;      // col[] of the 32-edge chunk being issued / the one after it
+    int p_issue;               // stream position of the next stage to issue
+    int ring_i;                // its ring slot
+
+    __device__ __forceinline__ int load_chunk(int pbase) const {
+        const int i = pbase + lane;
+        return (NQ && i < len) ? __ldg(colp + i) : 0;
+    }
+    // issues one stage (4 stream edges) and commits it as one cp.async group (an empty group past
+    // the end of the stream keeps the wait_group arithmetic uniform)
+    __device__ __forceinline__ void issue() {
+        if constexpr (NQ) {
+            if (p_issue < len) {
+                if ((p_issue & 31) == 0) { idx_cur = idx_nxt; idx_nxt = load_chunk(p_issue + 32); }
+                const uint32_t dst = base + (uint32_t)(ring_i * 4 * rowb);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = __shfl_sync(0xffffffffu, idx_cur, (p_issue & 31) + u);
+                    cp_async16(dst + (uint32_t)(u * rowb), Qc + (uint64_t)(uint32_t)j * ldq_b, live && (p_issue + u < len));
+                }
+            }
+        }
+        cp_async_commit();
+        p_issue += 4;
+        ring_i = ring_i + 1 == NST ? 0 : ring_i + 1;
+    }
+    __device__ __forceinline__ void begin(const int32_t *col_at_s0, int len_) {
+        colp = col_at_s0; len = len_;
+        p_issue = 0; ring_i = 0;
+        idx_cur = 0; idx_nxt = load_chunk(0);
+#pragma unroll 1
+        for (int k = 0; k < NST; ++k) issue();
+        cp_async_wait<NST - 1>();                   // stage 0 has landed
+    }
+    // the consumer is done with its current stage: refill that slot with the stage NST ahead, then make
+    // sure the next stage has landed
+    __device__ __forceinline__ void advance() {
+        issue();
+        cp_async_wait<NST - 1>();
+    }
+    __device__ __forceinline__ void end() { cp_async_wait<0>(); }
+};
+
+// One int per stream edge (G-row slot, original edge id), read by the CONSUMER in coalesced chunks of
+// 32 edges, one chunk ahead.  load(pbase) returns the value of stream edge pbase + lane (0 past the end).
+struct EdgeAttr {
+    int cur, nxt;
+    template <typename Load>
+    __device__ __forceinline__ void init(Load &&load) { cur = load(0); nxt = load(32); }
+    template <typename Load>
+    __device__ __forceinline__ void at_stage(int s, Load &&load) {      // s: first edge of the stage (multiple of 4)
+        if ((s & 31) == 0 && s > 0) { cur = nxt; nxt = load(s + 32); }
+    }
+    __device__ __forceinline__ int get(int s) const { return __shfl_sync(0xffffffffu, cur, s & 31); }
+};
+
+// Drives one chunk: walks the stages of the stream; calls
+//   row_next()            when the stream passes the end of the current row (finish it, start the next),
+//   edge4(at, q[4], s)    for a stage of 4 edges inside the current row (at = CSR slot of the first),
+//   edge1(at, q, s)       for single edges,
+//   fast_ok()             whether the 4-edge body may be used now (dropout word boundaries),
+//   stage_begin(s)        at the first edge of every stage.
+// row_end is read through a reference: row_next() updates it.
+template <int NST, bool NQ, typename RowNext, typename Edge4, typename Edge1, typename FastOk, typename StageBegin>
+__device__ __forceinline__ void run_stream(Ring<NST, NQ> &ring, int s0, int len, const int &row_end, RowNext &&row_next,
+                                           Edge4 &&edge4, Edge1 &&edge1, FastOk &&fast_ok, StageBegin &&stage_begin) {
+    int cons_i = 0;
+#pragma unroll 1
+    for (int s = 0; s < len; s += 4) {
+        const int n = len - s < 4 ? len - s : 4;
+        const uint32_t sb = ring.base + (uint32_t)(cons_i * 4 * ring.rowb);
+        stage_begin(s);
+        int u = 0;
+#pragma unroll 1
+        while (u < n) {
+            const int at = s0 + s + u;
+            if (at == row_end) { row_next(); continue; }
+            if (u == 0 && n == 4 && row_end - at >= 4 && fast_ok()) {
+                Vec<4> q[4];
+                if constexpr (NQ) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) q[i] = lds4(sb + (uint32_t)(i * ring.rowb));
+                }
+                edge4(at, q, s);
+                u = 4;
+            } else {
+                Vec<4> q{};
+                if constexpr (NQ) q = lds4(sb + (uint32_t)(u * ring.rowb));
+                edge1(at, q, s + u);
+                ++u;
+            }
+        }
+        ring.advance();
+        cons_i = cons_i + 1 == NST ? 0 : cons_i + 1;
+    }
+    ring.end();
+}
+
+// dropout words for in-row position pos: refreshes `bits` at the word boundaries of the row's stream
+template <int DROP>
+__device__ __forceinline__ void rng_refresh(const MMConvParams &p, uint32_t rid, int pos, int c, uint32_t (&bits)[4]) {
+    if constexpr (DROP == FD_BIT) {
+        if ((pos & 31) == 0) {
+            const uint4 t = row_rng_bits1(p.drop, rid, (uint32_t)pos, (uint32_t)c);
+            bits[0] = t.x; bits[1] = t.y; bits[2] = t.z; bits[3] = t.w;
+        }
+    } else if constexpr (DROP == FD_BYTE) {
+        if ((pos & 3) == 0) {
+            const uint4 t = row_rng_bits8(p.drop, rid, (uint32_t)pos, (uint32_t)c);
+            bits[0] = t.x; bits[1] = t.y; bits[2] = t.z; bits[3] = t.w;
+        }
+    }
+}
+// non-zero iff column v of the edge at in-row position pos is kept
+template <int DROP>
+__device__ __forceinline__ uint32_t keep_at(uint32_t word, int pos, uint32_t thr) {
+    if constexpr (DROP == FD_BIT) return word & (1u << (pos & 31));
+    else if constexpr (DROP == FD_BYTE) return ((word >> (8 * (pos & 3))) & 0xFFu) >= thr ? 1u : 0u;
+    else return 1u;
+}
+
+// IEEE-correct a / y for the row's degree y (integer valued, 1 <= y <= 2^24) with the reciprocal shared by
+// all columns: r = 1/y refined once; q = a*r corrected by one residual step is the correctly rounded
+// quotient whenever nothing under/overflows, which the exponent test guarantees; otherwise __fdiv_rn.
+struct DivByDeg {
+    float y, r;
+    __device__ __forceinline__ explicit DivByDeg(float y_) : y(y_) {
+        float r0;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(y_));
+        const float e = __fmaf_rn(-y_, r0, 1.0f);
+        r = __fmaf_rn(r0, e, r0);
+    }
+    __device__ __forceinline__ float operator()(float a) const {
+        const uint32_t ex = (__float_as_uint(a) >> 23) & 0xFFu;
+        if (ex - 40u < 176u) {                       // 2^-87 <= |a| < 2^89: no intermediate can leave the normal range
+            const float q0 = __fmul_rn(a, r);
+            const float rem = __fmaf_rn(-y, q0, a);
+            return __fmaf_rn(r, rem, q0);
+        }
+        return __fdiv_rn(a, y);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+template <int NST, int WARPS, int DROP, bool MINMAX, bool SQ>
+__global__ void __launch_bounds__(WARPS * 32, 1) mmconv_fwd_stream(const __grid_constant__ MMConvParams p) {
+    extern __shared__ __align__(16) uint8_t smem_ring[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t gw = (int64_t)blockIdx.x * WARPS + warp, tw = (int64_t)gridDim.x * WARPS;
+    const int64_t n_chunks = p.row_chunks ? p.n_chunks : tw;
+    const bool live = lane * 4 < p.ncols;
+    const int c = p.col0 + lane * 4;
+    const float scale = p.drop.scale;
+    const uint32_t thr = p.drop.thr;
+    // outputs of the common case (S == 1, every aggregator kind at most once): column offset of each kind in a
+    // row of Y, or -1 (fill_params); anything else goes through the generic loop
+    const bool simple_out = p.simple_out != 0;
+
+    Ring<NST, true> ring;
+    ring.rowb = p.ncols * 4;
+    ring.base = smem_addr(smem_ring) + (uint32_t)warp * (uint32_t)(NST * 4 * ring.rowb) + (live ? (uint32_t)lane * 16u : 0u);   // idle lanes stay inside the ring
+    ring.Qc = reinterpret_cast<const char *>(p.Q + c);
+    ring.ldq_b = (uint32_t)p.ldq * 4u;
+    ring.lane = lane; ring.live = live;
+
+#pragma unroll 1
+    for (int64_t chunk = gw; chunk < n_chunks; chunk += tw) {
+        int r0, r1;
+        chunk_rows(p, chunk, n_chunks, r0, r1);
+        if (r0 >= r1) continue;
+        const int s0 = __ldg(p.rowptr + r0);
+        const int len = __ldg(p.rowptr + r1) - s0;
+
+        // ---- per-row state; the next row's inputs are fetched one row ahead ----
+        int row = r0;
+        int row_beg = s0, row_end = __ldg(p.rowptr + r0 + 1);
+        int next_end = r0 + 2 <= p.n_rows ? __ldg(p.rowptr + r0 + 2) : 0x7fffffff;
+        Vec<4> pv{}, pv_next{};
+        uint32_t rid = 0, rid_next = 0;
+        float sum[4], sq[4], mn[4], mx[4];
+        int amn[4], amx[4];
+        uint32_t bits[4] = {0u, 0u, 0u, 0u};
+        int pos = 0;                                        // in-row position of the next edge
+        // running output pointers (this lane's columns of row `row`)
+        float *yp = p.Y + (int64_t)r0 * p.ldy + (p.T == 1 ? c : (c / p.F_in) * (p.S * p.A * p.F_in) + c % p.F_in);
+        const int64_t rowF = (int64_t)r0 * p.F + c;
+        int32_t *amn_p = p.arg_min ? p.arg_min + rowF : nullptr;
+        int32_t *amx_p = p.arg_max ? p.arg_max + rowF : nullptr;
+        float *mean_p = p.stat_mean ? p.stat_mean + rowF : nullptr;
+        float *var_p = p.stat_var ? p.stat_var + rowF : nullptr;
+
+        auto fetch_row_inputs = [&](int r, Vec<4> &pvv, uint32_t &rd) {      // P row (pre-scaled) and rng id of row r
+            pvv = Vec<4>{}; rd = 0;
+            if (r < r1) {
+                const int64_t prow = p.row_map ? (int64_t)__ldg(p.row_map + r) : (int64_t)r;
+                if (live) pvv = ld_vec_stream<4>(p.P + prow * p.ldp + c);
+                if (p.use_rng) rd = (uint32_t)(p.rng_row0 + (p.rng_row ? (int64_t)__ldg(p.rng_row + r) : (int64_t)r));
+            }
+            if constexpr (DROP == FD_BIT) {
+#pragma unroll
+                for (int v = 0; v < 4; ++v) pvv.v[v] *= 2.0f;
+            }
+        };
+        auto reset_acc = [&]() {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                sum[v] = 0.0f; sq[v] = 0.0f; mn[v] = FLT_MAX; mx[v] = -FLT_MAX; amn[v] = -1; amx[v] = -1;
+            }
+            pos = 0;
+        };
+        auto finish_row = [&]() {
+            if (!live) return;
+            const int deg = row_end - row_beg;
+            const int degc = deg > 1 ? deg : 1;                     // deg.clamp_(1), mma_conv.py:179
+            const DivByDeg div((float)degc);
+            Vec<4> mean, var, sd, vmin, vmax, vsum;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                vsum.v[v] = sum[v];
+                mean.v[v] = div(sum[v]);                            // sum / count.clamp(min=1)
+                if constexpr (SQ) {
+                    const float msq = div(sq[v]);
+                    var.v[v] = __fsub_rn(msq, __fmul_rn(mean.v[v], mean.v[v]));         // mma_conv.py:170, no FMA
+                    sd.v[v] = sqrtf(__fadd_rn(fmaxf(var.v[v], 0.0f), 1e-5f));           // mma_conv.py:172
+                } else {
+                    var.v[v] = 0.0f; sd.v[v] = 0.0f;
+                }
+                vmin.v[v] = (MINMAX && amn[v] >= 0) ? mn[v] : 0.0f;                      // empty row -> 0
+                vmax.v[v] = (MINMAX && amx[v] >= 0) ? mx[v] : 0.0f;
+            }
+            if (simple_out) {
+                if (p.zoff[MMA_AGGR_SUM] >= 0) st_vec_stream<4>(yp + p.zoff[MMA_AGGR_SUM], vsum);
+                if (p.zoff[MMA_AGGR_MEAN] >= 0) st_vec_stream<4>(yp + p.zoff[MMA_AGGR_MEAN], mean);
+                if constexpr (MINMAX) {
+                    if (p.zoff[MMA_AGGR_MIN] >= 0) st_vec_stream<4>(yp + p.zoff[MMA_AGGR_MIN], vmin);
+                    if (p.zoff[MMA_AGGR_MAX] >= 0) st_vec_stream<4>(yp + p.zoff[MMA_AGGR_MAX], vmax);
+                }
+                if constexpr (SQ) {
+                    if (p.zoff[MMA_AGGR_VAR] >= 0) st_vec_stream<4>(yp + p.zoff[MMA_AGGR_VAR], var);
+                    if (p.zoff[MMA_AGGR_STD] >= 0) st_vec_stream<4>(yp + p.zoff[MMA_AGGR_STD], sd);
+                }
+            } else {
+                float fac[MMA_MAX_SCALER];
+                scaler_factors(p, degc, fac);
+                for (int a = 0; a < p.A; ++a) {
+                    const int kind = p.akind[a];
+                    Vec<4> val = kind == MMA_AGGR_SUM ? vsum : kind == MMA_AGGR_MEAN ? mean : kind == MMA_AGGR_MIN ? vmin
+                               : kind == MMA_AGGR_MAX ? vmax : kind == MMA_AGGR_VAR ? var : sd;
+                    for (int s = 0; s < p.S; ++s) {
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) val.v[v] = __fmul_rn(val.v[v], fac[s]);       // cumulative (Q4)
+                        st_vec_stream<4>(yp + (int64_t)(s * p.A + a) * p.F_in, val);
+                    }
+                }
+            }
+            if constexpr (MINMAX) {
+                int32_t o_mn[4], o_mx[4];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    o_mn[v] = amn[v] < 0 ? (int32_t)p.E_total : (p.args_local ? amn[v] : orig_edge_id(p, amn[v]));
+                    o_mx[v] = amx[v] < 0 ? (int32_t)p.E_total : (p.args_local ? amx[v] : orig_edge_id(p, amx[v]));
+                }
+                if (amn_p) st_vec_i32_stream<4>(amn_p, o_mn);
+                if (amx_p) st_vec_i32_stream<4>(amx_p, o_mx);
+            }
+            if (mean_p) st_vec_stream<4>(mean_p, mean);
+            if constexpr (SQ) {
+                if (var_p) st_vec_stream<4>(var_p, var);
+            }
+        };
+        auto row_next = [&]() {
+            finish_row();
+            ++row;
+            yp += p.ldy;
+            if (amn_p) amn_p += p.F;
+            if (amx_p) amx_p += p.F;
+            if (mean_p) mean_p += p.F;
+            if (var_p) var_p += p.F;
+            row_beg = row_end;
+            row_end = next_end;
+            next_end = row + 2 <= p.n_rows ? __ldg(p.rowptr + row + 2) : 0x7fffffff;
+            pv = pv_next; rid = rid_next;
+            fetch_row_inputs(row + 1, pv_next, rid_next);
+            reset_acc();
+        };
+
+        fetch_row_inputs(row, pv, rid);
+        fetch_row_inputs(row + 1, pv_next, rid_next);
+        reset_acc();
+
+        if (len > 0) {
+            ring.begin(p.col + s0, len);
+            run_stream<NST, true>(ring, s0, len, row_end, row_next,
+                [&](int at, const Vec<4> (&q)[4], int) {                    // 4 edges inside the row
+                    rng_refresh<DROP>(p, rid, pos, c, bits);
+                    uint32_t w[4];
+                    const int sh = DROP == FD_BIT ? (pos & 31) : 0;
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) w[v] = bits[v] >> sh;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            const float x = fast_message<MSG_PQ, DROP>(pv.v[v], q[u].v[v], 0.0f, scale);
+                            accumulate<false, DROP != FD_NONE, MINMAX, SQ>(x, keep_word<DROP>(w[v], u, thr), 1u, at + u,
+                                                                           sum[v], sq[v], mn[v], mx[v], amn[v], amx[v]);
+                        }
+                    }
+                    pos += 4;
+                },
+                [&](int at, const Vec<4> &q, int) {                         // one edge
+                    rng_refresh<DROP>(p, rid, pos, c, bits);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const float x = fast_message<MSG_PQ, DROP>(pv.v[v], q.v[v], 0.0f, scale);
+                        accumulate<false, DROP != FD_NONE, MINMAX, SQ>(x, keep_at<DROP>(bits[v], pos, thr), 1u, at,
+                                                                       sum[v], sq[v], mn[v], mx[v], amn[v], amx[v]);
+                    }
+                    ++pos;
+                },
+                [&]() { return DROP == FD_BIT ? (pos & 31) <= 28 : (DROP == FD_BYTE ? (pos & 3) == 0 : true); },
+                [](int) {});
+        }
+        // the last row with edges, then trailing empty rows
+        for (;;) {
+            if (row + 1 >= r1) { finish_row(); break; }
+            row_next();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward, destination pass
+// ---------------------------------------------------------------------------------------------
+template <int NST, int WARPS, int DROP, bool NEEDM, bool LOCAL>
+__global__ void __launch_bounds__(WARPS * 32, 1) mmconv_bwd_stream(const __grid_constant__ MMConvParams p) {
+    extern __shared__ __align__(16) uint8_t smem_ring[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t gw = (int64_t)blockIdx.x * WARPS + warp, tw = (int64_t)gridDim.x * WARPS;
+    const int64_t n_chunks = p.row_chunks ? p.n_chunks : tw;
+    const bool live = lane * 4 < p.ncols;
+    const int c = p.col0 + lane * 4;
+    const float scale = DROP == FD_BIT ? 2.0f : (DROP == FD_BYTE ? p.drop.scale : 1.0f);
+    const uint32_t thr = p.drop.thr;
+    const bool simple_out = p.simple_out != 0;
+
+    Ring<NST, NEEDM> ring;
+    ring.rowb = p.ncols * 4;
+    ring.base = smem_addr(smem_ring) + (uint32_t)warp * (uint32_t)(NST * 4 * ring.rowb) + (live ? (uint32_t)lane * 16u : 0u);   // idle lanes stay inside the ring
+    ring.Qc = reinterpret_cast<const char *>(p.Q + c);
+    ring.ldq_b = (uint32_t)p.ldq * 4u;
+    ring.lane = lane; ring.live = live;
+    char *Gc = p.G ? reinterpret_cast<char *>(p.G + c) : nullptr;
+    const uint32_t ldg_b = (uint32_t)p.ldg * 4u;
+
+#pragma unroll 1
+    for (int64_t chunk = gw; chunk < n_chunks; chunk += tw) {
+        int r0, r1;
+        chunk_rows(p, chunk, n_chunks, r0, r1);
+        if (r0 >= r1) continue;
+        const int s0 = __ldg(p.rowptr + r0);
+        const int len = __ldg(p.rowptr + r1) - s0;
+
+        int row = r0;
+        int row_beg = s0, row_end = __ldg(p.rowptr + r0 + 1);
+        Vec<4> base{}, gmin{}, gmax{}, alpha{}, pv{}, dp{};
+        int32_t amn[4], amx[4];
+        uint32_t rid = 0;
+        uint32_t bits[4] = {0u, 0u, 0u, 0u};
+        int pos = 0;
+        int64_t prow = 0;
+        const float *dyp = p.dY + (int64_t)r0 * p.ldy + (p.T == 1 ? c : (c / p.F_in) * (p.S * p.A * p.F_in) + c % p.F_in);
+        int64_t rowF = (int64_t)r0 * p.F + c;
+
+        auto start_row = [&]() {          // folds dY of `row` into base / gmin / gmax / alpha (times the keep-scale)
+            pos = 0;
+            base = Vec<4>{}; gmin = Vec<4>{}; gmax = Vec<4>{}; alpha = Vec<4>{}; pv = Vec<4>{}; dp = Vec<4>{};
+#pragma unroll
+            for (int v = 0; v < 4; ++v) { amn[v] = -1; amx[v] = -1; }
+            prow = p.row_map ? (int64_t)__ldg(p.row_map + row) : (int64_t)row;
+            if (p.use_rng) rid = (uint32_t)(p.rng_row0 + (p.rng_row ? (int64_t)__ldg(p.rng_row + row) : (int64_t)row));
+            if (!live) return;
+            const int deg = row_end - row_beg;
+            const int degc = deg > 1 ? deg : 1;
+            const float degf = (float)degc;
+            const float rdeg = 1.0f / degf;
+            Vec<4> mean{}, var{};
+            if constexpr (NEEDM) {
+                mean = ld_vec_stream<4>(p.c_mean + rowF);
+                var = ld_vec_stream<4>(p.c_var + rowF);
+            }
+            if (simple_out) {
+                // every kind at most once, S == 1: straight-line fold
+                if (p.zoff[MMA_AGGR_SUM] >= 0) {
+                    const Vec<4> d = ld_vec_stream<4>(dyp + p.zoff[MMA_AGGR_SUM]);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) base.v[v] += d.v[v];
+                }
+                if (p.zoff[MMA_AGGR_MEAN] >= 0) {
+                    const Vec<4> d = ld_vec_stream<4>(dyp + p.zoff[MMA_AGGR_MEAN]);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) base.v[v] += d.v[v] * rdeg;
+                }
+                if (p.zoff[MMA_AGGR_MIN] >= 0) {
+                    gmin = ld_vec_stream<4>(dyp + p.zoff[MMA_AGGR_MIN]);
+                    ld_vec_i32_as<4>(p.c_arg_min + rowF, amn);
+                }
+                if (p.zoff[MMA_AGGR_MAX] >= 0) {
+                    gmax = ld_vec_stream<4>(dyp + p.zoff[MMA_AGGR_MAX]);
+                    ld_vec_i32_as<4>(p.c_arg_max + rowF, amx);
+                }
+                if constexpr (NEEDM) {
+                    if (p.zoff[MMA_AGGR_VAR] >= 0) {    // var = E[m^2] - E[m]^2 -> d/dm_e = 2 (m_e - mean) / cnt
+                        const Vec<4> d = ld_vec_stream<4>(dyp + p.zoff[MMA_AGGR_VAR]);
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            const float k = 2.0f * d.v[v] * rdeg;
+                            alpha.v[v] += k; base.v[v] -= k * mean.v[v];
+                        }
+                    }
+                    if (p.zoff[MMA_AGGR_STD] >= 0) {    // std = sqrt(relu(var) + 1e-5); relu'(0) = 0
+                        const Vec<4> d = ld_vec_stream<4>(dyp + p.zoff[MMA_AGGR_STD]);
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            if (var.v[v] > 0.0f) {
+                                const float k = d.v[v] * rdeg * rsqrtf(var.v[v] + 1e-5f);
+                                alpha.v[v] += k; base.v[v] -= k * mean.v[v];
+                            }
+                        }
+                    }
+                }
+            } else {
+                float fac[MMA_MAX_SCALER];
+                scaler_factors(p, degc, fac);
+                for (int s = 1; s < p.S; ++s) fac[s] *= fac[s - 1];
+                bool has_min = false, has_max = false;
+                for (int a = 0; a < p.A; ++a) {
+                    Vec<4> dz{};
+                    for (int s = 0; s < p.S; ++s) {
+                        const Vec<4> d = ld_vec_stream<4>(dyp + (int64_t)(s * p.A + a) * p.F_in);
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) dz.v[v] += d.v[v] * fac[s];
+                    }
+                    const int kind = p.akind[a];
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const float gg = dz.v[v];
+                        if (kind == MMA_AGGR_SUM) base.v[v] += gg;
+                        else if (kind == MMA_AGGR_MEAN) base.v[v] += gg / degf;
+                        else if (kind == MMA_AGGR_MIN) gmin.v[v] += gg;
+                        else if (kind == MMA_AGGR_MAX) gmax.v[v] += gg;
+                        else if (kind == MMA_AGGR_VAR) {
+                            const float k = 2.0f * gg / degf;
+                            alpha.v[v] += k; base.v[v] -= k * mean.v[v];
+                        } else if (var.v[v] > 0.0f) {
+                            const float k = gg / (sqrtf(var.v[v] + 1e-5f) * degf);
+                            alpha.v[v] += k; base.v[v] -= k * mean.v[v];
+                        }
+                    }
+                    has_min |= kind == MMA_AGGR_MIN;
+                    has_max |= kind == MMA_AGGR_MAX;
+                }
+                if (has_min) ld_vec_i32_as<4>(p.c_arg_min + rowF, amn);
+                if (has_max) ld_vec_i32_as<4>(p.c_arg_max + rowF, amx);
+            }
+            if (NEEDM && p.P) pv = ld_vec_stream<4>(p.P + prow * p.ldp + c);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                base.v[v] *= scale; gmin.v[v] *= scale; gmax.v[v] *= scale; alpha.v[v] *= scale;
+                if constexpr (DROP == FD_BIT) pv.v[v] *= 2.0f;
+            }
+        };
+        auto finish_row = [&]() {
+            if (p.dP && live) st_vec_stream<4>(p.dP + prow * p.lddp + c, dp);
+        };
+        auto row_next = [&]() {
+            finish_row();
+            ++row;
+            dyp += p.ldy;
+            rowF += p.F;
+            row_beg = row_end;
+            row_end = __ldg(p.rowptr + row + 1);
+            start_row();
+        };
+
+        start_row();
+        if (len > 0) {
+            auto load_slot = [&](int pbase) {
+                const int i = pbase + lane;
+                return i < len ? (p.gslot ? __ldg(p.gslot + s0 + i) : s0 + i) : 0;
+            };
+            auto load_eid = [&](int pbase) {               // global original edge id (public arg indices)
+                const int i = pbase + lane;
+                if (i >= len) return 0;
+                const int e = p.perm ? __ldg(p.perm + s0 + i) : s0 + i;
+                return p.gid ? __ldg(p.gid + e) : e;
+            };
+            EdgeAttr gslot, eid;
+            gslot.init(load_slot);
+            if constexpr (!LOCAL) eid.init(load_eid);
+            else { eid.cur = 0; eid.nxt = 0; }
+
+            auto one_edge = [&](int at, int s, const Vec<4> &q, const uint32_t (&kw)[4]) {
+                const int gs = gslot.get(s);
+                int id = at;
+                if constexpr (!LOCAL) id = eid.get(s);
+                Vec<4> gr;
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    float t = base.v[v];
+                    if constexpr (NEEDM) {
+                        const float x = fast_message<MSG_PQ, DROP>(pv.v[v], q.v[v], 0.0f, scale);
+                        t = __fmaf_rn(alpha.v[v], x, t);
+                    }
+                    route_grad<false>(t, id, amn[v], amx[v], gmin.v[v], gmax.v[v], kw[v], 1u, gr.v[v], dp.v[v]);
+                }
+                if (live && Gc) st_vec_stream<4>(reinterpret_cast<float *>(Gc + (uint64_t)(uint32_t)gs * ldg_b), gr);
+            };
+
+            ring.begin(p.col + s0, len);
+            run_stream<NST, NEEDM>(ring, s0, len, row_end, row_next,
+                [&](int at, const Vec<4> (&q)[4], int s) {
+                    rng_refresh<DROP>(p, rid, pos, c, bits);
+                    uint32_t w[4];
+                    const int sh = DROP == FD_BIT ? (pos & 31) : 0;
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) w[v] = bits[v] >> sh;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        uint32_t kw[4];
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) kw[v] = keep_word<DROP>(w[v], u, thr);
+                        one_edge(at + u, s + u, q[u], kw);
+                    }
+                    pos += 4;
+                },
+                [&](int at, const Vec<4> &q, int s) {
+                    rng_refresh<DROP>(p, rid, pos, c, bits);
+                    uint32_t kw[4];
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) kw[v] = keep_at<DROP>(bits[v], pos, thr);
+                    one_edge(at, s, q, kw);
+                    ++pos;
+                },
+                [&]() { return DROP == FD_BIT ? (pos & 31) <= 28 : (DROP == FD_BYTE ? (pos & 3) == 0 : true); },
+                [&](int s) {
+                    gslot.at_stage(s, load_slot);
+                    if constexpr (!LOCAL) eid.at_stage(s, load_eid);
+                });
+        }
+        for (;;) {
+            if (row + 1 >= r1) { finish_row(); break; }
+            row_next();
+        }
+    }
+}
+
+}  // namespace stream

@@ -55,10 +55,12 @@ def k1_forward(graph: Graph, P, Q, R, keep, *, T: int, F_in: int, akinds, skinds
     sharded path: a narrow gathered window addressed with global column indices)."""
     dev = graph.device
     ak, sk = _lib.i32_array(akinds), _lib.i32_array(skinds)
+    chunks = graph.k1_chunks()
     with _lib.kernel_scope("mmconv_aggregate_fwd", dev):
         _lib.check(_lib.lib().mmconv_aggregate_fwd(
             _lib.ptr(graph.rowptr), _lib.ptr(graph.col), _lib.ptr(graph.perm), _lib.ptr(graph.gid), graph.E_total,
-            _lib.ptr(graph.row_map), _lib.ptr(graph.rng_row), int(graph.rng_row0), graph.n_dst, graph.E,
+            _lib.ptr(graph.row_map), _lib.ptr(graph.rng_row), int(graph.rng_row0), _lib.ptr(chunks),
+            0 if chunks is None else chunks.numel() - 1, graph.n_dst, graph.E,
             _lib.ptr(P), _ld(P), (_lib.ptr(Q) if q_ptr is None else q_ptr), (_ld(Q) if ldq is None else ldq),
             _lib.ptr(R), _ld(R), _lib.ptr(keep), _ld(keep),
             float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, T, F_in, len(akinds), ak, len(skinds), sk,
@@ -74,10 +76,12 @@ def k1_backward_dst(graph: Graph, P, Q, R, keep, *, T: int, F_in: int, akinds, s
     """One launch of mmconv_aggregate_bwd_dst (destination pass of K1's backward)."""
     dev = graph.device
     ak, sk = _lib.i32_array(akinds), _lib.i32_array(skinds)
+    chunks = graph.k1_chunks()
     with _lib.kernel_scope("mmconv_aggregate_bwd_dst", dev):
         _lib.check(_lib.lib().mmconv_aggregate_bwd_dst(
             _lib.ptr(graph.rowptr), _lib.ptr(graph.col), _lib.ptr(graph.perm), _lib.ptr(graph.gid), graph.E_total,
-            _lib.ptr(graph.row_map), _lib.ptr(graph.rng_row), int(graph.rng_row0), graph.n_dst, graph.E,
+            _lib.ptr(graph.row_map), _lib.ptr(graph.rng_row), int(graph.rng_row0), _lib.ptr(chunks),
+            0 if chunks is None else chunks.numel() - 1, graph.n_dst, graph.E,
             _lib.ptr(P), _ld(P), (_lib.ptr(Q) if q_ptr is None else q_ptr), (_ld(Q) if ldq is None else ldq),
             _lib.ptr(R), _ld(R), _lib.ptr(keep), _ld(keep),
             float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, T, F_in, len(akinds), ak, len(skinds), sk,

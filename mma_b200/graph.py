@@ -134,6 +134,25 @@ class Graph:
                 self._max_deg = int((self.rowptr[1:] - self.rowptr[:-1]).max().item())
         return self._max_deg
 
+    K1_ROW_COST = 6          # a row costs about this many edges in the K1 kernels (epilogue, per-row loads)
+    K1_CHUNKS_PER_WARP = 16
+
+    def k1_chunks(self) -> Optional[Tensor]:
+        """Work partition of the persistent K1 kernels (include/mma_b200.h, `row_chunks`): int32
+        [n_chunks + 1] row boundaries of chunks of about equal cost (edges + K1_ROW_COST per row),
+        K1_CHUNKS_PER_WARP chunks per resident warp, dealt round-robin in the kernel.  Built once per graph."""
+        ch = self.__dict__.get("_k1_chunks")
+        if ch is None:
+            n = self.n_dst
+            sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+            n_chunks = max(1, min(sms * 16 * self.K1_CHUNKS_PER_WARP, n // 8))
+            cost = self.rowptr.to(torch.int64) + self.K1_ROW_COST * torch.arange(n + 1, device=self.device)
+            targets = (torch.arange(n_chunks + 1, device=self.device, dtype=torch.int64) * int(cost[-1].item())) // n_chunks
+            ch = torch.searchsorted(cost, targets, right=False).clamp_(max=n).to(torch.int32)
+            ch[0], ch[-1] = 0, n
+            ch = self.__dict__["_k1_chunks"] = ch.contiguous()
+        return ch
+
     @staticmethod
     def from_edge_index(edge_index: Tensor, num_nodes: int, need_transpose: bool = True,
                         sort_rows: bool = False, relabel: bool = False) -> "Graph":
