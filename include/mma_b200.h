@@ -248,9 +248,12 @@ int mma_tf32_split(const float *w, float *hi, float *lo, int64_t n, mma_stream_t
  *     GROUPED GEMM -- rows [row0, row_end) use the weight rows b_off .. b_off+N (degree ranges
  *     with scaler-folded weights); null = plain GEMM over M rows, b_off = 0;
  *   out_map (optional) int32 [M]: output row of input row r (row scatter fused in the epilogue);
- *   bias [N], add (indexed like C, may alias C) optional.
+ *   bias [N], add (indexed like C, i.e. by OUTPUT row, may alias C; with MMA_GEMM_ADD_BY_INPUT_ROW
+ *     or-ed into `mode`: indexed by the input row r) optional.
  *   mode 0 = 3xTF32 (hi written back), 1 = 3xTF32 (raw operand as hi), 2 = plain TF32 (not fp32-accurate).
  *   max_ctas <= 0: one persistent CTA per SM. */
+#define MMA_GEMM_ADD_BY_INPUT_ROW 4
+
 int mma_linear_tf32x3(const float *A0, int64_t lda0, int K0, const float *A1, int64_t lda1, int K1,
                       const float *Bhi, const float *Blo, int64_t ldb, int64_t b_rows,
                       int64_t M, int N, const int32_t *tile_tab, int64_t n_tiles_m,

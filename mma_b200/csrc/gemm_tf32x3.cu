@@ -51,8 +51,9 @@ struct alignas(64) NtParams {
     int64_t ldc;
     const int32_t *out_map;     // output row of tile row r (null: r)
     const float *bias;          // [N]
-    const float *add;           // indexed like C
+    const float *add;           // indexed like C (output rows) or, add_in != 0, by the input row
     int64_t ldadd;
+    int add_in;
 };
 
 struct Tile { int64_t row0, row_end; int b_off, n0; };
@@ -89,7 +90,7 @@ __device__ __forceinline__ void load_acc(uint32_t taddr, bool with_corr, uint32_
 // conflict-free both ways) so that every store instruction writes 4 rows x 128 B of full lines.
 __device__ __forceinline__ void store_chunk(float *stg, const uint32_t (&r)[32], int lane, int64_t row0, int64_t row_end,
                                             int col0, int n_cols, float *C, int64_t ldc, const int32_t *out_map,
-                                            const float *bias, const float *add, int64_t ldadd) {
+                                            const float *bias, const float *add, int64_t ldadd, int add_in) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
@@ -111,7 +112,7 @@ __device__ __forceinline__ void store_chunk(float *stg, const uint32_t (&r)[32],
                 v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
             }
             if (add) {
-                const float4 a = __ldcs(reinterpret_cast<const float4 *>(add + orow * ldadd + col));
+                const float4 a = __ldcs(reinterpret_cast<const float4 *>(add + (add_in ? grow : orow) * ldadd + col));
                 v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
             }
             __stcs(reinterpret_cast<float4 *>(C + orow * ldc + col), v);
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
                     if (lane == 0) mbar_arrive(tempty_bar(buf));
                 }
                 store_chunk(stg, r, lane, tl.row0 + wq * 32, tl.row_end, tl.n0 + c * 32, p.N, p.C, p.ldc, p.out_map,
-                            p.bias, p.add, p.ldadd);
+                            p.bias, p.add, p.ldadd, p.add_in);
                 __syncwarp();
             }
         }
@@ -448,7 +449,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_con
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tempty_bar(buf));
                 }
-                store_chunk(stg, r, lane, x.n0 + wq * 32, p.N, x.k0 + c * 32, p.K, out, p.K, nullptr, nullptr, nullptr, 0);
+                store_chunk(stg, r, lane, x.n0 + wq * 32, p.N, x.k0 + c * 32, p.K, out, p.K, nullptr, nullptr, nullptr, 0, 0);
             }
         }
     }
@@ -458,18 +459,32 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_con
     if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-// out[i] = sum_s coef[s] * part[s][i] in slab order (coef null: 1)
-__global__ void reduce_slabs_kernel(const float *__restrict__ part, const float *__restrict__ coef, int64_t n_slots,
-                                    int64_t n4, float *__restrict__ out) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n4) return;
+// out[i] = sum_s coef[s] * part[s][i] (coef null: 1).  Block = 32 float4 columns x 32 slab partitions:
+// partition ty sums its contiguous range of slabs in ascending order, then the 32 partial sums are added
+// in ascending ty -- a fixed summation tree, so the result is bit-reproducible (no atomics).
+__global__ void __launch_bounds__(1024) reduce_slabs_kernel(const float *__restrict__ part, const float *__restrict__ coef,
+                                                            int64_t n_slots, int64_t n4, float *__restrict__ out) {
+    __shared__ float4 sm[32][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * 32 + tx;
+    const int64_t per = (n_slots + 31) / 32;
+    const int64_t s0 = ty * per, s1 = s0 + per < n_slots ? s0 + per : n_slots;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t s = 0; s < n_slots; ++s) {
-        const float4 v = __ldcs(reinterpret_cast<const float4 *>(part) + s * n4 + i);
-        const float c = coef ? __ldg(coef + s) : 1.0f;
-        acc.x += c * v.x; acc.y += c * v.y; acc.z += c * v.z; acc.w += c * v.w;
+    if (i < n4) {
+#pragma unroll 4
+        for (int64_t s = s0; s < s1; ++s) {
+            const float4 v = __ldcs(reinterpret_cast<const float4 *>(part) + s * n4 + i);
+            const float c = coef ? __ldg(coef + s) : 1.0f;
+            acc.x += c * v.x; acc.y += c * v.y; acc.z += c * v.z; acc.w += c * v.w;
+        }
     }
-    reinterpret_cast<float4 *>(out)[i] = acc;
+    sm[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && i < n4) {
+        float4 t = sm[0][tx];
+        for (int k = 1; k < 32; ++k) { const float4 v = sm[k][tx]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+        reinterpret_cast<float4 *>(out)[i] = t;
+    }
 }
 
 // out[g][i] = sum over slots s in [seg_ptr[g], seg_ptr[g+1]) of part[s][i], ascending s
@@ -554,9 +569,10 @@ extern "C" int mma_linear_tf32x3(const float *A0, int64_t lda0, int K0, const fl
                                  const float *Bhi, const float *Blo, int64_t ldb, int64_t b_rows,
                                  int64_t M, int N, const int32_t *tile_tab, int64_t n_tiles_m,
                                  float *C, int64_t ldc, const int32_t *out_map, const float *bias,
-                                 const float *add, int64_t ldadd, int mode, int max_ctas, mma_stream_t stream) {
+                                 const float *add, int64_t ldadd, int mode_flags, int max_ctas, mma_stream_t stream) {
     if (!A0 || !Bhi || !Blo || !C || M < 0 || N < 1 || K0 < 1 || K1 < 0 || b_rows < 1) return MMA_ERR_INVALID;
-    if (mode < 0 || mode > 2) return MMA_ERR_INVALID;
+    const int mode = mode_flags & 3;
+    if (mode_flags < 0 || mode > 2 || (mode_flags & ~(3 | MMA_GEMM_ADD_BY_INPUT_ROW))) return MMA_ERR_INVALID;
     if ((N % 4) != 0 || (ldc % 4) != 0 || !aligned16(C) || !aligned16(bias) || !aligned16(add) || (ldadd % 4) != 0)
         return MMA_ERR_UNSUPPORTED;
     if (K1 > 0 && (!A1 || (K0 % BK) != 0)) return MMA_ERR_INVALID;
@@ -579,6 +595,7 @@ extern "C" int mma_linear_tf32x3(const float *A0, int64_t lda0, int K0, const fl
     p.n_tiles_m = tile_tab ? n_tiles_m : (M + BM - 1) / BM;
     if (p.n_tiles_m < 1) return tile_tab ? MMA_OK : MMA_ERR_INVALID;
     p.C = C; p.ldc = ldc; p.out_map = out_map; p.bias = bias; p.add = add; p.ldadd = ldadd;
+    p.add_in = (mode_flags & MMA_GEMM_ADD_BY_INPUT_ROW) ? 1 : 0;
     MMA_CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     int sms = 0, dev = 0;
     MMA_CUDA_CHECK(cudaGetDevice(&dev));
@@ -630,7 +647,7 @@ extern "C" int mma_reduce_slabs(const float *part, const float *coef, int64_t n_
         return MMA_ERR_INVALID;
     if (n == 0) return MMA_OK;
     const int64_t n4 = n / 4;
-    reduce_slabs_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    reduce_slabs_kernel<<<(unsigned)((n4 + 31) / 32), dim3(32, 32), 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         part, coef, n_slots, n4, out);
     MMA_LAUNCH_CHECK();
     return MMA_OK;

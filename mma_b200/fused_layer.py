@@ -5,10 +5,10 @@ reference (graph_regression/mma_conv.py)                  here, all rows in degr
 x.view(-1,1,F).repeat(1,T,1)                (:128)        x_s = x[node_perm]                      (row gather)
 mask Linear over cat([x_i,x_j])   (:146-152, mask_aggr)   [P|Q|XW] = x_s [W_i;W_j;W_x]^T + [b;0;b_post]  (G1, tcgen05)
 dropout + A scatters + degree     (:157-179)              Z = K1(P, Q)      raw aggregates [N, A*F]
-S cumulative scalers, cat, post Linear (:181-196,132-133) H = Z W_eff(deg)^T + XW   (G2: grouped tcgen05 GEMM,
+S cumulative scalers, cat, post Linear (:181-196,132-133) out = Z W_c(deg)^T + XW   (G2: grouped tcgen05 GEMM,
                                                             one effective weight per equal-degree row range)
-lin                                (:136)                  out[node_perm[r]] = H[r] W_lin^T + b   (G3, row scatter fused
-                                                            in the epilogue)
+lin                                (:136)                  composed into G1 / G2 (no nonlinearity in between): W_lin W_eff(d),
+                                                            W_lin W_x; G2's epilogue scatters rows back to node order
 autograd backward                  (mma.py:157)            dgrad = same GEMM kernel on transposed weights, wgrad =
                                                             split-K tcgen05 kernel + fixed-order slab reduction,
                                                             K1 destination pass + transpose-CSR pass (no atomics)
@@ -110,92 +110,117 @@ def _k1_bwd(graph: Graph, P, Q, R, keep, F, akinds, p_drop, seed, dZ, arg_min, a
 
 
 class _FusedMMAConv(torch.autograd.Function):
+    """post_layers == 1: there is no nonlinearity between the post Linear (mma_conv.py:132-133) and `lin`
+    (:136), so the two compose:  out = Z (W_lin W_eff(d))^T + x (W_lin W_x)^T + (W_lin b_post + b_lin).
+    The composed x-part rides along in G1, H is never materialised, and `lin` costs no GEMM of its own
+    in either direction; the gradients of W_lin / W_post are recovered from those of the composed
+    weights by small [F_out x K] matrix products."""
+
     @staticmethod
-    def forward(ctx, x, W1, b1, Wy, Wlin, blin, R, keep, graph: Graph, plan: PostPlan, cfg):
-        F, Fo, akinds, p_drop, seed = cfg
-        dev = _lib.require_cuda(x, W1, Wy, Wlin)
+    def forward(ctx, x, Wm, bm, Wp, bp, Wl, bl, R, keep, graph: Graph, plan: PostPlan, cfg):
+        F, akinds, p_drop, seed = cfg
+        dev = _lib.require_cuda(x, Wm, Wp, Wl)
         n = graph.n_dst
         A, S = len(akinds), plan.S
         K = A * F
+        Fo, Co = Wp.shape[0], Wl.shape[0]
+        zeros = lambda k: torch.zeros(k, dtype=torch.float32, device=dev)
+        Wx, Wy = Wp[:, :F], Wp[:, F:].contiguous()
+        Wcx = Wl @ Wx                                                                               # [Co, F]
+        bc = (Wl @ bp if bp is not None else zeros(Co)) + (bl if bl is not None else zeros(Co))
+        W1 = torch.cat([Wm[:, :F], Wm[:, F:2 * F], Wcx], dim=0)                                     # [2F+Co, F]
+        b1 = torch.cat([bm if bm is not None else zeros(F), zeros(F), bc])
         x_s = x.index_select(0, graph.node_perm)
         W1hi, W1lo = tg.split_weight(W1)
-        PQX = tg.linear(x_s, W1hi, W1lo, 2 * F + Fo, bias=b1, name="gemm_mask_proj")              # [n, 2F+Fo]
+        PQX = tg.linear(x_s, W1hi, W1lo, 2 * F + Co, bias=b1, name="gemm_mask_proj")                # [n, 2F+Co]
         P, Q, XW = PQX[:, :F], PQX[:, F:2 * F], PQX[:, 2 * F:]
         Z, arg_min, arg_max, mean, var = _k1_fwd(graph, P, Q, R, keep, F, akinds, p_drop, seed)
-        H = torch.empty((n, Fo), dtype=torch.float32, device=dev)
+        out = torch.empty((n, Co), dtype=torch.float32, device=dev)
         Ws = Wy.view(Fo, S, K)
-        Weff = None
+        Weff = Wc = None
         if plan.big:
             Weff = torch.einsum("sb,osk->bok", plan.cum_big, Ws).contiguous()                       # [B, Fo, K]
-            hi, lo = tg.split_weight(Weff.view(-1, K))
-            tg.linear(Z, hi, lo, Fo, tile_tab=plan.tile_tab, out=H, add=XW, name="gemm_post_grouped")
+            Wc = torch.matmul(Wl, Weff).contiguous()                                                # [B, Co, K]
+            hi, lo = tg.split_weight(Wc.view(-1, K))
+            tg.linear(Z, hi, lo, Co, tile_tab=plan.tile_tab, out=out, out_map=graph.node_perm32, add=XW,
+                      add_by_input_row=True, name="gemm_post_grouped")
         if plan.tail_idx is not None:
-            Zt = Z.index_select(0, plan.tail_idx)
+            ti = plan.tail_idx
+            Zt = Z.index_select(0, ti)
             ct = plan.cum[:, plan.tail_bucket].t()                                                  # [nt, S]
             Yt = (Zt.unsqueeze(1) * ct.unsqueeze(2)).reshape(Zt.shape[0], S * K)
-            H.index_copy_(0, plan.tail_idx, Yt @ Wy.t() + XW.index_select(0, plan.tail_idx))
-        lhi, llo = tg.split_weight(Wlin)
-        out = torch.empty((n, Wlin.shape[0]), dtype=torch.float32, device=dev)
-        tg.linear(H, lhi, llo, Wlin.shape[0], bias=blin, out=out, out_map=graph.node_perm32, name="gemm_lin")
+            out.index_copy_(0, graph.node_perm.index_select(0, ti), (Yt @ Wy.t()) @ Wl.t() + XW.index_select(0, ti))
         ctx.graph, ctx.plan, ctx.cfg = graph, plan, cfg
-        ctx.has_R = R is not None
-        ctx.save_for_backward(x_s, PQX, Z, H, W1, Wy, Wlin, Weff, R, keep, arg_min, arg_max, mean, var)
+        ctx.has_R, ctx.has_b = R is not None, (bm is not None, bp is not None, bl is not None)
+        ctx.save_for_backward(x_s, PQX, Z, Wm, Wp, bp, Wl, Weff, Wc, R, keep, arg_min, arg_max, mean, var)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
-        x_s, PQX, Z, H, W1, Wy, Wlin, Weff, R, keep, arg_min, arg_max, mean, var = ctx.saved_tensors
+        x_s, PQX, Z, Wm, Wp, bp, Wl, Weff, Wc, R, keep, arg_min, arg_max, mean, var = ctx.saved_tensors
         graph, plan = ctx.graph, ctx.plan
-        F, Fo, akinds, p_drop, seed = ctx.cfg
+        F, akinds, p_drop, seed = ctx.cfg
         dev = d_out.device
         n = graph.n_dst
         A, S = len(akinds), plan.S
         K = A * F
-        P, Q, XW = PQX[:, :F], PQX[:, F:2 * F], PQX[:, 2 * F:]
-        d_out = d_out.contiguous()
-        d_out_s = d_out.index_select(0, graph.node_perm)
-        # ---- lin
-        thi, tlo = tg.split_weight(Wlin.t())
-        dH = tg.linear(d_out_s, thi, tlo, Wlin.shape[1], name="gemm_lin_dgrad")                     # [n, Fo]
-        dWlin = tg.wgrad(d_out_s, H, name="gemm_lin_wgrad")
-        dblin = d_out.sum(0)
-        # ---- grouped post transform
+        Fo, Co = Wp.shape[0], Wl.shape[0]
+        P, Q = PQX[:, :F], PQX[:, F:2 * F]
+        Wx, Wy = Wp[:, :F], Wp[:, F:].contiguous()
+        dO = d_out.index_select(0, graph.node_perm)                                                 # sorted rows
+        dbc = d_out.sum(0)                                                                          # [Co]
+        # ---- grouped post transform (composed with lin)
         dZ = torch.empty((n, K), dtype=torch.float32, device=dev)
+        dWl = torch.outer(dbc, bp) if bp is not None else torch.zeros_like(Wl)
         dWy = None
         if plan.big:
-            WeffT = Weff.transpose(1, 2).contiguous()                                               # [B, K, Fo]
-            hi, lo = tg.split_weight(WeffT.view(-1, Fo))
-            tg.linear(dH, hi, lo, K, tile_tab=plan.tile_tab_t, out=dZ, name="gemm_post_dgrad")
-            part = tg.wgrad_partials(dH, Z, plan.slabs, plan.slabs.shape[0], name="gemm_post_wgrad")
-            dWeff = tg.reduce_slabs_segmented(part, plan.seg_ptr)                                   # [B, Fo, K]
+            WcT = Wc.transpose(1, 2).contiguous()                                                   # [B, K, Co]
+            hi, lo = tg.split_weight(WcT.view(-1, Co))
+            tg.linear(dO, hi, lo, K, tile_tab=plan.tile_tab_t, out=dZ, name="gemm_post_dgrad")
+            part = tg.wgrad_partials(dO, Z, plan.slabs, plan.slabs.shape[0], name="gemm_post_wgrad")
+            dWc = tg.reduce_slabs_segmented(part, plan.seg_ptr)                                     # [B, Co, K]
+            dWl = dWl + torch.einsum("bck,bok->co", dWc, Weff)
+            dWeff = torch.matmul(Wl.t(), dWc)                                                       # [B, Fo, K]
             dWy = torch.einsum("sb,bok->osk", plan.cum_big, dWeff).reshape(Fo, S * K)
         if plan.tail_idx is not None:
             ti = plan.tail_idx
             Zt = Z.index_select(0, ti)
             ct = plan.cum[:, plan.tail_bucket].t()
-            dHt = dH.index_select(0, ti)
+            dOt = dO.index_select(0, ti)
+            dHt = dOt @ Wl
             dYt = (dHt @ Wy).view(-1, S, K)
             dZ.index_copy_(0, ti, (dYt * ct.unsqueeze(2)).sum(dim=1))
             Yt = (Zt.unsqueeze(1) * ct.unsqueeze(2)).reshape(Zt.shape[0], S * K)
+            dWl = dWl + dOt.t() @ (Yt @ Wy.t())
             g = dHt.t() @ Yt
             dWy = g if dWy is None else dWy + g
         # ---- K1 backward: dP, dQ (and dR)
         dPQ = torch.empty((n, 2 * F), dtype=torch.float32, device=dev)
-        need_R = ctx.has_R and ctx.needs_input_grad[6]
+        need_R = ctx.has_R and ctx.needs_input_grad[7]
         dR = _k1_bwd(graph, P, Q, R, keep, F, akinds, p_drop, seed, dZ, arg_min, arg_max, mean, var, dPQ, need_R)
         del dZ
-        # ---- mask projection: dx (scattered back to node order), dW1, db1
+        # ---- mask projection + composed x-part: dx (scattered back to node order), dW1
+        Wcx = Wl @ Wx
+        W1 = torch.cat([Wm[:, :F], Wm[:, F:2 * F], Wcx], dim=0)
         w1hi, w1lo = tg.split_weight(W1.t())
-        dx = torch.empty((n, W1.shape[1]), dtype=torch.float32, device=dev)
+        dx = torch.empty((n, F), dtype=torch.float32, device=dev)
         if (2 * F) % 128 == 0:
-            tg.linear(dPQ, w1hi, w1lo, W1.shape[1], A1=dH, out=dx, out_map=graph.node_perm32, name="gemm_mask_dgrad")
-            dW1 = tg.wgrad(dPQ, x_s, G1=dH, name="gemm_mask_wgrad")
+            tg.linear(dPQ, w1hi, w1lo, F, A1=dO, out=dx, out_map=graph.node_perm32, name="gemm_mask_dgrad")
+            dW1 = tg.wgrad(dPQ, x_s, G1=dO, name="gemm_mask_wgrad")
         else:
-            dPQX = torch.cat([dPQ, dH], dim=1)
-            tg.linear(dPQX, w1hi, w1lo, W1.shape[1], out=dx, out_map=graph.node_perm32, name="gemm_mask_dgrad")
+            dPQX = torch.cat([dPQ, dO], dim=1)
+            tg.linear(dPQX, w1hi, w1lo, F, out=dx, out_map=graph.node_perm32, name="gemm_mask_dgrad")
             dW1 = tg.wgrad(dPQX, x_s, name="gemm_mask_wgrad")
-        db1 = torch.cat([dPQ.sum(0), dH.sum(0)])
-        return dx, dW1, db1, dWy, dWlin, dblin, dR, None, None, None, None
+        dWm = torch.zeros_like(Wm)
+        dWm[:, :F] = dW1[:F]
+        dWm[:, F:2 * F] = dW1[F:2 * F]
+        dWcx = dW1[2 * F:]                                                                          # [Co, F]
+        dWl = dWl + dWcx @ Wx.t()
+        dWp = torch.cat([Wl.t() @ dWcx, dWy if dWy is not None else torch.zeros_like(Wy)], dim=1)
+        has_bm, has_bp, has_bl = ctx.has_b
+        dbm = dPQ[:, :F].sum(0) if has_bm else None
+        dbp = dbc @ Wl if has_bp else None
+        return dx, dWm, dbm, dWp, dbp, dWl, (dbc if has_bl else None), dR, None, None, None, None
 
 
 def supported(F_in: int, F_out: int, out_channels: int) -> bool:
@@ -208,24 +233,17 @@ def fused_mmaconv(x: Tensor, graph: Graph, *, W_mask: Tensor, b_mask: Optional[T
                   keep: Optional[Tensor], aggregators: Sequence[str], scalers: Sequence[str],
                   avg_deg: Dict[str, float], p_drop: float, seed: int, min_rows: int) -> Tensor:
     """x [N, F] (node order) -> MMAConv output [N, out] for towers == 1, pre_layers == post_layers == 1.
-    W_mask [F, 2F or 3F] (the live mask Linear, Q2), W_post [Fo, (S*A+1)*F], W_lin [out, Fo]."""
+    W_mask [F, 2F or 3F] (the live mask Linear, Q2; only the first 2F columns are used here, the edge
+    part arrives as R), W_post [Fo, (S*A+1)*F], W_lin [out, Fo]."""
     if graph.node_perm is None or graph.buckets is None:
         raise RuntimeError("fused_mmaconv needs a Graph built with sort_rows=True, relabel=True")
     F = x.shape[1]
-    Fo = W_post.shape[0]
     for a in aggregators:                       # aggregate(), mma_conv.py:164-177: exact names only
         if a not in _lib.AGGR_KINDS:
             raise ValueError(f'Unknown aggregator "{a}".')
     if len(aggregators) > _lib.MAX_AGGR or len(scalers) > _lib.MAX_SCALER:
         raise _lib.MMAError("more than 8 aggregators or scalers in one call")
     akinds = tuple(_lib.AGGR_KINDS[a] for a in aggregators)
-    dev = x.device
-    zeros = lambda k: torch.zeros(k, dtype=torch.float32, device=dev)
-    W1 = torch.cat([W_mask[:, :F], W_mask[:, F:2 * F], W_post[:, :F]], dim=0)                        # [2F+Fo, F]
-    b1 = torch.cat([b_mask if b_mask is not None else zeros(F), zeros(F),
-                    b_post if b_post is not None else zeros(Fo)])
-    Wy = W_post[:, F:]
-    plan = post_plan(graph, scalers, avg_deg, min_rows, Fo, len(akinds) * F)
-    blin = b_lin if b_lin is not None else zeros(W_lin.shape[0])
-    return _FusedMMAConv.apply(x, W1, b1, Wy.contiguous(), W_lin, blin, R, keep, graph, plan,
-                               (F, Fo, akinds, float(p_drop), int(seed)))
+    plan = post_plan(graph, scalers, avg_deg, min_rows, W_lin.shape[0], len(akinds) * F)
+    return _FusedMMAConv.apply(x, W_mask, b_mask, W_post, b_post, W_lin, b_lin, R, keep, graph, plan,
+                               (F, akinds, float(p_drop), int(seed)))

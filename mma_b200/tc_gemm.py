@@ -15,6 +15,7 @@ from . import _lib
 
 BM = BN = 128
 BK = 32
+ADD_BY_INPUT_ROW = 4    # MMA_GEMM_ADD_BY_INPUT_ROW
 MODE = 0            # 0: 3xTF32 with the hi part written back (safe); 1: raw operand as hi; 2: plain TF32
 
 
@@ -42,9 +43,10 @@ def split_weight(W: Tensor) -> Tuple[Tensor, Tensor]:
 
 def linear(A0: Tensor, Whi: Tensor, Wlo: Tensor, n_out: int, *, A1: Optional[Tensor] = None,
            tile_tab: Optional[Tensor] = None, out: Optional[Tensor] = None, out_map: Optional[Tensor] = None,
-           bias: Optional[Tensor] = None, add: Optional[Tensor] = None, mode: Optional[int] = None,
-           max_ctas: int = 0, name: str = "mma_linear_tf32x3") -> Tensor:
-    """out[out_map[r]] = [A0|A1][r] @ W[b_off : b_off + n_out].T (+ bias) (+ add[out_map[r]]).
+           bias: Optional[Tensor] = None, add: Optional[Tensor] = None, add_by_input_row: bool = False,
+           mode: Optional[int] = None, max_ctas: int = 0, name: str = "mma_linear_tf32x3") -> Tensor:
+    """out[out_map[r]] = [A0|A1][r] @ W[b_off : b_off + n_out].T (+ bias) (+ add[out_map[r]], or add[r]
+    with add_by_input_row).
 
     Whi/Wlo: [b_rows, K0+K1] (stacked weights for a grouped GEMM; `tile_tab` int32 [tiles, 4] =
     (row0, row_end, b_off, 0) selects the weight per 128-row tile)."""
@@ -66,7 +68,8 @@ def linear(A0: Tensor, Whi: Tensor, Wlo: Tensor, n_out: int, *, A1: Optional[Ten
             _lib.ptr(Whi), _lib.ptr(Wlo), Whi.stride(0), Whi.shape[0], M, n_out,
             _lib.ptr(tile_tab), 0 if tile_tab is None else tile_tab.shape[0],
             _lib.ptr(out), out.stride(0), _lib.ptr(out_map), _lib.ptr(bias), _lib.ptr(add),
-            0 if add is None else add.stride(0), MODE if mode is None else mode, max_ctas,
+            0 if add is None else add.stride(0),
+            (MODE if mode is None else mode) | (ADD_BY_INPUT_ROW if add_by_input_row else 0), max_ctas,
             _lib.stream_ptr(dev)), name)
     return out
 
