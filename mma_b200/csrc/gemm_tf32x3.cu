@@ -29,13 +29,21 @@ namespace gemm {
 using namespace tc;
 
 constexpr int BM = 128, BN = 128, BK = 32;
-constexpr int STAGES = 3;
 constexpr int A_BYTES = BM * BK * 4;                      // 16 KB
 constexpr int B_BYTES = BN * BK * 4;                      // 16 KB
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;    // A, A_lo, B_hi, B_lo
 constexpr int EPI_BYTES = 4 * 32 * 32 * 4;                // one 32x32 fp32 transpose buffer per epilogue warp
 constexpr int BAR_BYTES = 256;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;   // + alignment slack
+// The operands that come from HBM need ~90 KB in flight per SM to cover the DRAM latency at full
+// bandwidth, so the RAW tiles get a deep ring of their own; the split (lo) tiles live only from the
+// converter to the MMA and the weights come from L2, so their rings are shallow.
+//   linear: raw A ring (hi written in place) | A_lo ring | B ring (B_hi + B_lo per slot)
+constexpr int NT_NA = 5, NT_NL = 2, NT_NB = 3;
+constexpr int NT_SMEM_BYTES = (NT_NA + NT_NL) * A_BYTES + NT_NB * 2 * B_BYTES + EPI_BYTES + BAR_BYTES + 1024;
+constexpr int NT_THREADS = 352;                           // + 1 warp: the B (weight) producer
+//   wgrad: raw [G | A] ring | [G_lo | A_lo] ring
+constexpr int WG_NR = 4, WG_NL = 2;
+constexpr int WG_SMEM_BYTES = (WG_NR + WG_NL) * (A_BYTES + B_BYTES) + EPI_BYTES + BAR_BYTES + 1024;
+static_assert(NT_SMEM_BYTES <= 232448 && WG_SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory per CTA");
 constexpr int THREADS = 320;
 constexpr int TMEM_COLS = 512;   // 2 tiles in flight x (main + correction) accumulators of 128 columns
 
@@ -121,19 +129,27 @@ __device__ __forceinline__ void store_chunk(float *stg, const uint32_t (&r)[32],
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_constant__ NtParams p) {
+__global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_kernel(const __grid_constant__ NtParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
-    const uint32_t epi_base = smem_base + STAGES * STAGE_BYTES;
+    const uint32_t lo_base = smem_base + NT_NA * A_BYTES;
+    const uint32_t b_base = lo_base + NT_NL * A_BYTES;
+    const uint32_t epi_base = b_base + NT_NB * 2 * B_BYTES;
     const uint32_t bar_base = epi_base + EPI_BYTES;
-    // barriers: full[3], conv[3], empty[3], tfull[2], tempty[2], then the TMEM base address word
-    auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto conv_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-    auto tfull_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + b); };
-    auto tempty_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + 2 + b); };
-    const uint32_t tmem_slot = bar_base + 8u * (3 * STAGES + 4);
+    // barriers: a_full[NA], a_empty[NA], lo_full[NL], lo_empty[NL], b_full[NB], b_empty[NB], tfull[2], tempty[2],
+    // then the TMEM base address word
+    auto a_full = [&](int i) { return bar_base + 8u * i; };
+    auto a_empty = [&](int i) { return bar_base + 8u * (NT_NA + i); };
+    auto lo_full = [&](int i) { return bar_base + 8u * (2 * NT_NA + i); };
+    auto lo_empty = [&](int i) { return bar_base + 8u * (2 * NT_NA + NT_NL + i); };
+    auto b_full = [&](int i) { return bar_base + 8u * (2 * NT_NA + 2 * NT_NL + i); };
+    auto b_empty = [&](int i) { return bar_base + 8u * (2 * NT_NA + 2 * NT_NL + NT_NB + i); };
+    constexpr int kTBar = 2 * NT_NA + 2 * NT_NL + 2 * NT_NB;
+    auto tfull_bar = [&](int b) { return bar_base + 8u * (kTBar + b); };
+    auto tempty_bar = [&](int b) { return bar_base + 8u * (kTBar + 2 + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (kTBar + 4);
+    static_assert(8 * (kTBar + 4) + 4 <= BAR_BYTES, "barrier block too small");
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem + (tmem_slot - smem_base));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -142,7 +158,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.map_a0); tma_prefetch_desc(&p.map_a1);
         tma_prefetch_desc(&p.map_bhi); tma_prefetch_desc(&p.map_blo);
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(conv_bar(s), 4); mbar_init(empty_bar(s), 1); }
+        for (int i = 0; i < NT_NA; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
+        for (int i = 0; i < NT_NL; ++i) { mbar_init(lo_full(i), 4); mbar_init(lo_empty(i), 1); }
+        for (int i = 0; i < NT_NB; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
         fence_barrier_init();
     }
@@ -153,21 +171,33 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     if (warp == 0) {
-        // ===================================================================== TMA producer
+        // ===================================================================== TMA producer: activations (HBM)
         if (lane == 0) {
             uint32_t it = 0;
             for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
                 const Tile tl = locate_tile(p, t);
                 for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1u;
-                    mbar_wait(empty_bar(s), ph ^ 1u);
-                    const uint32_t sa = smem_base + s * STAGE_BYTES;
-                    mbar_expect_tx(full_bar(s), A_BYTES + (p.mode == 2 ? 1 : 2) * B_BYTES);
-                    if (kb < p.kb_split) tma_load_2d(sa, &p.map_a0, full_bar(s), kb * BK, (int)tl.row0);
-                    else tma_load_2d(sa, &p.map_a1, full_bar(s), (kb - p.kb_split) * BK, (int)tl.row0);
-                    tma_load_2d(sa + 2 * A_BYTES, &p.map_bhi, full_bar(s), kb * BK, tl.b_off + tl.n0);
-                    if (p.mode != 2) tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &p.map_blo, full_bar(s), kb * BK, tl.b_off + tl.n0);
+                    const int sa = it % NT_NA;
+                    mbar_wait(a_empty(sa), ((it / NT_NA) & 1u) ^ 1u);
+                    mbar_expect_tx(a_full(sa), A_BYTES);
+                    if (kb < p.kb_split) tma_load_2d(smem_base + sa * A_BYTES, &p.map_a0, a_full(sa), kb * BK, (int)tl.row0);
+                    else tma_load_2d(smem_base + sa * A_BYTES, &p.map_a1, a_full(sa), (kb - p.kb_split) * BK, (int)tl.row0);
+                }
+            }
+        }
+    } else if (warp == 10) {
+        // ===================================================================== TMA producer: weights (L2)
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const Tile tl = locate_tile(p, t);
+                for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+                    const int sb = it % NT_NB;
+                    mbar_wait(b_empty(sb), ((it / NT_NB) & 1u) ^ 1u);
+                    const uint32_t dst = b_base + sb * 2 * B_BYTES;
+                    mbar_expect_tx(b_full(sb), (p.mode == 2 ? 1 : 2) * B_BYTES);
+                    tma_load_2d(dst, &p.map_bhi, b_full(sb), kb * BK, tl.b_off + tl.n0);
+                    if (p.mode != 2) tma_load_2d(dst + B_BYTES, &p.map_blo, b_full(sb), kb * BK, tl.b_off + tl.n0);
                 }
             }
         }
@@ -182,18 +212,18 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * 2 * BN;      // main accumulator; correction at +BN
                 for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1u;
-                    mbar_wait(full_bar(s), ph);
-                    if (p.mode != 2) mbar_wait(conv_bar(s), ph);
+                    const int sa = it % NT_NA, sl = it % NT_NL, sb = it % NT_NB;
+                    mbar_wait(a_full(sa), (it / NT_NA) & 1u);
+                    if (p.mode != 2) mbar_wait(lo_full(sl), (it / NT_NL) & 1u);
+                    mbar_wait(b_full(sb), (it / NT_NB) & 1u);
                     tc_fence_after();
-                    const uint32_t sa = smem_base + s * STAGE_BYTES;
+                    const uint32_t pa = smem_base + sa * A_BYTES, pl = lo_base + sl * A_BYTES, pb = b_base + sb * 2 * B_BYTES;
 #pragma unroll
                     for (int k = 0; k < BK / 8; ++k) {
-                        const uint64_t a_hi = umma_desc_sw128(sa + k * 32, 16, 1024);
-                        const uint64_t a_lo = umma_desc_sw128(sa + A_BYTES + k * 32, 16, 1024);
-                        const uint64_t b_hi = umma_desc_sw128(sa + 2 * A_BYTES + k * 32, 16, 1024);
-                        const uint64_t b_lo = umma_desc_sw128(sa + 2 * A_BYTES + B_BYTES + k * 32, 16, 1024);
+                        const uint64_t a_hi = umma_desc_sw128(pa + k * 32, 16, 1024);
+                        const uint64_t a_lo = umma_desc_sw128(pl + k * 32, 16, 1024);
+                        const uint64_t b_hi = umma_desc_sw128(pb + k * 32, 16, 1024);
+                        const uint64_t b_lo = umma_desc_sw128(pb + B_BYTES + k * 32, 16, 1024);
                         const uint32_t first = (kb | k) != 0;
                         // The tensor core truncates when it adds into the fp32 accumulator, a bias that grows
                         // with the length of the accumulation chain.  The two small cross terms go to their
@@ -205,7 +235,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
                         }
                         umma_tf32_ss(d_tmem, a_hi, b_hi, idesc, first);
                     }
-                    tc_commit(empty_bar(s));            // smem stage reusable once these MMAs retire
+                    tc_commit(a_empty(sa));             // slots reusable once these MMAs retire
+                    if (p.mode != 2) tc_commit(lo_empty(sl));
+                    tc_commit(b_empty(sb));
                 }
                 tc_commit(tfull_bar(buf));              // accumulator complete
             }
@@ -217,27 +249,34 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
             uint32_t it = 0;
             for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
                 for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1u;
-                    mbar_wait(full_bar(s), ph);
-                    float4 *a = reinterpret_cast<float4 *>(smem + s * STAGE_BYTES);
-                    float4 *alo = reinterpret_cast<float4 *>(smem + s * STAGE_BYTES + A_BYTES);
+                    const int sa = it % NT_NA, sl = it % NT_NL;
+                    mbar_wait(a_full(sa), (it / NT_NA) & 1u);
+                    mbar_wait(lo_empty(sl), ((it / NT_NL) & 1u) ^ 1u);
+                    float4 *a = reinterpret_cast<float4 *>(smem + sa * A_BYTES);
+                    float4 *alo = reinterpret_cast<float4 *>(smem + (lo_base - smem_base) + sl * A_BYTES);
+                    // all loads first (8 independent LDS.128 in flight), then the split: a serial
+                    // load -> split -> store chain made the converter the slowest stage of the pipeline
+                    float4 v[A_BYTES / 16 / 128];
 #pragma unroll
-                    for (int i = 0; i < A_BYTES / 16 / 128; ++i) {
-                        const float4 v = a[i * 128 + ct];
-                        if (p.mode == 0) {
-                            const float4 h = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
-                            alo[i * 128 + ct] = make_float4(tf32_rna(v.x - h.x), tf32_rna(v.y - h.y), tf32_rna(v.z - h.z),
-                                                            tf32_rna(v.w - h.w));
+                    for (int i = 0; i < A_BYTES / 16 / 128; ++i) v[i] = a[i * 128 + ct];
+                    if (p.mode == 0) {
+#pragma unroll
+                        for (int i = 0; i < A_BYTES / 16 / 128; ++i) {
+                            const float4 h = make_float4(tf32_rna(v[i].x), tf32_rna(v[i].y), tf32_rna(v[i].z), tf32_rna(v[i].w));
+                            alo[i * 128 + ct] = make_float4(tf32_rna(v[i].x - h.x), tf32_rna(v[i].y - h.y),
+                                                            tf32_rna(v[i].z - h.z), tf32_rna(v[i].w - h.w));
                             a[i * 128 + ct] = h;
-                        } else {        // the tensor core ignores the low 13 mantissa bits: raw A acts as trunc(A)
-                            const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-                            alo[i * 128 + ct] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                        }
+                    } else {            // the tensor core ignores the low 13 mantissa bits: raw A acts as trunc(A)
+#pragma unroll
+                        for (int i = 0; i < A_BYTES / 16 / 128; ++i) {
+                            const float4 h = make_float4(tf32_hi(v[i].x), tf32_hi(v[i].y), tf32_hi(v[i].z), tf32_hi(v[i].w));
+                            alo[i * 128 + ct] = make_float4(v[i].x - h.x, v[i].y - h.y, v[i].z - h.z, v[i].w - h.w);
                         }
                     }
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(conv_bar(s));
+                    if (lane == 0) mbar_arrive(lo_full(sl));
                 }
             }
         }
@@ -298,14 +337,19 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_con
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
-    const uint32_t epi_base = smem_base + STAGES * STAGE_BYTES;
+    constexpr int RAW_BYTES = A_BYTES + B_BYTES;           // one raw stage: G [4 x 4 KB] | A [4 x 4 KB]
+    const uint32_t lo_base = smem_base + WG_NR * RAW_BYTES;   // lo stage: G_lo | A_lo
+    const uint32_t epi_base = lo_base + WG_NL * RAW_BYTES;
     const uint32_t bar_base = epi_base + EPI_BYTES;
-    auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto conv_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-    auto tfull_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + b); };
-    auto tempty_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + 2 + b); };
-    const uint32_t tmem_slot = bar_base + 8u * (3 * STAGES + 4);
+    // barriers: full[NR] (TMA landed), empty[NR] (MMAs retired), lo_full[NL] (converted), lo_empty[NL]
+    auto full_bar = [&](int i) { return bar_base + 8u * i; };
+    auto empty_bar = [&](int i) { return bar_base + 8u * (WG_NR + i); };
+    auto lo_full = [&](int i) { return bar_base + 8u * (2 * WG_NR + i); };
+    auto lo_empty = [&](int i) { return bar_base + 8u * (2 * WG_NR + WG_NL + i); };
+    constexpr int kTBar = 2 * WG_NR + 2 * WG_NL;
+    auto tfull_bar = [&](int b) { return bar_base + 8u * (kTBar + b); };
+    auto tempty_bar = [&](int b) { return bar_base + 8u * (kTBar + 2 + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (kTBar + 4);
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem + (tmem_slot - smem_base));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -326,7 +370,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_con
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.map_g0); tma_prefetch_desc(&p.map_g1); tma_prefetch_desc(&p.map_a);
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(conv_bar(s), 4); mbar_init(empty_bar(s), 1); }
+        for (int i = 0; i < WG_NR; ++i) { mbar_init(full_bar(i), 1); mbar_init(empty_bar(i), 1); }
+        for (int i = 0; i < WG_NL; ++i) { mbar_init(lo_full(i), 4); mbar_init(lo_empty(i), 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
         fence_barrier_init();
     }
@@ -344,15 +389,14 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_con
                 const CUtensorMap *mg = x.n0 < p.n_split ? &p.map_g0 : &p.map_g1;
                 const int gc0 = x.n0 < p.n_split ? x.n0 : x.n0 - p.n_split;
                 for (int r = x.row0; r < x.row_end; r += BK, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1u;
-                    mbar_wait(empty_bar(s), ph ^ 1u);
-                    const uint32_t sa = smem_base + s * STAGE_BYTES;
-                    mbar_expect_tx(full_bar(s), A_BYTES + B_BYTES);
+                    const int s = it % WG_NR;
+                    mbar_wait(empty_bar(s), ((it / WG_NR) & 1u) ^ 1u);
+                    const uint32_t sa = smem_base + s * RAW_BYTES;
+                    mbar_expect_tx(full_bar(s), RAW_BYTES);
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         tma_load_2d(sa + g * 4096, mg, full_bar(s), gc0 + g * 32, r);
-                        tma_load_2d(sa + 2 * A_BYTES + g * 4096, &p.map_a, full_bar(s), x.k0 + g * 32, r);
+                        tma_load_2d(sa + A_BYTES + g * 4096, &p.map_a, full_bar(s), x.k0 + g * 32, r);
                     }
                 }
             }
@@ -369,18 +413,17 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_con
                 const uint32_t d_tmem = tmem_base + buf * 2 * BN;
                 uint32_t acc = 0;
                 for (int r = x.row0; r < x.row_end; r += BK, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1u;
-                    mbar_wait(full_bar(s), ph);
-                    mbar_wait(conv_bar(s), ph);
+                    const int s = it % WG_NR, sl = it % WG_NL;
+                    mbar_wait(full_bar(s), (it / WG_NR) & 1u);
+                    mbar_wait(lo_full(sl), (it / WG_NL) & 1u);
                     tc_fence_after();
-                    const uint32_t sa = smem_base + s * STAGE_BYTES;
+                    const uint32_t sa = smem_base + s * RAW_BYTES, sq = lo_base + sl * RAW_BYTES;
 #pragma unroll
                     for (int k = 0; k < BK / 8; ++k) {
                         const uint64_t g_hi = umma_desc(sa + k * 1024, 4096, 512, 1);
-                        const uint64_t g_lo = umma_desc(sa + A_BYTES + k * 1024, 4096, 512, 1);
-                        const uint64_t a_hi = umma_desc(sa + 2 * A_BYTES + k * 1024, 4096, 512, 1);
-                        const uint64_t a_lo = umma_desc(sa + 2 * A_BYTES + B_BYTES + k * 1024, 4096, 512, 1);
+                        const uint64_t g_lo = umma_desc(sq + k * 1024, 4096, 512, 1);
+                        const uint64_t a_hi = umma_desc(sa + A_BYTES + k * 1024, 4096, 512, 1);
+                        const uint64_t a_lo = umma_desc(sq + A_BYTES + k * 1024, 4096, 512, 1);
                         if (p.mode != 2) {
                             umma_tf32_ss(d_tmem + BN, g_lo, a_hi, idesc, acc);
                             umma_tf32_ss(d_tmem + BN, g_hi, a_lo, idesc, 1u);
@@ -389,6 +432,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_con
                         acc = 1u;
                     }
                     tc_commit(empty_bar(s));
+                    tc_commit(lo_empty(sl));
                 }
                 tc_commit(tfull_bar(buf));
             }
@@ -399,35 +443,39 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_con
         for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
             const Unit x = locate(u);
             for (int r = x.row0; r < x.row_end; r += BK, ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1u;
+                const int s = it % WG_NR, sl = it % WG_NL;
                 const int valid = x.row_end - r;            // rows of this block inside the slab (>= 32: all)
-                mbar_wait(full_bar(s), ph);
+                mbar_wait(full_bar(s), (it / WG_NR) & 1u);
+                mbar_wait(lo_empty(sl), ((it / WG_NL) & 1u) ^ 1u);
 #pragma unroll
                 for (int op = 0; op < 2; ++op) {
-                    float4 *a = reinterpret_cast<float4 *>(smem + s * STAGE_BYTES + op * 2 * A_BYTES);
-                    float4 *alo = a + A_BYTES / 16;
+                    float4 *a = reinterpret_cast<float4 *>(smem + s * RAW_BYTES + op * A_BYTES);
+                    float4 *alo = reinterpret_cast<float4 *>(smem + (lo_base - smem_base) + sl * RAW_BYTES + op * A_BYTES);
+                    float4 v[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int idx = i * 128 + ct;       // 16-byte chunk; box g = idx/256, row = (idx/8) % 32
-                        float4 v = a[idx];
-                        const bool dead = ((idx >> 3) & 31) >= valid;
-                        if (dead) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        v[i] = a[idx];
+                        if (((idx >> 3) & 31) >= valid) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int idx = i * 128 + ct;
                         if (p.mode == 0) {
-                            const float4 h = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
-                            alo[idx] = make_float4(tf32_rna(v.x - h.x), tf32_rna(v.y - h.y), tf32_rna(v.z - h.z),
-                                                   tf32_rna(v.w - h.w));
+                            const float4 h = make_float4(tf32_rna(v[i].x), tf32_rna(v[i].y), tf32_rna(v[i].z), tf32_rna(v[i].w));
+                            alo[idx] = make_float4(tf32_rna(v[i].x - h.x), tf32_rna(v[i].y - h.y), tf32_rna(v[i].z - h.z),
+                                                   tf32_rna(v[i].w - h.w));
                             a[idx] = h;
                         } else {
-                            const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-                            if (p.mode != 2) alo[idx] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                            const float4 h = make_float4(tf32_hi(v[i].x), tf32_hi(v[i].y), tf32_hi(v[i].z), tf32_hi(v[i].w));
+                            if (p.mode != 2) alo[idx] = make_float4(v[i].x - h.x, v[i].y - h.y, v[i].z - h.z, v[i].w - h.w);
                             if (valid < BK) a[idx] = h;
                         }
                     }
                 }
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(conv_bar(s));
+                if (lane == 0) mbar_arrive(lo_full(sl));
             }
         }
     } else {
@@ -596,14 +644,14 @@ extern "C" int mma_linear_tf32x3(const float *A0, int64_t lda0, int K0, const fl
     if (p.n_tiles_m < 1) return tile_tab ? MMA_OK : MMA_ERR_INVALID;
     p.C = C; p.ldc = ldc; p.out_map = out_map; p.bias = bias; p.add = add; p.ldadd = ldadd;
     p.add_in = (mode_flags & MMA_GEMM_ADD_BY_INPUT_ROW) ? 1 : 0;
-    MMA_CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    MMA_CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NT_SMEM_BYTES));
     int sms = 0, dev = 0;
     MMA_CUDA_CHECK(cudaGetDevice(&dev));
     MMA_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
     const int64_t n_tiles = p.n_tiles_m * p.n_tiles_n;
     const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
-    gemm_nt_kernel<<<grid, THREADS, SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    gemm_nt_kernel<<<grid, NT_THREADS, NT_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     MMA_LAUNCH_CHECK();
     return MMA_OK;
 }
@@ -629,14 +677,14 @@ extern "C" int mma_wgrad_tf32x3(const float *G0, int64_t ldg0, int N0, const flo
     p.tiles_k = (K + BN - 1) / BN;
     p.mode = mode;
     p.n_slabs = n_slabs; p.slab_tab = slab_tab; p.part = part;
-    MMA_CUDA_CHECK(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    MMA_CUDA_CHECK(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES));
     int sms = 0, dev = 0;
     MMA_CUDA_CHECK(cudaGetDevice(&dev));
     MMA_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
     const int64_t n_units = n_slabs * p.tiles_n * p.tiles_k;
     const unsigned grid = (unsigned)(n_units < sms ? n_units : sms);
-    gemm_wgrad_kernel<<<grid, THREADS, SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    gemm_wgrad_kernel<<<grid, THREADS, WG_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     MMA_LAUNCH_CHECK();
     return MMA_OK;
 }
