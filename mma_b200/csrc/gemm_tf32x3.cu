@@ -94,39 +94,70 @@ __device__ __forceinline__ void load_acc(uint32_t taddr, bool with_corr, uint32_
 }
 
 // One 32-row x 32-column accumulator chunk held row-per-thread (thread = row) -> global memory.
-// The chunk is transposed through a swizzled 4 KB staging buffer (16-byte chunk index XOR row%8:
-// conflict-free both ways) so that every store instruction writes 4 rows x 128 B of full lines.
+// A thread owns 32 consecutive columns of its row = one full 128-byte line, so it stores straight from
+// registers (8 x 16 B; consecutive instructions complete each 32-byte sector): no shared-memory
+// transpose, a quarter of the instructions of the staged version, which had made the epilogue warps
+// the slowest stage of the pipeline.  `stg` is unused (kept for the call sites).
 __device__ __forceinline__ void store_chunk(float *stg, const uint32_t (&r)[32], int lane, int64_t row0, int64_t row_end,
                                             int col0, int n_cols, float *C, int64_t ldc, const int32_t *out_map,
                                             const float *bias, const float *add, int64_t ldadd, int add_in) {
+    (void)stg;
+    const int64_t grow = row0 + lane;
+    if (grow >= row_end || col0 >= n_cols) return;
+    const int64_t orow = out_map ? (int64_t)__ldg(out_map + grow) : grow;
+    float *crow = C + orow * ldc + col0;
+    const float *arow = add ? add + (add_in ? grow : orow) * ldadd + col0 : nullptr;
+    const bool wide = ((reinterpret_cast<uintptr_t>(crow) | reinterpret_cast<uintptr_t>(arow)) & 31u) == 0 && col0 + 32 <= n_cols;
+    if (wide) {
+        // 256-bit accesses: every store instruction writes whole 32-byte sectors
+        float av[32];
+        if (arow) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                asm volatile("ld.global.cs.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                             : "=f"(av[8 * j]), "=f"(av[8 * j + 1]), "=f"(av[8 * j + 2]), "=f"(av[8 * j + 3]),
+                               "=f"(av[8 * j + 4]), "=f"(av[8 * j + 5]), "=f"(av[8 * j + 6]), "=f"(av[8 * j + 7])
+                             : "l"(arow + 8 * j));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * j + i]);
+            if (bias) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + col0) + 2 * j);
+                const float4 b1 = __ldg(reinterpret_cast<const float4 *>(bias + col0) + 2 * j + 1);
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            if (arow) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] += av[8 * j + i];
+            }
+            asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(crow + 8 * j), "f"(v[0]), "f"(v[1]),
+                         "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                         : "memory");
+        }
+        return;
+    }
+    float4 av[8];
+    if (arow) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (col0 + 4 * j < n_cols) av[j] = __ldcs(reinterpret_cast<const float4 *>(arow) + j);
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                     __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-        *reinterpret_cast<float4 *>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = v;
-    }
-    __syncwarp();
-    const int ch = lane & 7;
-    const int col = col0 + ch * 4;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int rr = i * 4 + (lane >> 3);
-        const int64_t grow = row0 + rr;
-        if (grow < row_end && col < n_cols) {
-            float4 v = *reinterpret_cast<const float4 *>(stg + rr * 32 + ((ch ^ (rr & 7)) << 2));
-            const int64_t orow = out_map ? (int64_t)__ldg(out_map + grow) : grow;
+        if (col0 + 4 * j < n_cols) {
+            float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
             if (bias) {
-                const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + col));
-                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                const float4 bb = __ldg(reinterpret_cast<const float4 *>(bias + col0) + j);
+                v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
             }
-            if (add) {
-                const float4 a = __ldcs(reinterpret_cast<const float4 *>(add + (add_in ? grow : orow) * ldadd + col));
-                v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-            }
-            __stcs(reinterpret_cast<float4 *>(C + orow * ldc + col), v);
+            if (arow) { v.x += av[j].x; v.y += av[j].y; v.z += av[j].z; v.w += av[j].w; }
+            __stcs(reinterpret_cast<float4 *>(crow) + j, v);
         }
     }
-    __syncwarp();
 }
 
 __global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_kernel(const __grid_constant__ NtParams p) {
