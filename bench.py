@@ -236,7 +236,7 @@ def main():
         rows = graph.rows
         graph.local.build_transpose()
     else:
-        graph = mma_b200.Graph(src, dst, N, sort_rows=True, relabel=not args.no_tc)   # degree-sorted, relabelled: fused tcgen05 layer
+        graph = mma_b200.Graph(src, dst, N, sort_rows=True)      # degree-sorted CSR rows: scalers folded into the post GEMM
         rows = N
         _ = graph.max_deg
     del src, dst

@@ -173,6 +173,14 @@ int mma_segment_sum_rows(const int32_t *ptr, const int32_t *idx, const float *va
                          int64_t n_rows, const float *src, int64_t lds, int F,
                          float *out, int64_t ldo, mma_stream_t stream);
 
+/* Row gather with fused column sums (the row permutation x[node_perm] of the degree-sorted layer
+ * interior and the bias gradient sum_r dOut[r] in one pass):
+ *   out[r, :] = src[idx[r], :]   r < n_out (idx NULL = identity), F % 4 == 0;
+ *   colsum_part [n_parts, F] (optional): part p holds the column sums of rows [p*per, (p+1)*per),
+ *   per = ceil(n_out / n_parts); reduce them in order with mma_reduce_slabs (no atomics). */
+int mma_gather_rows(const float *src, int64_t lds, const int32_t *idx, int64_t n_out, int F,
+                    float *out, int64_t ldo, float *colsum_part, int64_t n_parts, mma_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * K2: masked multi-aggregator layer of node_classification (layers.py:201-728),
  * all A aggregators in one pass over the CSR of neighbour lists (add_all):

@@ -37,6 +37,7 @@ _SIGS = {
                                   _vp, _i64, _f32, _u64, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _i64,
                                   _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp],
                                  C.c_int),
+    "mma_gather_rows": ([_vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp, _i64, _vp], C.c_int),
     "mma_segment_sum_rows": ([_vp, _vp, _vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp], C.c_int),
     "mma_nc_aggregate_fwd": ([_vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32,
                               _vp, _vp, _vp, _f32, _u64, _vp, _vp, _vp], C.c_int),

@@ -58,9 +58,62 @@ __global__ void __launch_bounds__(256) segment_sum_rows_kernel(const __grid_cons
     st_vec_stream<VEC>(p.out + row * p.ldo + c, acc);
 }
 
+
+// out[r] = src[idx[r]] for r < n_out, plus (optionally) the column sums of the gathered rows as
+// per-part partial sums: part p owns the contiguous rows [p * per, (p + 1) * per) and writes
+// colsum_part[p][c]; summing the parts in ascending p (mma_reduce_slabs) is a fixed-order reduction.
+// One warp per part; a lane owns 4-column groups lane, lane + 32, ... (F % 4 == 0).
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float *__restrict__ src, int64_t lds,
+                                                          const int32_t *__restrict__ idx, int64_t n_out, int F,
+                                                          float *__restrict__ out, int64_t ldo,
+                                                          float *__restrict__ colsum_part, int64_t n_parts) {
+    const int64_t part = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (part >= n_parts) return;
+    const int64_t per = (n_out + n_parts - 1) / n_parts;
+    const int64_t r0 = part * per, r1 = r0 + per < n_out ? r0 + per : n_out;
+    for (int c = lane * 4; c < F; c += 128) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int64_t r = r0;
+        for (; r + 4 <= r1; r += 4) {          // 4 independent gathers in flight
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t j = idx ? (int64_t)__ldg(idx + r + u) : r + u;
+                v[u] = __ldcs(reinterpret_cast<const float4 *>(src + j * lds + c));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                __stcs(reinterpret_cast<float4 *>(out + (r + u) * ldo + c), v[u]);
+                acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+            }
+        }
+        for (; r < r1; ++r) {
+            const int64_t j = idx ? (int64_t)__ldg(idx + r) : r;
+            const float4 v = __ldcs(reinterpret_cast<const float4 *>(src + j * lds + c));
+            __stcs(reinterpret_cast<float4 *>(out + r * ldo + c), v);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        if (colsum_part) *reinterpret_cast<float4 *>(colsum_part + part * F + c) = acc;
+    }
+}
+
 }  // namespace mma
 
 using namespace mma;
+
+extern "C" int mma_gather_rows(const float *src, int64_t lds, const int32_t *idx, int64_t n_out, int F,
+                               float *out, int64_t ldo, float *colsum_part, int64_t n_parts, mma_stream_t stream) {
+    if (!src || !out || n_out < 0 || F < 1 || n_parts < 1) return MMA_ERR_INVALID;
+    if ((F % 4) != 0 || (lds % 4) != 0 || (ldo % 4) != 0 || !aligned16(src) || !aligned16(out) || !aligned16(colsum_part))
+        return MMA_ERR_UNSUPPORTED;
+    if (n_parts * 32 > (int64_t)INT32_MAX * 256) return MMA_ERR_UNSUPPORTED;
+    const int64_t threads = n_parts * 32;
+    gather_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        src, lds, idx, n_out, F, out, ldo, colsum_part, n_parts);
+    MMA_LAUNCH_CHECK();
+    return MMA_OK;
+}
 
 extern "C" int mma_segment_sum_rows(const int32_t *ptr, const int32_t *idx, const float *val,
                                     int64_t n_rows, const float *src, int64_t lds, int F,

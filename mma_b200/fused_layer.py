@@ -1,9 +1,9 @@
 """The whole MultiMaskConv layer (towers == 1) as ONE autograd node over the C-ABI kernels.
 
-reference (graph_regression/mma_conv.py)                  here, all rows in degree-sorted node order
+reference (graph_regression/mma_conv.py)                  here (CSR rows degree-sorted, everything else in node order)
 --------------------------------------------------------  ------------------------------------------------
-x.view(-1,1,F).repeat(1,T,1)                (:128)        x_s = x[node_perm]                      (row gather)
-mask Linear over cat([x_i,x_j])   (:146-152, mask_aggr)   [P|Q|XW] = x_s [W_i;W_j;W_x]^T + [b;0;b_post]  (G1, tcgen05)
+x.view(-1,1,F).repeat(1,T,1)                (:128)        never materialised
+mask Linear over cat([x_i,x_j])   (:146-152, mask_aggr)   [P|Q|XW] = x [W_i;W_j;W_lin W_x]^T + [b;0;b']  (G1, tcgen05)
 dropout + A scatters + degree     (:157-179)              Z = K1(P, Q)      raw aggregates [N, A*F]
 S cumulative scalers, cat, post Linear (:181-196,132-133) out = Z W_c(deg)^T + XW   (G2: grouped tcgen05 GEMM,
                                                             one effective weight per equal-degree row range)
@@ -57,8 +57,10 @@ class PostPlan:
         self.cum_big = self.cum[:, big].contiguous() if big else None                 # [S, B]
         self.tile_tab, self.tile_tab_t, self.slabs = i32(tiles), i32(tiles_t), i32(slabs)
         self.seg_ptr = torch.tensor(seg_ptr, dtype=torch.int32, device=dev)
-        self.tail_idx = torch.cat(tail_rows).to(dev) if tail_rows else None
+        self.tail_idx = torch.cat(tail_rows).to(dev) if tail_rows else None           # CSR rows of the small buckets
         self.tail_bucket = torch.cat(tail_b).to(dev) if tail_b else None
+        self.tail_nodes = (graph.row_map.to(torch.int64).index_select(0, self.tail_idx)
+                           if tail_rows else None)                                      # their node ids
 
 
 def post_plan(graph: Graph, scalers, avg_deg, min_rows: int, Fo: int, K: int) -> PostPlan:
@@ -114,7 +116,12 @@ class _FusedMMAConv(torch.autograd.Function):
     (:136), so the two compose:  out = Z (W_lin W_eff(d))^T + x (W_lin W_x)^T + (W_lin b_post + b_lin).
     The composed x-part rides along in G1, H is never materialised, and `lin` costs no GEMM of its own
     in either direction; the gradients of W_lin / W_post are recovered from those of the composed
-    weights by small [F_out x K] matrix products."""
+    weights by small [F_out x K] matrix products.
+
+    Row orders: x, P, Q, XW, dP, dQ, dx and the layer output live in NODE order; only the CSR rows (hence
+    Z, dZ and the row tiles of the grouped GEMMs) are degree-sorted.  K1 reaches P / dP through
+    graph.row_map, G2's epilogue scatters its rows to node order, and the single row permutation left
+    is dOut[row_map] in the backward (one gather pass that also yields the bias gradient)."""
 
     @staticmethod
     def forward(ctx, x, Wm, bm, Wp, bp, Wl, bl, R, keep, graph: Graph, plan: PostPlan, cfg):
@@ -130,11 +137,10 @@ class _FusedMMAConv(torch.autograd.Function):
         bc = (Wl @ bp if bp is not None else zeros(Co)) + (bl if bl is not None else zeros(Co))
         W1 = torch.cat([Wm[:, :F], Wm[:, F:2 * F], Wcx], dim=0)                                     # [2F+Co, F]
         b1 = torch.cat([bm if bm is not None else zeros(F), zeros(F), bc])
-        x_s = x.index_select(0, graph.node_perm)
         W1hi, W1lo = tg.split_weight(W1)
-        PQX = tg.linear(x_s, W1hi, W1lo, 2 * F + Co, bias=b1, name="gemm_mask_proj")                # [n, 2F+Co]
+        PQX = tg.linear(x, W1hi, W1lo, 2 * F + Co, bias=b1, name="gemm_mask_proj")                  # [n, 2F+Co], node order
         P, Q, XW = PQX[:, :F], PQX[:, F:2 * F], PQX[:, 2 * F:]
-        Z, arg_min, arg_max, mean, var = _k1_fwd(graph, P, Q, R, keep, F, akinds, p_drop, seed)
+        Z, arg_min, arg_max, mean, var = _k1_fwd(graph, P, Q, R, keep, F, akinds, p_drop, seed)     # sorted rows
         out = torch.empty((n, Co), dtype=torch.float32, device=dev)
         Ws = Wy.view(Fo, S, K)
         Weff = Wc = None
@@ -142,22 +148,23 @@ class _FusedMMAConv(torch.autograd.Function):
             Weff = torch.einsum("sb,osk->bok", plan.cum_big, Ws).contiguous()                       # [B, Fo, K]
             Wc = torch.matmul(Wl, Weff).contiguous()                                                # [B, Co, K]
             hi, lo = tg.split_weight(Wc.view(-1, K))
-            tg.linear(Z, hi, lo, Co, tile_tab=plan.tile_tab, out=out, out_map=graph.node_perm32, add=XW,
-                      add_by_input_row=True, name="gemm_post_grouped")
+            tg.linear(Z, hi, lo, Co, tile_tab=plan.tile_tab, out=out, out_map=graph.row_map, add=XW,
+                      name="gemm_post_grouped")                                                     # rows -> node order
         if plan.tail_idx is not None:
             ti = plan.tail_idx
+            nodes = plan.tail_nodes
             Zt = Z.index_select(0, ti)
             ct = plan.cum[:, plan.tail_bucket].t()                                                  # [nt, S]
             Yt = (Zt.unsqueeze(1) * ct.unsqueeze(2)).reshape(Zt.shape[0], S * K)
-            out.index_copy_(0, graph.node_perm.index_select(0, ti), (Yt @ Wy.t()) @ Wl.t() + XW.index_select(0, ti))
+            out.index_copy_(0, nodes, (Yt @ Wy.t()) @ Wl.t() + XW.index_select(0, nodes))
         ctx.graph, ctx.plan, ctx.cfg = graph, plan, cfg
         ctx.has_R, ctx.has_b = R is not None, (bm is not None, bp is not None, bl is not None)
-        ctx.save_for_backward(x_s, PQX, Z, Wm, Wp, bp, Wl, Weff, Wc, R, keep, arg_min, arg_max, mean, var)
+        ctx.save_for_backward(x, PQX, Z, Wm, Wp, bp, Wl, Weff, Wc, R, keep, arg_min, arg_max, mean, var)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
-        x_s, PQX, Z, Wm, Wp, bp, Wl, Weff, Wc, R, keep, arg_min, arg_max, mean, var = ctx.saved_tensors
+        x, PQX, Z, Wm, Wp, bp, Wl, Weff, Wc, R, keep, arg_min, arg_max, mean, var = ctx.saved_tensors
         graph, plan = ctx.graph, ctx.plan
         F, akinds, p_drop, seed = ctx.cfg
         dev = d_out.device
@@ -167,8 +174,8 @@ class _FusedMMAConv(torch.autograd.Function):
         Fo, Co = Wp.shape[0], Wl.shape[0]
         P, Q = PQX[:, :F], PQX[:, F:2 * F]
         Wx, Wy = Wp[:, :F], Wp[:, F:].contiguous()
-        dO = d_out.index_select(0, graph.node_perm)                                                 # sorted rows
-        dbc = d_out.sum(0)                                                                          # [Co]
+        d_out = d_out.contiguous()
+        dO, dbc = tg.gather_rows_colsum(d_out, graph.row_map)                                       # sorted rows; [Co]
         # ---- grouped post transform (composed with lin)
         dZ = torch.empty((n, K), dtype=torch.float32, device=dev)
         dWl = torch.outer(dbc, bp) if bp is not None else torch.zeros_like(Wl)
@@ -194,23 +201,24 @@ class _FusedMMAConv(torch.autograd.Function):
             dWl = dWl + dOt.t() @ (Yt @ Wy.t())
             g = dHt.t() @ Yt
             dWy = g if dWy is None else dWy + g
-        # ---- K1 backward: dP, dQ (and dR)
+        del dO
+        # ---- K1 backward: dP, dQ in node order (and dR)
         dPQ = torch.empty((n, 2 * F), dtype=torch.float32, device=dev)
         need_R = ctx.has_R and ctx.needs_input_grad[7]
         dR = _k1_bwd(graph, P, Q, R, keep, F, akinds, p_drop, seed, dZ, arg_min, arg_max, mean, var, dPQ, need_R)
         del dZ
-        # ---- mask projection + composed x-part: dx (scattered back to node order), dW1
+        # ---- mask projection + composed x-part, all in node order: dx, dW1
         Wcx = Wl @ Wx
         W1 = torch.cat([Wm[:, :F], Wm[:, F:2 * F], Wcx], dim=0)
         w1hi, w1lo = tg.split_weight(W1.t())
         dx = torch.empty((n, F), dtype=torch.float32, device=dev)
         if (2 * F) % 128 == 0:
-            tg.linear(dPQ, w1hi, w1lo, F, A1=dO, out=dx, out_map=graph.node_perm32, name="gemm_mask_dgrad")
-            dW1 = tg.wgrad(dPQ, x_s, G1=dO, name="gemm_mask_wgrad")
+            tg.linear(dPQ, w1hi, w1lo, F, A1=d_out, out=dx, name="gemm_mask_dgrad")
+            dW1 = tg.wgrad(dPQ, x, G1=d_out, name="gemm_mask_wgrad")
         else:
-            dPQX = torch.cat([dPQ, dO], dim=1)
-            tg.linear(dPQX, w1hi, w1lo, F, out=dx, out_map=graph.node_perm32, name="gemm_mask_dgrad")
-            dW1 = tg.wgrad(dPQX, x_s, name="gemm_mask_wgrad")
+            dPQX = torch.cat([dPQ, d_out], dim=1)
+            tg.linear(dPQX, w1hi, w1lo, F, out=dx, name="gemm_mask_dgrad")
+            dW1 = tg.wgrad(dPQX, x, name="gemm_mask_wgrad")
         dWm = torch.zeros_like(Wm)
         dWm[:, :F] = dW1[:F]
         dWm[:, F:2 * F] = dW1[F:2 * F]
@@ -235,8 +243,8 @@ def fused_mmaconv(x: Tensor, graph: Graph, *, W_mask: Tensor, b_mask: Optional[T
     """x [N, F] (node order) -> MMAConv output [N, out] for towers == 1, pre_layers == post_layers == 1.
     W_mask [F, 2F or 3F] (the live mask Linear, Q2; only the first 2F columns are used here, the edge
     part arrives as R), W_post [Fo, (S*A+1)*F], W_lin [out, Fo]."""
-    if graph.node_perm is None or graph.buckets is None:
-        raise RuntimeError("fused_mmaconv needs a Graph built with sort_rows=True, relabel=True")
+    if graph.row_map is None or graph.buckets is None:
+        raise RuntimeError("fused_mmaconv needs a Graph built with sort_rows=True (degree-sorted CSR rows)")
     F = x.shape[1]
     for a in aggregators:                       # aggregate(), mma_conv.py:164-177: exact names only
         if a not in _lib.AGGR_KINDS:

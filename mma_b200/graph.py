@@ -62,13 +62,12 @@ class Graph:
     """
 
     def __init__(self, src: Tensor, dst: Tensor, n_dst: int, n_src: Optional[int] = None,
-                 need_transpose: bool = True, sort_rows: bool = False, relabel: bool = False):
+                 need_transpose: bool = True, sort_rows: bool = False):
         dev = _lib.require_cuda(src, dst)
         self.device = dev
         self.E = int(dst.numel())
         self.n_dst = int(n_dst)
         self.n_src = int(n_src if n_src is not None else n_dst)
-        self.node_perm = self.node_perm32 = self.node_rank = None
         self.rng_row, self.rng_row0 = None, 0      # id of CSR row r in K1's dropout stream: rng_row0 + rng_row[r]
         self.row_map = None                        # node id of each CSR row (None = identity)
         self.row_rank = None                       # CSR row of each node (inverse of row_map)
@@ -91,18 +90,6 @@ class Graph:
             self.rng_row = self.row_map                # stream keyed by the ORIGINAL node id: layout-invariant
             self.row_rank = rank
             dst = rank.index_select(0, dst)
-            if relabel:
-                # Relabel the SOURCES too: the whole layer interior then lives in degree-sorted node
-                # numbering (P, Q, Z, H rows all sorted) and the kernels need no row indirection; only
-                # the layer entry / exit permute rows (node_perm: sorted position -> node id).  Edge
-                # ids, hence arg indices and the Philox stream, are untouched.
-                if self.n_src != self.n_dst:
-                    raise RuntimeError("relabel=True needs one node set (n_src == n_dst)")
-                src = rank.index_select(0, src)
-                self.node_perm = order.contiguous()                  # int64, for index_select
-                self.node_perm32 = self.row_map                      # int32, for the GEMM scatter epilogue
-                self.node_rank = rank.contiguous()
-                self.row_map = None
         self.rowptr, self.col, self.perm = csr_build(dst, src, self.n_dst)
         self.gid, self.E_total = None, self.E      # set by the partitioner for a shard
         self._src, self._dst = src, dst
@@ -155,8 +142,8 @@ class Graph:
 
     @staticmethod
     def from_edge_index(edge_index: Tensor, num_nodes: int, need_transpose: bool = True,
-                        sort_rows: bool = False, relabel: bool = False) -> "Graph":
-        return Graph(edge_index[0], edge_index[1], num_nodes, num_nodes, need_transpose, sort_rows, relabel)
+                        sort_rows: bool = False) -> "Graph":
+        return Graph(edge_index[0], edge_index[1], num_nodes, num_nodes, need_transpose, sort_rows)
 
     @staticmethod
     def from_index(index: Tensor, dim_size: int) -> "Graph":
@@ -169,7 +156,6 @@ class Graph:
         g.rowptr, g.col, g.perm = csr_build(index, None, g.n_dst)
         g.gid, g.E_total = None, g.E
         g.row_map = g.row_rank = g.buckets = None
-        g.node_perm = g.node_perm32 = g.node_rank = None
         g.rng_row, g.rng_row0 = None, 0
         g._t_built = False
         g.colptr = g.row_t = g.perm_t = g.csr2csc = None
@@ -182,15 +168,15 @@ _CACHE: "OrderedDict[tuple, Graph]" = OrderedDict()
 _CACHE_SIZE = 16
 
 
-def cached_graph(edge_index: Tensor, num_nodes: int, sort_rows: bool = False, relabel: bool = False) -> Graph:
+def cached_graph(edge_index: Tensor, num_nodes: int, sort_rows: bool = False) -> Graph:
     """Graph for an `edge_index` tensor, cached on (storage pointer, shape, version, N).
     A tensor mutated in place bumps `_version` and is rebuilt; pass a `Graph`
     explicitly to the layers to bypass the cache altogether."""
     key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes),
-           str(edge_index.device), bool(sort_rows), bool(relabel))
+           str(edge_index.device), bool(sort_rows))
     g = _CACHE.get(key)
     if g is None:
-        g = Graph.from_edge_index(edge_index, num_nodes, sort_rows=sort_rows, relabel=relabel)
+        g = Graph.from_edge_index(edge_index, num_nodes, sort_rows=sort_rows)
         _CACHE[key] = g
         while len(_CACHE) > _CACHE_SIZE:
             _CACHE.popitem(last=False)

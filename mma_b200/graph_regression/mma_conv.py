@@ -152,12 +152,12 @@ class MMAConv(torch.nn.Module):
             if not aggregator.startswith(ok):
                 raise ValueError(f'Unknown aggregator "{aggregator}".')
 
-    def _graph(self, edge_index, n: int, sort_rows: bool = False, relabel: bool = False):
+    def _graph(self, edge_index, n: int, sort_rows: bool = False):
         if isinstance(edge_index, (Graph, ShardedGraph)):
             return edge_index
         if not edge_index.is_cuda:
             raise RuntimeError("mma_b200.MMAConv needs CUDA tensors (no CPU fallback)")
-        return cached_graph(edge_index, n, sort_rows=sort_rows, relabel=relabel)
+        return cached_graph(edge_index, n, sort_rows=sort_rows)
 
     # ------------------------------------------------------------------ forward
     def forward(self, x: Tensor, edge_index, edge_attr: Optional[Tensor] = None) -> Tensor:
@@ -170,9 +170,9 @@ class MMAConv(torch.nn.Module):
         if T == 1 and self.fold_scalers and self.pre_layers == 1 and self.mask != "no_linear":
             fused_ok = (self.use_tensor_cores and self.post_layers == 1 and
                         fused_layer.supported(F_in, self.F_out, self.out_channels))
-            graph = self._graph(edge_index, n, sort_rows=True, relabel=fused_ok)
-            if fused_ok and isinstance(graph, Graph) and graph.node_perm is not None:
-                return self._forward_fused(xt[:, 0], graph, edge_attr)
+            graph = self._graph(edge_index, n, sort_rows=True)
+            if fused_ok and isinstance(graph, Graph) and graph.row_map is not None:
+                return self._forward_fused(x.view(n, F_in), graph, edge_attr)
             local = graph.local if isinstance(graph, ShardedGraph) else graph
             if local.buckets is not None and not (isinstance(graph, ShardedGraph) and edge_attr is not None):
                 return self._forward_folded(xt[:, 0], graph, edge_attr)
@@ -231,8 +231,8 @@ class MMAConv(torch.nn.Module):
         return P, Q, R
 
     def _forward_fused(self, x: Tensor, graph: Graph, edge_attr: Optional[Tensor]) -> Tensor:
-        """towers == 1 on a relabelled (degree-sorted) graph: the whole layer is one autograd node --
-        three tcgen05 3xTF32 GEMMs around K1, rows permuted only at entry and exit (fused_layer.py)."""
+        """towers == 1 on a graph with degree-sorted CSR rows: the whole layer is one autograd node --
+        two tcgen05 3xTF32 GEMMs around K1 in the forward, four in the backward (fused_layer.py)."""
         F_in = self.F_in
         self._check_names()
         for s_ in self.scalers:

@@ -152,3 +152,22 @@ def wgrad(G0: Tensor, A: Tensor, *, G1: Optional[Tensor] = None, mode: Optional[
     slabs = cached_slabs(G0.shape[0], tiles, G0.device)
     part = wgrad_partials(G0, A, slabs, slabs.shape[0], G1=G1, mode=mode, name=name)
     return reduce_slabs(part)
+
+
+GATHER_PARTS = 148 * 32     # warps of the gather kernel = partial column sums
+
+
+def gather_rows_colsum(src: Tensor, idx32: Tensor) -> Tuple[Tensor, Tensor]:
+    """(src[idx], src[idx].sum(0)) in one pass: the row permutation into degree-sorted order fused
+    with the bias-gradient column sum (mma_gather_rows + fixed-order mma_reduce_slabs)."""
+    dev = _lib.require_cuda(src, idx32)
+    n, F = idx32.numel(), src.shape[1]
+    if not usable(src) or F % 4 != 0 or idx32.dtype != torch.int32:
+        raise RuntimeError("gather_rows_colsum: src must be fp32 row-major, 16-byte aligned, F % 4 == 0; idx int32")
+    out = torch.empty((n, F), dtype=torch.float32, device=dev)
+    parts = max(1, min(GATHER_PARTS, (n + 63) // 64))
+    part = torch.empty((parts, F), dtype=torch.float32, device=dev)
+    with _lib.kernel_scope("mma_gather_rows", dev):
+        _lib.check(_lib.lib().mma_gather_rows(_lib.ptr(src), src.stride(0), _lib.ptr(idx32), n, F, _lib.ptr(out), F,
+                                              _lib.ptr(part), parts, _lib.stream_ptr(dev)), "mma_gather_rows")
+    return out, reduce_slabs(part)
