@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-tc", action="store_true", help="cuBLAS fp32 GEMMs instead of the tcgen05 3xTF32 layer")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches in the timed region (host-bound for N > 1)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -186,7 +187,9 @@ def main():
                        f"{','.join(AGGR)} x scalers {','.join(SCAL)}, towers=1, dropout {args.dropout}",
            "nodes": N, "edges": E, "hidden": F, "aggregators": AGGR, "scalers": SCAL,
            "parallelism": f"dst-range x{world}" if world > 1 else "single GPU",
-           "l2": "inputs larger than L2 (x, P, Q, Y, G are 1-20 GB each vs 126 MB L2): no flush needed"}
+           "l2": "inputs larger than L2 (x, P, Q, Z, G are 1-16 GB each vs 126 MB L2): no flush needed",
+           "launch": "eager" if args.no_graph else "one CUDA graph per step (fwd+bwd+exchanges), seed advanced on device",
+           "kernel_timing": "CUDA events around every launch in an eager pass of the same steps after the timed region"}
 
     # ---------------- reference arm: the CPU path on a bounded sample (rank 0 only) ----------------
     if args.impl == "reference":
@@ -259,11 +262,40 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(warm):
-        step(x)
+    # ---------------- warm-up (eager, side stream), then capture ONE step in a CUDA graph ----------------
+    # The step is ~60 kernel launches driven from Python (~10 ms of host time): eager replay is host-bound as
+    # soon as the per-GPU work shrinks (N > 1).  The graph holds the whole fwd+bwd (+ the NCCL exchanges and the
+    # weight-gradient all-reduce for N > 1); the dropout seed lives on the device and is advanced inside the
+    # graph, so every replay draws a fresh mask exactly like an eager call.
+    use_graph = not args.no_graph
+    conv.device_seed = use_graph
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for _ in range(warm):
+            step(x)
+    torch.cuda.current_stream(dev).wait_stream(side)
     barrier()
     _lib.reset_counters()
-    _lib.enable_timing(True)
+    step(x)                                     # one counted eager step: kernels launched per step
+    launches_per_step = sum(_lib.LAUNCH_COUNTS.values())
+    barrier()
+    loss_static = None
+    if use_graph:
+        cg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(cg):
+            y_s, gx_s = step(x)
+            loss_static = (y_s * gy).sum() + gx_s[0, 0] * 0
+
+        def run():
+            cg.replay()
+    else:
+        def run():
+            step(x)
+    for _ in range(warm):
+        run()
+    barrier()
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -271,32 +303,60 @@ def main():
     barrier()
     e0.record()
     for _ in range(args.steps):
-        step(x)
+        run()
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1) / args.steps
-    ktimes = _lib.timing_summary()
-    launches = sum(_lib.LAUNCH_COUNTS.values())
-    _lib.enable_timing(False)
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
 
-    # ---------------- e2e: host buffers, H2D of x each step, D2H of the loss ----------------
+    # ---------------- per-kernel launch durations: the same steps once more, eager, with CUDA events around every
+    # launch of our kernels on the launching stream (events cannot bracket nodes inside a captured graph) --------
+    conv.device_seed = False
+    _lib.enable_timing(True)
+    for _ in range(args.steps):
+        step(x)
+    barrier()
+    ktimes = _lib.timing_summary()
+    _lib.enable_timing(False)
+    conv.device_seed = use_graph
+    launches = launches_per_step * args.steps
+
+    # ---------------- e2e: host buffers; every step uploads its x from pinned memory (on a copy stream, into a
+    # staging buffer, overlapping the previous step) and reads the loss back ----------------
     e2e = None
     if not args.no_e2e:
         xh = torch.randn(rows, F).pin_memory()
-        xd = torch.empty(rows, F, device=dev)
+        xs = torch.empty(rows, F, device=dev)
         lossh = torch.empty((), dtype=torch.float32).pin_memory()
+        copy_s = torch.cuda.Stream(device=dev)
+        main_s = torch.cuda.current_stream(dev)
+        ready, free = torch.cuda.Event(), torch.cuda.Event()
+
+        def upload():
+            with torch.cuda.stream(copy_s):
+                copy_s.wait_event(free)
+                xs.copy_(xh, non_blocking=True)
+                ready.record(copy_s)
 
         def e2e_step():
-            xd.copy_(xh, non_blocking=True)
-            xin = xd.detach().requires_grad_()
-            y, gx = step(xin)
-            lossh.copy_((y * gy).sum() + gx[0, 0] * 0, non_blocking=True)
+            main_s.wait_event(ready)
+            with torch.no_grad():
+                x.copy_(xs)                     # into the step's input buffer
+            free.record(main_s)
+            upload()                            # next step's input, under this step's compute
+            if use_graph:
+                cg.replay()
+                lossh.copy_(loss_static, non_blocking=True)
+            else:
+                y, gx = step(x)
+                lossh.copy_((y * gy).sum() + gx[0, 0] * 0, non_blocking=True)
 
+        free.record(main_s)
+        upload()
         for _ in range(2):
             e2e_step()
         barrier()
@@ -311,7 +371,9 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_e = float(t.item())
         e2e = {"value": E / (ms_e * 1e-3), "unit": "edges/s", "ms_per_step": ms_e,
-               "h2d_bytes_per_step": rows * F * 4 * world, "d2h_bytes_per_step": 4 * world}
+               "h2d_bytes_per_step": rows * F * 4 * world, "d2h_bytes_per_step": 4 * world,
+               "note": "x uploaded from pinned host memory every step on a copy stream (double-buffered under the "
+                       "previous step), loss read back every step"}
 
     if rank != 0:
         if world > 1:

@@ -107,6 +107,9 @@ int mma_invert_perm(const int32_t *perm, int64_t E, int32_t *inv, mma_stream_t s
  *                       position is layout-invariant); p is quantised to round(256 p)/256 (exact for
  *                       the reference's 0.5 / 0.75); p = 0.5 consumes one random bit per element,
  *                       any other p one byte (mma_dropout_keep_scale_rows materialises the stream)
+ *   seed_dev          : optional DEVICE pointer to the 64-bit seed; when set it overrides `seed` and is read
+ *                       by the kernel at run time, so a launch captured in a CUDA graph draws a fresh mask
+ *                       on every replay (advance the value between replays, e.g. inside the graph)
  *   aggr_kinds (host) [A], scaler_kinds (host) [S]
  *   scale_tab [4, tab_stride] : factor of scaler kind k (1..4) at clamped degree d is
  *                       scale_tab[(k-1)*tab_stride + d], d <= tab_stride-1 (built by the
@@ -132,7 +135,7 @@ int mmconv_aggregate_fwd(const int32_t *rowptr, const int32_t *col, const int32_
                          int64_t n_rows, int64_t E,
                          const float *P, int64_t ldp, const float *Q, int64_t ldq,
                          const float *R, int64_t ldr, const float *keep, int64_t ldk,
-                         float p_drop, uint64_t seed,
+                         float p_drop, uint64_t seed, const uint64_t *seed_dev,
                          int T, int F_in, int A, const int32_t *aggr_kinds,
                          int S, const int32_t *scaler_kinds,
                          const float *scale_tab, int64_t tab_stride,
@@ -152,7 +155,7 @@ int mmconv_aggregate_bwd_dst(const int32_t *rowptr, const int32_t *col, const in
                              int64_t n_rows, int64_t E,
                              const float *P, int64_t ldp, const float *Q, int64_t ldq,
                              const float *R, int64_t ldr, const float *keep, int64_t ldk,
-                             float p_drop, uint64_t seed,
+                             float p_drop, uint64_t seed, const uint64_t *seed_dev,
                              int T, int F_in, int A, const int32_t *aggr_kinds,
                              int S, const int32_t *scaler_kinds,
                              const float *scale_tab, int64_t tab_stride,

@@ -135,10 +135,21 @@ struct Dropout {
     uint32_t thr;     // drop iff random byte < thr   (thr = round(p * 256), 0..256)
     float scale;      // 1 / (1 - thr/256)
     uint32_t k0, k1;  // seed
+    const unsigned long long *seed_dev;   // if set, the seed is read from device memory at run time instead: a
+                                          // launch captured in a CUDA graph then draws a fresh mask on every replay
 };
 
-__host__ inline Dropout make_dropout(float p, uint64_t seed) {
+__device__ __forceinline__ uint2 dropout_key(const Dropout &d) {
+    if (d.seed_dev) {
+        const unsigned long long s = __ldg(d.seed_dev);
+        return make_uint2((uint32_t)(s & 0xFFFFFFFFull), (uint32_t)(s >> 32));
+    }
+    return make_uint2(d.k0, d.k1);
+}
+
+__host__ inline Dropout make_dropout(float p, uint64_t seed, const uint64_t *seed_dev = nullptr) {
     Dropout d;
+    d.seed_dev = reinterpret_cast<const unsigned long long *>(seed_dev);
     int t = (int)(p * 256.0f + 0.5f);
     d.thr = t < 0 ? 0u : (t > 256 ? 256u : (uint32_t)t);
     d.scale = d.thr < 256u ? 256.0f / (float)(256u - d.thr) : 0.0f;
@@ -159,7 +170,7 @@ __device__ __forceinline__ Vec<VEC> keep_from_word(const Dropout &d, uint32_t w,
 // keep-scale (0 or 1/(1-p)) for VEC consecutive columns starting at c (c % VEC == 0, VEC in {1,2,4}).
 template <int VEC>
 __device__ __forceinline__ Vec<VEC> dropout_keep(const Dropout &d, uint32_t eid, int c, uint32_t stream_id) {
-    const uint4 bits = philox4x32_10(make_uint4(eid, (uint32_t)(c >> 4), stream_id, 0u), make_uint2(d.k0, d.k1));
+    const uint4 bits = philox4x32_10(make_uint4(eid, (uint32_t)(c >> 4), stream_id, 0u), dropout_key(d));
     const int ws = (c >> 2) & 3;
     const uint32_t w = ws == 0 ? bits.x : (ws == 1 ? bits.y : (ws == 2 ? bits.z : bits.w));
     return keep_from_word<VEC>(d, w, c & 3);
@@ -180,10 +191,10 @@ __device__ __forceinline__ Vec<VEC> dropout_keep(const Dropout &d, uint32_t eid,
 __device__ __forceinline__ bool dropout_one_bit(const Dropout &d) { return d.thr == 128u; }
 
 __device__ __forceinline__ uint4 row_rng_bits1(const Dropout &d, uint32_t row_id, uint32_t pos, uint32_t c) {
-    return philox4x32_10(make_uint4(row_id, pos >> 5, c >> 2, 0u), make_uint2(d.k0, d.k1));
+    return philox4x32_10(make_uint4(row_id, pos >> 5, c >> 2, 0u), dropout_key(d));
 }
 __device__ __forceinline__ uint4 row_rng_bits8(const Dropout &d, uint32_t row_id, uint32_t pos, uint32_t c) {
-    return philox4x32_10(make_uint4(row_id, pos >> 2, c >> 2, 1u), make_uint2(d.k0, d.k1));
+    return philox4x32_10(make_uint4(row_id, pos >> 2, c >> 2, 1u), dropout_key(d));
 }
 
 // keep-scale of VEC consecutive columns starting at c for in-row edge `pos` of row `row_id`

@@ -796,6 +796,7 @@ static int fill_params(MMConvParams &p, const int32_t *rowptr, const int32_t *co
                        int64_t rng_row0, const int32_t *row_chunks, int64_t n_chunks, int64_t n_rows, int64_t E,
                        const float *P, int64_t ldp, const float *Q, int64_t ldq,
                        const float *R, int64_t ldr, const float *keep, int64_t ldk, float p_drop, uint64_t seed,
+                       const uint64_t *seed_dev,
                        int T, int F_in, int A, const int32_t *aggr_kinds, int S, const int32_t *scaler_kinds,
                        const float *scale_tab, int64_t tab_stride, int flags) {
     if (!rowptr || n_rows < 0 || E < 0 || T < 1 || F_in < 1 || A < 1 || S < 1 || !aggr_kinds || !scaler_kinds)
@@ -813,7 +814,7 @@ static int fill_params(MMConvParams &p, const int32_t *rowptr, const int32_t *co
     p.row_chunks = row_chunks; p.n_chunks = row_chunks ? n_chunks : 0;
     p.E_total = gid ? E_total : E;
     p.P = P; p.Q = Q; p.R = R; p.keep = keep; p.ldp = ldp; p.ldq = ldq; p.ldr = ldr; p.ldk = ldk;
-    p.drop = make_dropout(p_drop, seed);
+    p.drop = make_dropout(p_drop, seed, seed_dev);
     p.use_rng = (!keep && p.drop.thr > 0u) ? 1 : 0;
     p.args_local = (flags & MMA_K1_ARGS_LOCAL) ? 1 : 0;
     p.T = T; p.F_in = F_in; p.F = T * F_in; p.A = A; p.S = S;
@@ -946,6 +947,7 @@ extern "C" int mmconv_aggregate_fwd(const int32_t *rowptr, const int32_t *col, c
                                     int64_t n_rows, int64_t E, const float *P, int64_t ldp,
                                     const float *Q, int64_t ldq, const float *R, int64_t ldr,
                                     const float *keep, int64_t ldk, float p_drop, uint64_t seed,
+                                    const uint64_t *seed_dev,
                                     int T, int F_in, int A, const int32_t *aggr_kinds, int S,
                                     const int32_t *scaler_kinds, const float *scale_tab, int64_t tab_stride,
                                     float *Y, int64_t ldy, int32_t *arg_min, int32_t *arg_max,
@@ -954,7 +956,7 @@ extern "C" int mmconv_aggregate_fwd(const int32_t *rowptr, const int32_t *col, c
     MMConvParams p;
     int rc = fill_params(p, rowptr, col, perm, edge_gid, E_total, row_map, rng_row, rng_row0, row_chunks, n_chunks,
                          n_rows, E, P, ldp,
-                         Q, ldq, R, ldr, keep, ldk, p_drop, seed, T, F_in, A, aggr_kinds, S, scaler_kinds,
+                         Q, ldq, R, ldr, keep, ldk, p_drop, seed, seed_dev, T, F_in, A, aggr_kinds, S, scaler_kinds,
                          scale_tab, tab_stride, flags);
     if (rc != MMA_OK) return rc;
     if (!Y) return MMA_ERR_INVALID;
@@ -1022,6 +1024,7 @@ extern "C" int mmconv_aggregate_bwd_dst(const int32_t *rowptr, const int32_t *co
                                         int64_t n_rows, int64_t E, const float *P, int64_t ldp,
                                         const float *Q, int64_t ldq, const float *R, int64_t ldr,
                                         const float *keep, int64_t ldk, float p_drop, uint64_t seed,
+                                        const uint64_t *seed_dev,
                                         int T, int F_in, int A, const int32_t *aggr_kinds, int S,
                                         const int32_t *scaler_kinds, const float *scale_tab, int64_t tab_stride,
                                         const float *dY, int64_t ldy, const int32_t *arg_min,
@@ -1031,7 +1034,7 @@ extern "C" int mmconv_aggregate_bwd_dst(const int32_t *rowptr, const int32_t *co
     MMConvParams p;
     int rc = fill_params(p, rowptr, col, perm, edge_gid, E_total, row_map, rng_row, rng_row0, row_chunks, n_chunks,
                          n_rows, E, P, ldp,
-                         Q, ldq, R, ldr, keep, ldk, p_drop, seed, T, F_in, A, aggr_kinds, S, scaler_kinds,
+                         Q, ldq, R, ldr, keep, ldk, p_drop, seed, seed_dev, T, F_in, A, aggr_kinds, S, scaler_kinds,
                          scale_tab, tab_stride, flags);
     if (rc != MMA_OK) return rc;
     if (!dY || (!G && !dP && E > 0)) return MMA_ERR_INVALID;

@@ -49,10 +49,11 @@ def _ld(t: Optional[Tensor]) -> int:
 
 def k1_forward(graph: Graph, P, Q, R, keep, *, T: int, F_in: int, akinds, skinds, tab, p_drop: float, seed: int,
                Y: Tensor, arg_min, arg_max, mean, var, col0: int = 0, ncols: int = 0, local_args: bool = False,
-               q_ptr: Optional[int] = None, ldq: Optional[int] = None) -> None:
+               q_ptr: Optional[int] = None, ldq: Optional[int] = None, seed_dev: Optional[Tensor] = None) -> None:
     """One launch of mmconv_aggregate_fwd (include/mma_b200.h) on `graph`'s destination CSR.
     q_ptr / ldq override Q's base pointer and leading dimension (column-window pipeline of the
-    sharded path: a narrow gathered window addressed with global column indices)."""
+    sharded path: a narrow gathered window addressed with global column indices).  seed_dev: int64
+    device tensor holding the dropout seed (read at run time: CUDA-graph replays draw fresh masks)."""
     dev = graph.device
     ak, sk = _lib.i32_array(akinds), _lib.i32_array(skinds)
     chunks = graph.k1_chunks()
@@ -63,7 +64,7 @@ def k1_forward(graph: Graph, P, Q, R, keep, *, T: int, F_in: int, akinds, skinds
             0 if chunks is None else chunks.numel() - 1, graph.n_dst, graph.E,
             _lib.ptr(P), _ld(P), (_lib.ptr(Q) if q_ptr is None else q_ptr), (_ld(Q) if ldq is None else ldq),
             _lib.ptr(R), _ld(R), _lib.ptr(keep), _ld(keep),
-            float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, T, F_in, len(akinds), ak, len(skinds), sk,
+            float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.ptr(seed_dev), T, F_in, len(akinds), ak, len(skinds), sk,
             _lib.ptr(tab), 0 if tab is None else tab.shape[1],
             _lib.ptr(Y), Y.stride(0), _lib.ptr(arg_min), _lib.ptr(arg_max), _lib.ptr(mean), _lib.ptr(var),
             col0, ncols, _lib.K1_ARGS_LOCAL if local_args else 0, _lib.stream_ptr(dev)), "mmconv_aggregate_fwd")
@@ -72,7 +73,7 @@ def k1_forward(graph: Graph, P, Q, R, keep, *, T: int, F_in: int, akinds, skinds
 def k1_backward_dst(graph: Graph, P, Q, R, keep, *, T: int, F_in: int, akinds, skinds, tab, p_drop: float,
                     seed: int, dY: Tensor, arg_min, arg_max, mean, var, gslot, G, ldg: int, dP, lddp: int,
                     col0: int = 0, ncols: int = 0, local_args: bool = False, q_ptr: Optional[int] = None,
-                    ldq: Optional[int] = None) -> None:
+                    ldq: Optional[int] = None, seed_dev: Optional[Tensor] = None) -> None:
     """One launch of mmconv_aggregate_bwd_dst (destination pass of K1's backward)."""
     dev = graph.device
     ak, sk = _lib.i32_array(akinds), _lib.i32_array(skinds)
@@ -84,7 +85,7 @@ def k1_backward_dst(graph: Graph, P, Q, R, keep, *, T: int, F_in: int, akinds, s
             0 if chunks is None else chunks.numel() - 1, graph.n_dst, graph.E,
             _lib.ptr(P), _ld(P), (_lib.ptr(Q) if q_ptr is None else q_ptr), (_ld(Q) if ldq is None else ldq),
             _lib.ptr(R), _ld(R), _lib.ptr(keep), _ld(keep),
-            float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, T, F_in, len(akinds), ak, len(skinds), sk,
+            float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.ptr(seed_dev), T, F_in, len(akinds), ak, len(skinds), sk,
             _lib.ptr(tab), 0 if tab is None else tab.shape[1],
             _lib.ptr(dY), dY.stride(0), _lib.ptr(arg_min), _lib.ptr(arg_max), _lib.ptr(mean), _lib.ptr(var),
             _lib.ptr(gslot), _lib.ptr(G), ldg, _lib.ptr(dP), lddp, col0, ncols,

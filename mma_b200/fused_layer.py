@@ -73,7 +73,7 @@ def post_plan(graph: Graph, scalers, avg_deg, min_rows: int, Fo: int, K: int) ->
 
 
 def _k1_fwd(graph: Graph, P: Tensor, Q: Tensor, R: Optional[Tensor], keep: Optional[Tensor], F: int,
-            akinds: Tuple[int, ...], p_drop: float, seed: int):
+            akinds: Tuple[int, ...], p_drop: float, seed: int, seed_dev: Optional[Tensor] = None):
     dev = P.device
     n, A = graph.n_dst, len(akinds)
     Z = torch.empty((n, A * F), dtype=torch.float32, device=dev)
@@ -84,30 +84,30 @@ def _k1_fwd(graph: Graph, P: Tensor, Q: Tensor, R: Optional[Tensor], keep: Optio
     mean = torch.empty((n, F), dtype=torch.float32, device=dev) if need_sq else None
     var = torch.empty((n, F), dtype=torch.float32, device=dev) if need_sq else None
     MF.k1_forward(graph, P, Q, R, keep, T=1, F_in=F, akinds=akinds, skinds=(0,), tab=None, p_drop=p_drop, seed=seed,
-                  Y=Z, arg_min=arg_min, arg_max=arg_max, mean=mean, var=var, local_args=True)
+                  Y=Z, arg_min=arg_min, arg_max=arg_max, mean=mean, var=var, local_args=True, seed_dev=seed_dev)
     return Z, arg_min, arg_max, mean, var
 
 
 def _k1_bwd(graph: Graph, P, Q, R, keep, F, akinds, p_drop, seed, dZ, arg_min, arg_max, mean, var,
-            dPQ: Tensor, need_R: bool):
-    """dP -> dPQ[:, :F], dQ -> dPQ[:, F:2F]; returns dR (or None)."""
+            dP: Tensor, dQ: Tensor, need_R: bool, seed_dev: Optional[Tensor] = None):
+    """Destination pass (per-edge gradient rows G, dP) + transpose pass (dQ[j] = sum of G over j's out-edges).
+    dP [n_dst, F] and dQ [n_src, F] may be strided views.  Returns dR (or None)."""
     dev = dZ.device
-    n, E, A = graph.n_dst, graph.E, len(akinds)
+    E = graph.E
     if E == 0:
-        dPQ.zero_()
+        dP.zero_(); dQ.zero_()
         return torch.zeros_like(R) if need_R else None
     graph.build_transpose()
     G = torch.empty((E, F), dtype=torch.float32, device=dev)
     gslot = graph.perm if need_R else graph.csr2csc
-    l = _lib.lib()
-    dP, dQ = dPQ[:, :F], dPQ[:, F:2 * F]
     MF.k1_backward_dst(graph, P, Q, R, keep, T=1, F_in=F, akinds=akinds, skinds=(0,), tab=None, p_drop=p_drop,
                        seed=seed, dY=dZ, arg_min=arg_min, arg_max=arg_max, mean=mean, var=var, gslot=gslot, G=G,
-                       ldg=F, dP=dP, lddp=dPQ.stride(0), local_args=True)
+                       ldg=F, dP=dP, lddp=dP.stride(0), local_args=True, seed_dev=seed_dev)
     idx = graph.perm_t if need_R else None
     with _lib.kernel_scope("mma_segment_sum_rows", dev):
-        _lib.check(l.mma_segment_sum_rows(_lib.ptr(graph.colptr), _lib.ptr(idx), None, graph.n_src, _lib.ptr(G), F, F,
-                                          _lib.ptr(dQ), dPQ.stride(0), _lib.stream_ptr(dev)), "mma_segment_sum_rows")
+        _lib.check(_lib.lib().mma_segment_sum_rows(_lib.ptr(graph.colptr), _lib.ptr(idx), None, graph.n_src, _lib.ptr(G),
+                                                   F, F, _lib.ptr(dQ), dQ.stride(0), _lib.stream_ptr(dev)),
+                   "mma_segment_sum_rows")
     return G if need_R else None
 
 
@@ -124,9 +124,14 @@ class _FusedMMAConv(torch.autograd.Function):
     is dOut[row_map] in the backward (one gather pass that also yields the bias gradient)."""
 
     @staticmethod
-    def forward(ctx, x, Wm, bm, Wp, bp, Wl, bl, R, keep, graph: Graph, plan: PostPlan, cfg):
-        F, akinds, p_drop, seed = cfg
+    def forward(ctx, x, Wm, bm, Wp, bp, Wl, bl, R, keep, graph, plan: PostPlan, cfg):
+        F, akinds, p_drop, seed, seed_dev = cfg
+        if seed_dev is not None:
+            seed_dev = seed_dev.clone()      # this call's seed: the backward must see the same value
         dev = _lib.require_cuda(x, Wm, Wp, Wl)
+        sg = None if isinstance(graph, Graph) else graph          # ShardedGraph: x holds this rank's rows only
+        if sg is not None:
+            graph = sg.local
         n = graph.n_dst
         A, S = len(akinds), plan.S
         K = A * F
@@ -140,7 +145,12 @@ class _FusedMMAConv(torch.autograd.Function):
         W1hi, W1lo = tg.split_weight(W1)
         PQX = tg.linear(x, W1hi, W1lo, 2 * F + Co, bias=b1, name="gemm_mask_proj")                  # [n, 2F+Co], node order
         P, Q, XW = PQX[:, :F], PQX[:, F:2 * F], PQX[:, 2 * F:]
-        Z, arg_min, arg_max, mean, var = _k1_fwd(graph, P, Q, R, keep, F, akinds, p_drop, seed)     # sorted rows
+        if sg is not None:
+            # the one exchange of the forward: every rank's Q rows (the halo of a random graph is ~all of
+            # Q), rank-major padded layout that the shard's source indices already address
+            from .parallel import all_gather_rows
+            Q = all_gather_rows(Q.contiguous(), sg.max_rows, sg.group)
+        Z, arg_min, arg_max, mean, var = _k1_fwd(graph, P, Q, R, keep, F, akinds, p_drop, seed, seed_dev)   # sorted rows
         out = torch.empty((n, Co), dtype=torch.float32, device=dev)
         Ws = Wy.view(Fo, S, K)
         Weff = Wc = None
@@ -157,33 +167,70 @@ class _FusedMMAConv(torch.autograd.Function):
             ct = plan.cum[:, plan.tail_bucket].t()                                                  # [nt, S]
             Yt = (Zt.unsqueeze(1) * ct.unsqueeze(2)).reshape(Zt.shape[0], S * K)
             out.index_copy_(0, nodes, (Yt @ Wy.t()) @ Wl.t() + XW.index_select(0, nodes))
-        ctx.graph, ctx.plan, ctx.cfg = graph, plan, cfg
+        ctx.graph, ctx.sg, ctx.plan, ctx.cfg = graph, sg, plan, cfg
         ctx.has_R, ctx.has_b = R is not None, (bm is not None, bp is not None, bl is not None)
-        ctx.save_for_backward(x, PQX, Z, Wm, Wp, bp, Wl, Weff, Wc, R, keep, arg_min, arg_max, mean, var)
+        need_sq = 4 in akinds or 5 in akinds
+        Qsave = Q if (sg is not None and need_sq) else None       # gathered Q, kept so the backward does not re-gather
+        ctx.save_for_backward(x, PQX, Z, Wm, Wp, bp, Wl, Weff, Wc, R, keep, arg_min, arg_max, mean, var, Qsave,
+                              seed_dev)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
-        x, PQX, Z, Wm, Wp, bp, Wl, Weff, Wc, R, keep, arg_min, arg_max, mean, var = ctx.saved_tensors
-        graph, plan = ctx.graph, ctx.plan
-        F, akinds, p_drop, seed = ctx.cfg
+        (x, PQX, Z, Wm, Wp, bp, Wl, Weff, Wc, R, keep, arg_min, arg_max, mean, var, Qsave,
+         seed_dev) = ctx.saved_tensors
+        graph, sg, plan = ctx.graph, ctx.sg, ctx.plan
+        F, akinds, p_drop, seed, _ = ctx.cfg
         dev = d_out.device
         n = graph.n_dst
         A, S = len(akinds), plan.S
         K = A * F
         Fo, Co = Wp.shape[0], Wl.shape[0]
         P, Q = PQX[:, :F], PQX[:, F:2 * F]
+        if Qsave is not None:
+            Q = Qsave
         Wx, Wy = Wp[:, :F], Wp[:, F:].contiguous()
         d_out = d_out.contiguous()
         dO, dbc = tg.gather_rows_colsum(d_out, graph.row_map)                                       # sorted rows; [Co]
-        # ---- grouped post transform (composed with lin)
+        # ---- dgrad of the grouped post transform (composed with lin), then K1's backward
         dZ = torch.empty((n, K), dtype=torch.float32, device=dev)
-        dWl = torch.outer(dbc, bp) if bp is not None else torch.zeros_like(Wl)
-        dWy = None
+        WcT = None
         if plan.big:
             WcT = Wc.transpose(1, 2).contiguous()                                                   # [B, K, Co]
             hi, lo = tg.split_weight(WcT.view(-1, Co))
             tg.linear(dO, hi, lo, K, tile_tab=plan.tile_tab_t, out=dZ, name="gemm_post_dgrad")
+        if plan.tail_idx is not None:
+            ti = plan.tail_idx
+            ct = plan.cum[:, plan.tail_bucket].t()
+            dOt = dO.index_select(0, ti)
+            dHt = dOt @ Wl
+            dYt = (dHt @ Wy).view(-1, S, K)
+            dZ.index_copy_(0, ti, (dYt * ct.unsqueeze(2)).sum(dim=1))
+        dPQ = torch.empty((n, 2 * F), dtype=torch.float32, device=dev)
+        need_R = ctx.has_R and ctx.needs_input_grad[7]
+        pending = None
+        if sg is None:
+            dR = _k1_bwd(graph, P, Q, R, keep, F, akinds, p_drop, seed, dZ, arg_min, arg_max, mean, var,
+                         dPQ[:, :F], dPQ[:, F:2 * F], need_R, seed_dev)
+        else:
+            # partial dQ over ALL sources from this rank's edges, then the one exchange of the backward: a
+            # reduce-scatter that runs on the communication stream under the weight-gradient GEMM below
+            from .parallel import reduce_scatter_rows, _comm_stream
+            dQ_part = torch.empty((graph.n_src, F), dtype=torch.float32, device=dev)
+            dR = _k1_bwd(graph, P, Q, R, keep, F, akinds, p_drop, seed, dZ, arg_min, arg_max, mean, var,
+                         dPQ[:, :F], dQ_part, need_R, seed_dev)
+            comm, cur = _comm_stream(dev), torch.cuda.current_stream(dev)
+            comm.wait_stream(cur)
+            with torch.cuda.stream(comm):
+                dQ_loc = reduce_scatter_rows(dQ_part, sg.max_rows, n, sg.group)
+                done = torch.cuda.Event(); done.record(comm)
+            dQ_part.record_stream(comm)
+            pending = (dQ_loc, done)
+        del dZ
+        # ---- wgrad of the grouped post transform
+        dWl = torch.outer(dbc, bp) if bp is not None else torch.zeros_like(Wl)
+        dWy = None
+        if plan.big:
             part = tg.wgrad_partials(dO, Z, plan.slabs, plan.slabs.shape[0], name="gemm_post_wgrad")
             dWc = tg.reduce_slabs_segmented(part, plan.seg_ptr)                                     # [B, Co, K]
             dWl = dWl + torch.einsum("bck,bok->co", dWc, Weff)
@@ -192,21 +239,16 @@ class _FusedMMAConv(torch.autograd.Function):
         if plan.tail_idx is not None:
             ti = plan.tail_idx
             Zt = Z.index_select(0, ti)
-            ct = plan.cum[:, plan.tail_bucket].t()
-            dOt = dO.index_select(0, ti)
-            dHt = dOt @ Wl
-            dYt = (dHt @ Wy).view(-1, S, K)
-            dZ.index_copy_(0, ti, (dYt * ct.unsqueeze(2)).sum(dim=1))
             Yt = (Zt.unsqueeze(1) * ct.unsqueeze(2)).reshape(Zt.shape[0], S * K)
             dWl = dWl + dOt.t() @ (Yt @ Wy.t())
             g = dHt.t() @ Yt
             dWy = g if dWy is None else dWy + g
         del dO
-        # ---- K1 backward: dP, dQ in node order (and dR)
-        dPQ = torch.empty((n, 2 * F), dtype=torch.float32, device=dev)
-        need_R = ctx.has_R and ctx.needs_input_grad[7]
-        dR = _k1_bwd(graph, P, Q, R, keep, F, akinds, p_drop, seed, dZ, arg_min, arg_max, mean, var, dPQ, need_R)
-        del dZ
+        if pending is not None:
+            dQ_loc, done = pending
+            torch.cuda.current_stream(dev).wait_event(done)
+            dPQ[:, F:2 * F] = dQ_loc
+            dQ_loc.record_stream(torch.cuda.current_stream(dev))
         # ---- mask projection + composed x-part, all in node order: dx, dW1
         Wcx = Wl @ Wx
         W1 = torch.cat([Wm[:, :F], Wm[:, F:2 * F], Wcx], dim=0)
@@ -236,15 +278,19 @@ def supported(F_in: int, F_out: int, out_channels: int) -> bool:
     return F_in % 4 == 0 and F_out % 4 == 0 and out_channels % 4 == 0
 
 
-def fused_mmaconv(x: Tensor, graph: Graph, *, W_mask: Tensor, b_mask: Optional[Tensor], W_post: Tensor,
+def fused_mmaconv(x: Tensor, graph, *, W_mask: Tensor, b_mask: Optional[Tensor], W_post: Tensor,
                   b_post: Optional[Tensor], W_lin: Tensor, b_lin: Optional[Tensor], R: Optional[Tensor],
                   keep: Optional[Tensor], aggregators: Sequence[str], scalers: Sequence[str],
-                  avg_deg: Dict[str, float], p_drop: float, seed: int, min_rows: int) -> Tensor:
+                  avg_deg: Dict[str, float], p_drop: float, seed: int, min_rows: int,
+                  seed_dev: Optional[Tensor] = None) -> Tensor:
     """x [N, F] (node order) -> MMAConv output [N, out] for towers == 1, pre_layers == post_layers == 1.
     W_mask [F, 2F or 3F] (the live mask Linear, Q2; only the first 2F columns are used here, the edge
     part arrives as R), W_post [Fo, (S*A+1)*F], W_lin [out, Fo]."""
-    if graph.row_map is None or graph.buckets is None:
+    local = graph if isinstance(graph, Graph) else graph.local
+    if local.row_map is None or local.buckets is None:
         raise RuntimeError("fused_mmaconv needs a Graph built with sort_rows=True (degree-sorted CSR rows)")
+    if local is not graph and (R is not None or keep is not None):
+        raise RuntimeError("the sharded fused path supports neither edge features nor explicit keep masks")
     F = x.shape[1]
     for a in aggregators:                       # aggregate(), mma_conv.py:164-177: exact names only
         if a not in _lib.AGGR_KINDS:
@@ -252,6 +298,6 @@ def fused_mmaconv(x: Tensor, graph: Graph, *, W_mask: Tensor, b_mask: Optional[T
     if len(aggregators) > _lib.MAX_AGGR or len(scalers) > _lib.MAX_SCALER:
         raise _lib.MMAError("more than 8 aggregators or scalers in one call")
     akinds = tuple(_lib.AGGR_KINDS[a] for a in aggregators)
-    plan = post_plan(graph, scalers, avg_deg, min_rows, W_lin.shape[0], len(akinds) * F)
+    plan = post_plan(local, scalers, avg_deg, min_rows, W_lin.shape[0], len(akinds) * F)
     return _FusedMMAConv.apply(x, W_mask, b_mask, W_post, b_post, W_lin, b_lin, R, keep, graph, plan,
-                               (F, akinds, float(p_drop), int(seed)))
+                               (F, akinds, float(p_drop), int(seed), seed_dev))

@@ -111,6 +111,10 @@ class MMAConv(torch.nn.Module):
         self.fold_min_rows = 512             # degree ranges smaller than this use the literal formula
         self.comm_slices = 2                 # feature windows of the sharded comm/compute pipeline
         self.global_max_deg = None           # sharded runs: global max in-degree (else all-reduced per call)
+        self.device_seed = False             # True: the dropout seed lives in a device tensor that is advanced ON the
+                                             # device at every call, so a step captured in a CUDA graph draws a fresh
+                                             # mask on every replay (fused path only; `last_seed` is then not updated)
+        self._seed_dev: Optional[Tensor] = None
         self._uid = next(_UID)
         self._calls = 0
         self._inject_keep: Optional[Tensor] = None      # test hook: explicit keep-scale [E,T,F_in]
@@ -146,6 +150,14 @@ class MMAConv(torch.nn.Module):
         self.last_seed = s
         return s
 
+    def _next_seed_dev(self, dev) -> Tensor:
+        """Device-resident seed, advanced by a device-side add (capturable; create it before the capture)."""
+        if self._seed_dev is None or self._seed_dev.device != dev:
+            s = (torch.initial_seed() + 0x9E3779B97F4A7C15 * (self._uid * 1000003)) & 0x7FFFFFFFFFFFFFFF
+            self._seed_dev = torch.tensor([s], dtype=torch.int64, device=dev)
+        self._seed_dev.add_(0x9E3779B97F4A7C15 - (1 << 64))     # golden-ratio increment, wraps modulo 2^64
+        return self._seed_dev
+
     def _check_names(self):
         for aggregator in self.aggregators:     # message(), :150-154
             ok = ("sum", "mean", "min", "max") if self.strict_reference else ("sum", "mean", "min", "max", "var", "std")
@@ -173,6 +185,9 @@ class MMAConv(torch.nn.Module):
             graph = self._graph(edge_index, n, sort_rows=True)
             if fused_ok and isinstance(graph, Graph) and graph.row_map is not None:
                 return self._forward_fused(x.view(n, F_in), graph, edge_attr)
+            if (fused_ok and isinstance(graph, ShardedGraph) and edge_attr is None and self._inject_keep is None
+                    and graph.local is not None):
+                return self._forward_fused(x.view(n, F_in), graph, None)
             local = graph.local if isinstance(graph, ShardedGraph) else graph
             if local.buckets is not None and not (isinstance(graph, ShardedGraph) and edge_attr is not None):
                 return self._forward_folded(xt[:, 0], graph, edge_attr)
@@ -247,11 +262,12 @@ class MMAConv(torch.nn.Module):
         if keep is not None:
             keep = keep.reshape(graph.E, F_in)
         first = self.post_nns[0][0]
+        seed_dev = self._next_seed_dev(x.device) if (self.device_seed and keep is None) else None
         return fused_layer.fused_mmaconv(
             x.contiguous(), graph, W_mask=live.weight, b_mask=live.bias, W_post=first.weight, b_post=first.bias,
             W_lin=self.lin.weight, b_lin=self.lin.bias, R=R, keep=keep, aggregators=self.aggregators,
-            scalers=self.scalers, avg_deg=self.avg_deg, p_drop=self.dropout, seed=self._next_seed(),
-            min_rows=self.fold_min_rows)
+            scalers=self.scalers, avg_deg=self.avg_deg, p_drop=self.dropout,
+            seed=0 if seed_dev is not None else self._next_seed(), min_rows=self.fold_min_rows, seed_dev=seed_dev)
 
     def _forward_folded(self, x: Tensor, graph: Graph, edge_attr: Optional[Tensor]) -> Tensor:
         """towers == 1 fast path: K1 emits the RAW aggregates Z [N, A*F_in] in degree-sorted row

@@ -119,3 +119,54 @@ def test_sharded_aggregate_matches_single_gpu(p_drop):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     mp.spawn(_gpu_worker, args=(2, _free_port(), 4000, 60000, 128, p_drop), nprocs=2, join=True)
+
+
+def _gpu_layer_worker(rank, world, port, n, E, Fd):
+    """The whole drop-in layer on a destination-range shard (fused tcgen05 path) vs the single-GPU layer:
+    same seed -> same dropout stream (keyed by global node id), outputs and all gradients must agree."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import mma_b200
+        from mma_b200 import parallel as par
+        g = torch.Generator().manual_seed(3)
+        src = torch.randint(0, n, (E,), generator=g)
+        dst = torch.randint(0, n - 3, (E,), generator=g)
+        hist = torch.bincount(torch.bincount(dst, minlength=n))
+        aggr, scal = ["mean", "sum", "min", "max", "std"], ["identity", "amplification", "attenuation", "linear"]
+        torch.manual_seed(5)
+        conv = mma_b200.MMAConv(Fd, Fd, aggr, scal, hist, towers=1, strict_reference=False).to(dev)
+        conv.fold_min_rows = 64
+        x = torch.randn(n, Fd, generator=g)
+        gy = torch.randn(n, Fd, generator=g)
+        params = list(conv.parameters()) + conv.mask_parameters()
+        # single-GPU reference
+        full = mma_b200.Graph(src.to(dev), dst.to(dev), n, sort_rows=True)
+        xf = x.to(dev).requires_grad_()
+        torch.manual_seed(11); conv._calls = 0
+        yf = conv(xf, full)
+        gf = torch.autograd.grad(yf, [xf] + params, gy.to(dev))
+        for balance in ("nodes", "edges"):
+            sg = par.ShardedGraph(src.to(dev), dst.to(dev), n, rank, world, balance=balance)
+            xl = x[sg.lo:sg.hi].to(dev).requires_grad_()
+            torch.manual_seed(11); conv._calls = 0
+            yl = conv(xl, sg)
+            gl = torch.autograd.grad(yl, [xl] + params, gy[sg.lo:sg.hi].to(dev))
+            tol = lambda a: 2e-5 * a.abs().max().item() + 1e-30
+            assert (yl - yf[sg.lo:sg.hi]).abs().max().item() <= tol(yf), "sharded layer output"
+            assert (gl[0] - gf[0][sg.lo:sg.hi]).abs().max().item() <= tol(gf[0]), "sharded dx"
+            for a, b in zip(gl[1:], gf[1:]):                 # weight gradients: partial per rank -> all-reduce
+                a = a.clone()
+                dist.all_reduce(a)
+                assert (a - b).abs().max().item() <= tol(b), "sharded weight gradient"
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_sharded_fused_layer_matches_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    mp.spawn(_gpu_layer_worker, args=(2, _free_port(), 6000, 90000, 128), nprocs=2, join=True)
