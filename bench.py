@@ -281,6 +281,7 @@ def main():
     launches_per_step = sum(_lib.LAUNCH_COUNTS.values())
     barrier()
     loss_static = None
+    cg = None
     if use_graph:
         cg = torch.cuda.CUDAGraph()
         with torch.cuda.graph(cg):
@@ -375,9 +376,23 @@ def main():
                "note": "x uploaded from pinned host memory every step on a copy stream (double-buffered under the "
                        "previous step), loss read back every step"}
 
-    if rank != 0:
+    def finish():
+        """Tears the run down without dist.destroy_process_group(): destroying a communicator that a live CUDA
+        graph has captured collectives on was seen to hang; the graph is reset first and the process then
+        leaves through os._exit once everything is flushed."""
+        nonlocal cg
+        torch.cuda.synchronize()
+        if use_graph:
+            cg.reset()
+            cg = None
         if world > 1:
-            dist.destroy_process_group()
+            dist.barrier()
+            torch.cuda.synchronize()
+            sys.stdout.flush(); sys.stderr.flush()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return 0
 
     # ---------------- roofline of the dominant kernel ----------------
@@ -430,9 +445,8 @@ def main():
             "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "clocks": clocks,
             "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "detail": extra}
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
+    finish()
     return 0
 
 

@@ -30,6 +30,14 @@ from .functional import cumulative_scale_factors
 from .graph import Graph
 
 
+import os
+
+# Run the backward's reduce-scatter on a side stream under the weight-gradient GEMM.  Off by default: NCCL's
+# CTAs take SMs away from the persistent one-CTA-per-SM GEMM, whose displaced CTAs then run as a second wave
+# (measured: the GEMM took 2x as long, cancelling the overlap).
+OVERLAP_EXCHANGE = os.environ.get("MMA_OVERLAP_EXCHANGE", "0") == "1"
+
+
 class PostPlan:
     """Row ranges of equal in-degree (graph.buckets) -> tile / slab tables of the grouped GEMMs."""
 
@@ -219,13 +227,16 @@ class _FusedMMAConv(torch.autograd.Function):
             dQ_part = torch.empty((graph.n_src, F), dtype=torch.float32, device=dev)
             dR = _k1_bwd(graph, P, Q, R, keep, F, akinds, p_drop, seed, dZ, arg_min, arg_max, mean, var,
                          dPQ[:, :F], dQ_part, need_R, seed_dev)
-            comm, cur = _comm_stream(dev), torch.cuda.current_stream(dev)
-            comm.wait_stream(cur)
-            with torch.cuda.stream(comm):
-                dQ_loc = reduce_scatter_rows(dQ_part, sg.max_rows, n, sg.group)
-                done = torch.cuda.Event(); done.record(comm)
-            dQ_part.record_stream(comm)
-            pending = (dQ_loc, done)
+            if OVERLAP_EXCHANGE:
+                comm, cur = _comm_stream(dev), torch.cuda.current_stream(dev)
+                comm.wait_stream(cur)
+                with torch.cuda.stream(comm):
+                    dQ_loc = reduce_scatter_rows(dQ_part, sg.max_rows, n, sg.group)
+                    done = torch.cuda.Event(); done.record(comm)
+                dQ_part.record_stream(comm)
+                pending = (dQ_loc, done)
+            else:
+                dPQ[:, F:2 * F] = reduce_scatter_rows(dQ_part, sg.max_rows, n, sg.group)
         del dZ
         # ---- wgrad of the grouped post transform
         dWl = torch.outer(dbc, bp) if bp is not None else torch.zeros_like(Wl)
