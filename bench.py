@@ -39,6 +39,9 @@ CONFIGS = {
     "c4s": (125_000, 2_000_000, 128),      # the 1/16 sub-graph (CPU-baseline size), for quick checks
 }
 METRIC = "MultiMaskConv fwd+bwd edges/sec"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
+# workload at N = 1 (profiles/r1z_ncu_full_selected.csv)
+NCU_TRAFFIC_C4 = {"mmconv_aggregate_fwd": 25.85e9, "mmconv_aggregate_bwd_dst": 43.95e9, "mma_segment_sum_rows": 17.41e9}
 
 
 def peaks():
@@ -416,7 +419,10 @@ def main():
     if dom:
         d = per_kernel[dom]
         roofline = {"bound": "hbm", "kernel": dom, "achieved": d["GBps"], "peak": peak, "unit": "GB/s",
-                    "frac": d["GBps"] / peak, "traffic": None, "peak_kind": peak_kind,
+                    "frac": d["GBps"] / peak,
+                    "traffic": NCU_TRAFFIC_C4.get(dom) if (args.config == "c4" and world == 1) else None,
+                    "traffic_source": "profiles/r1z_ncu_full_selected.csv (ncu --set full, bytes per launch)",
+                    "peak_kind": peak_kind,
                     "launch_ms": d["ms_per_launch"], "share_of_step": d["ms_per_step"] / ms}
     agg_ms = sum(v["ms_per_step"] for k, v in per_kernel.items()
                  if k in ("mmconv_aggregate_fwd", "mmconv_aggregate_bwd_dst", "mma_segment_sum_rows"))
