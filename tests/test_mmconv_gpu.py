@@ -330,3 +330,113 @@ def test_folded_post_transform_vs_oracle(edge_dim, tc):
     conv.fold_scalers = False
     y2 = conv(xg, ei.cuda(), eag)
     close(y2, yr, what="unfolded y")
+
+
+@pytest.mark.parametrize("F,p", [(128, 0.5), (64, 0.5), (128, 0.25), (32, 0.0)])
+def test_stream_kernels_long_rows_and_hubs(F, p):
+    """Skewed degrees: a few hub rows (thousands of in-edges: many index chunks, ring wrap-arounds, dropout words
+    refreshed every 32 edges), runs of empty rows, rows of every small length -- forward (bit-exact min/max +
+    arg indices) and backward of the persistent stream kernels against the oracle fed the same dropout mask."""
+    import mma_b200
+    from oracle import restate
+    g = torch.Generator().manual_seed(F + int(p * 100))
+    n = 700
+    deg = torch.cat([torch.tensor([5000, 1537, 260, 129, 97, 65, 64, 63, 33, 32, 31]),
+                     torch.randint(0, 9, (n - 11 - 40,), generator=g), torch.zeros(40, dtype=torch.long)])
+    deg = deg[torch.randperm(n, generator=g)]
+    dst = torch.repeat_interleave(torch.arange(n), deg)
+    E = dst.numel()
+    shuffle = torch.randperm(E, generator=g)
+    dst = dst[shuffle]
+    src = torch.randint(0, n, (E,), generator=g)
+    P, Q = torch.randn(n, F, generator=g), torch.randn(n, F, generator=g)
+    P[torch.rand(n, F, generator=g) < 0.2] = 0.0; Q[torch.rand(n, F, generator=g) < 0.2] = 0.0     # exact ties
+    aggr = ["mean", "sum", "min", "max", "std"]
+    for sort_rows in (False, True):
+        graph = mma_b200.Graph(src.cuda(), dst.cuda(), n, sort_rows=sort_rows)
+        seed = 99
+        keep = mma_b200.dropout_keep_scale(p, seed, E, F, "cuda", graph=graph).cpu() if p > 0 else None
+        if keep is not None:
+            assert abs((keep > 0).float().mean().item() - (1 - p)) < 0.02
+        Pg, Qg = P.cuda().requires_grad_(), Q.cuda().requires_grad_()
+        Y, amin, amax = mma_b200.mmconv_aggregate(Pg, Qg, None, graph, towers=1, F_in=F, aggregators=aggr,
+                                                  scalers=["identity"], p_drop=p, seed=seed, return_args=True)
+        Pr, Qr = P.clone().requires_grad_(), Q.clone().requires_grad_()
+        ref, rargs = restate.mmconv_fused_op(Pr, Qr, None, keep, src, dst, n, aggr, ["identity"], {}, return_args=True)
+        # with sorted rows Y is in CSR-row order: bring it back to node order
+        Yn = Y.view(n, -1)
+        if sort_rows:
+            inv = graph.row_map.long()
+            Yn = torch.empty_like(Yn).index_copy_(0, inv, Yn)
+            amin = torch.empty_like(amin).index_copy_(0, inv, amin)
+            amax = torch.empty_like(amax).index_copy_(0, inv, amax)
+        Yv, Rv = Yn.detach().cpu().view(n, 5, F), ref.detach().view(n, 5, F)
+        bitexact(Yv[:, 2:4], Rv[:, 2:4], f"min/max F={F} p={p} sorted={sort_rows}")
+        close(Yv, Rv, what="sum/mean/std")
+        assert torch.equal(amin.cpu().long(), rargs["min"].view(n, F)), "argmin"
+        assert torch.equal(amax.cpu().long(), rargs["max"].view(n, F)), "argmax"
+        gy = torch.randn(n, 5 * F, generator=g)
+        gyg = gy.cuda()
+        if sort_rows:
+            gyg = gyg.index_select(0, graph.row_map.long())
+        a = torch.autograd.grad(Y, [Pg, Qg], gyg.view_as(Y))
+        b = torch.autograd.grad(ref, [Pr, Qr], gy)
+        close(a[0], b[0], what="dP"); close(a[1], b[1], what="dQ")
+
+
+def test_gather_rows_colsum():
+    from mma_b200 import tc_gemm as tg
+    g = torch.Generator().manual_seed(0)
+    for n, F in ((1000, 128), (77, 4), (5000, 200)):
+        src = torch.randn(n, F, generator=g).cuda()
+        idx = torch.randperm(n, generator=g).to(torch.int32).cuda()
+        out, cs = tg.gather_rows_colsum(src, idx)
+        assert torch.equal(out, src.index_select(0, idx.long()))
+        ref = src.double().sum(0)
+        assert (cs.double() - ref).abs().max().item() <= 1e-5 * ref.abs().max().item() + 1e-4
+        out2, cs2 = tg.gather_rows_colsum(src, idx)
+        assert torch.equal(cs, cs2), "fixed-order reduction must be bit-reproducible"
+
+
+def test_cuda_graph_replay_draws_fresh_dropout():
+    """The fused layer is capture-safe; with device_seed every replay advances the seed on the device: replay k
+    must equal the k-th eager call started from the same seed state (forward and gradients)."""
+    from mma_b200 import MMAConv, Graph
+    from oracle import restate
+    torch.manual_seed(0)
+    n, E, Fd = 3000, 40000, 64
+    src, dst = rand_graph(n, E, 21)
+    hist = torch.bincount(torch.bincount(dst, minlength=n))
+    conv = MMAConv(Fd, Fd, ["mean", "max", "std"], ["identity", "amplification"], hist, towers=1,
+                   strict_reference=False).cuda()
+    conv.fold_min_rows = 32
+    conv.device_seed = True
+    graph = Graph(src.cuda(), dst.cuda(), n, sort_rows=True)
+    x = torch.randn(n, Fd).cuda().requires_grad_()
+    gy = torch.randn(n, Fd).cuda()
+    params = list(conv.parameters()) + conv.mask_parameters()
+
+    def step():
+        y = conv(x, graph)
+        return (y,) + torch.autograd.grad(y, [x] + params, gy)
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    start = conv._seed_dev.clone()
+    eager = [[t.detach().clone() for t in step()] for _ in range(2)]     # detached: no autograd graph of an eager
+    torch.cuda.synchronize()                                              # step may outlive into the capture
+    assert not torch.equal(eager[0][0], eager[1][0]), "two calls must draw different masks"
+    conv._seed_dev.copy_(start)
+    cg = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(cg):
+        outs = step()
+    conv._seed_dev.copy_(start)          # the capture itself does not run the kernels
+    for k in range(2):
+        cg.replay()
+        torch.cuda.synchronize()
+        for a, b in zip(outs, eager[k]):
+            assert torch.equal(a, b), f"replay {k} differs from eager call {k}"
