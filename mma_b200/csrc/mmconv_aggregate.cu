@@ -900,21 +900,27 @@ static cudaError_t launch_stream(K kernel, const MMConvParams &p, int nst, int w
     kernel<<<sm_count(), warps * 32, smem, st>>>(p);
     return cudaSuccess;
 }
-template <int NST, int WARPS, int DROP>
+template <int NST, int WARPS, int VEC, int DROP>
 static cudaError_t launch_fwd_stream(const MMConvParams &p, bool minmax, bool sq, cudaStream_t st) {
-    if (minmax && sq) return launch_stream(stream::mmconv_fwd_stream<NST, WARPS, DROP, true, true>, p, NST, WARPS, st);
-    if (minmax) return launch_stream(stream::mmconv_fwd_stream<NST, WARPS, DROP, true, false>, p, NST, WARPS, st);
-    if (sq) return launch_stream(stream::mmconv_fwd_stream<NST, WARPS, DROP, false, true>, p, NST, WARPS, st);
-    return launch_stream(stream::mmconv_fwd_stream<NST, WARPS, DROP, false, false>, p, NST, WARPS, st);
+    if (minmax && sq) return launch_stream(stream::mmconv_fwd_stream<NST, WARPS, VEC, DROP, true, true>, p, NST, WARPS, st);
+    if (minmax) return launch_stream(stream::mmconv_fwd_stream<NST, WARPS, VEC, DROP, true, false>, p, NST, WARPS, st);
+    if (sq) return launch_stream(stream::mmconv_fwd_stream<NST, WARPS, VEC, DROP, false, true>, p, NST, WARPS, st);
+    return launch_stream(stream::mmconv_fwd_stream<NST, WARPS, VEC, DROP, false, false>, p, NST, WARPS, st);
 }
-template <int NST, int WARPS, int DROP>
+template <int NST, int WARPS, int VEC, int DROP>
 static cudaError_t launch_bwd_stream(const MMConvParams &p, bool needm, cudaStream_t st) {
     if (needm) {
-        if (p.args_local) return launch_stream(stream::mmconv_bwd_stream<NST, WARPS, DROP, true, true>, p, NST, WARPS, st);
-        return launch_stream(stream::mmconv_bwd_stream<NST, WARPS, DROP, true, false>, p, NST, WARPS, st);
+        if (p.args_local) return launch_stream(stream::mmconv_bwd_stream<NST, WARPS, VEC, DROP, true, true>, p, NST, WARPS, st);
+        return launch_stream(stream::mmconv_bwd_stream<NST, WARPS, VEC, DROP, true, false>, p, NST, WARPS, st);
     }
-    if (p.args_local) return launch_stream(stream::mmconv_bwd_stream<NST, WARPS, DROP, false, true>, p, NST, WARPS, st);
-    return launch_stream(stream::mmconv_bwd_stream<NST, WARPS, DROP, false, false>, p, NST, WARPS, st);
+    if (p.args_local) return launch_stream(stream::mmconv_bwd_stream<NST, WARPS, VEC, DROP, false, true>, p, NST, WARPS, st);
+    return launch_stream(stream::mmconv_bwd_stream<NST, WARPS, VEC, DROP, false, false>, p, NST, WARPS, st);
+}
+// columns per lane of the stream kernels: 4 (128-bit) for windows of up to 128 columns; windows of <= 64 / <= 32
+// columns use 2 / 1 so that all 32 lanes of the warp stay busy (per-byte dropout modes keep 4)
+static int stream_vec(const MMConvParams &p, int fd) {
+    if (fd == FD_BYTE) return 4;
+    return p.ncols > 64 ? 4 : (p.ncols > 32 ? 2 : 1);
 }
 // the stream kernels take: 128-bit columns, one warp per row window (<= 128 columns), message P + Q
 static bool stream_ok(const MMConvParams &p, int vec, const float *keep) {
@@ -983,11 +989,20 @@ extern "C" int mmconv_aggregate_fwd(const int32_t *rowptr, const int32_t *col, c
         const int fd = fast_drop_mode(p.drop);
         const StreamCfg sc = stream_cfg();
         cudaError_t e;
-        if (fd == FD_BIT && minmax && sq && sc.nst == 8) e = launch_fwd_stream<8, 12, FD_BIT>(p, minmax, sq, st);
-        else if (fd == FD_BIT && minmax && sq && sc.nst == 4) e = launch_fwd_stream<4, 16, FD_BIT>(p, minmax, sq, st);
-        else if (fd == FD_NONE) e = launch_fwd_stream<6, 16, FD_NONE>(p, minmax, sq, st);
-        else if (fd == FD_BIT) e = launch_fwd_stream<6, 16, FD_BIT>(p, minmax, sq, st);
-        else e = launch_fwd_stream<6, 16, FD_BYTE>(p, minmax, sq, st);
+        const int vw = stream_vec(p, fd);
+        if (vw == 4) {
+            if (fd == FD_BIT && minmax && sq && sc.nst == 8) e = launch_fwd_stream<8, 12, 4, FD_BIT>(p, minmax, sq, st);
+            else if (fd == FD_BIT && minmax && sq && sc.nst == 4) e = launch_fwd_stream<4, 16, 4, FD_BIT>(p, minmax, sq, st);
+            else if (fd == FD_NONE) e = launch_fwd_stream<6, 16, 4, FD_NONE>(p, minmax, sq, st);
+            else if (fd == FD_BIT) e = launch_fwd_stream<6, 16, 4, FD_BIT>(p, minmax, sq, st);
+            else e = launch_fwd_stream<6, 16, 4, FD_BYTE>(p, minmax, sq, st);
+        } else if (vw == 2) {
+            if (fd == FD_NONE) e = launch_fwd_stream<6, 16, 2, FD_NONE>(p, minmax, sq, st);
+            else e = launch_fwd_stream<6, 16, 2, FD_BIT>(p, minmax, sq, st);
+        } else {
+            if (fd == FD_NONE) e = launch_fwd_stream<6, 16, 1, FD_NONE>(p, minmax, sq, st);
+            else e = launch_fwd_stream<6, 16, 1, FD_BIT>(p, minmax, sq, st);
+        }
         MMA_CUDA_CHECK(e);
     } else if (vec == 4 && !keep && (msg == MSG_PQ || msg == MSG_PQR)) {
         // fast kernels: 128-bit columns, message and dropout mode fixed at compile time
@@ -1064,11 +1079,20 @@ extern "C" int mmconv_aggregate_bwd_dst(const int32_t *rowptr, const int32_t *co
         const int fd = fast_drop_mode(p.drop);
         const StreamCfg sc = stream_cfg();
         cudaError_t e;
-        if (fd == FD_BIT && needm && sc.nst == 8) e = launch_bwd_stream<8, 12, FD_BIT>(p, needm, st);
-        else if (fd == FD_BIT && needm && sc.nst == 4) e = launch_bwd_stream<4, 16, FD_BIT>(p, needm, st);
-        else if (fd == FD_NONE) e = launch_bwd_stream<6, 16, FD_NONE>(p, needm, st);
-        else if (fd == FD_BIT) e = launch_bwd_stream<6, 16, FD_BIT>(p, needm, st);
-        else e = launch_bwd_stream<6, 16, FD_BYTE>(p, needm, st);
+        const int vw = stream_vec(p, fd);
+        if (vw == 4) {
+            if (fd == FD_BIT && needm && sc.nst == 8) e = launch_bwd_stream<8, 12, 4, FD_BIT>(p, needm, st);
+            else if (fd == FD_BIT && needm && sc.nst == 4) e = launch_bwd_stream<4, 16, 4, FD_BIT>(p, needm, st);
+            else if (fd == FD_NONE) e = launch_bwd_stream<6, 16, 4, FD_NONE>(p, needm, st);
+            else if (fd == FD_BIT) e = launch_bwd_stream<6, 16, 4, FD_BIT>(p, needm, st);
+            else e = launch_bwd_stream<6, 16, 4, FD_BYTE>(p, needm, st);
+        } else if (vw == 2) {
+            if (fd == FD_NONE) e = launch_bwd_stream<6, 16, 2, FD_NONE>(p, needm, st);
+            else e = launch_bwd_stream<6, 16, 2, FD_BIT>(p, needm, st);
+        } else {
+            if (fd == FD_NONE) e = launch_bwd_stream<6, 16, 1, FD_NONE>(p, needm, st);
+            else e = launch_bwd_stream<6, 16, 1, FD_BIT>(p, needm, st);
+        }
         MMA_CUDA_CHECK(e);
     } else if (vec == 4 && !keep && (!needm || msg == MSG_PQ || msg == MSG_PQR)) {
         const int fd = fast_drop_mode(p.drop);

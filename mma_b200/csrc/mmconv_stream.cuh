@@ -9,8 +9,9 @@
 //     are dealt round-robin to persistent warps; a chunk's in-edges are one contiguous stream of CSR
 //     slots, so col[] is read with coalesced, prefetched loads and the row boundaries come from rowptr
 //     one row ahead -- no data-dependent index chain;
-//   * the gathered rows Q[src] are copied global -> shared with cp.async (LDGSTS, 16 B per lane: a lane
-//     copies exactly the 4 columns it later consumes, so completion needs no cross-lane barrier) into a
+//   * the gathered rows Q[src] are copied global -> shared with cp.async (LDGSTS, 16 B per lane -- 8 / 4 B for
+//     column windows of <= 64 / 32 columns, where a lane owns 2 / 1 columns: a lane copies exactly the
+//     columns it later consumes, so completion needs no cross-lane barrier) into a
 //     per-warp ring of NST stages x 4 edges that runs NST-1 stages AHEAD of consumption and does not
 //     stop at row boundaries;
 //   * a stage that lies inside one row is consumed by a 4-edge unrolled, branch-free body (12
@@ -26,17 +27,32 @@ constexpr int kRowCost = 6;        // a row costs about this many edges (used wh
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool pred) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}"
-                 :: "r"(dst), "l"(src), "r"((int)pred) : "memory");
+// BYTES = 16: L2-only (.cg); 8 / 4 (narrow column windows: 2 / 1 columns per lane): .ca is the only form
+template <int BYTES>
+__device__ __forceinline__ void cp_async_pred(uint32_t dst, const void *src, bool pred) {
+    if constexpr (BYTES == 16)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}"
+                     :: "r"(dst), "l"(src), "r"((int)pred) : "memory");
+    else if constexpr (BYTES == 8)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.ca.shared.global [%0], [%1], 8;\n\t}"
+                     :: "r"(dst), "l"(src), "r"((int)pred) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.ca.shared.global [%0], [%1], 4;\n\t}"
+                     :: "r"(dst), "l"(src), "r"((int)pred) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
-__device__ __forceinline__ Vec<4> lds4(uint32_t addr) {
-    Vec<4> r;
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "r"(addr));
+template <int VEC>
+__device__ __forceinline__ Vec<VEC> lds_vec(uint32_t addr) {
+    Vec<VEC> r;
+    if constexpr (VEC == 4)
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "r"(addr));
+    else if constexpr (VEC == 2)
+        asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(r.v[0]), "=f"(r.v[1]) : "r"(addr));
+    else
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r.v[0]) : "r"(addr));
     return r;
 }
 
@@ -62,7 +78,7 @@ __device__ __forceinline__ void chunk_rows(const MMConvParams &p, int64_t i, int
 }
 
 // Issue side of the pipeline: index chunks + the cp.async ring of one warp.
-template <int NST, bool NQ>
+template <int NST, bool NQ, int VEC>
 struct Ring {
     uint32_t base;             // shared-memory address of this lane's 16 bytes in ring slot 0
     int rowb;                  // bytes of one gathered row window
@@ -89,7 +105,7 @@ struct Ring {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int j = __shfl_sync(0xffffffffu, idx_cur, (p_issue & 31) + u);
-                    cp_async16(dst + (uint32_t)(u * rowb), Qc + (uint64_t)(uint32_t)j * ldq_b, live && (p_issue + u < len));
+                    cp_async_pred<VEC * 4>(dst + (uint32_t)(u * rowb), Qc + (uint64_t)(uint32_t)j * ldq_b, live && (p_issue + u < len));
                 }
             }
         }
@@ -134,8 +150,8 @@ struct EdgeAttr {
 //   fast_ok()             whether the 4-edge body may be used now (dropout word boundaries),
 //   stage_begin(s)        at the first edge of every stage.
 // row_end is read through a reference: row_next() updates it.
-template <int NST, bool NQ, typename RowNext, typename Edge4, typename Edge1, typename FastOk, typename StageBegin>
-__device__ __forceinline__ void run_stream(Ring<NST, NQ> &ring, int s0, int len, const int &row_end, RowNext &&row_next,
+template <int NST, bool NQ, int VEC, typename RowNext, typename Edge4, typename Edge1, typename FastOk, typename StageBegin>
+__device__ __forceinline__ void run_stream(Ring<NST, NQ, VEC> &ring, int s0, int len, const int &row_end, RowNext &&row_next,
                                            Edge4 &&edge4, Edge1 &&edge1, FastOk &&fast_ok, StageBegin &&stage_begin) {
     int cons_i = 0;
 #pragma unroll 1
@@ -149,16 +165,16 @@ __device__ __forceinline__ void run_stream(Ring<NST, NQ> &ring, int s0, int len,
             const int at = s0 + s + u;
             if (at == row_end) { row_next(); continue; }
             if (u == 0 && n == 4 && row_end - at >= 4 && fast_ok()) {
-                Vec<4> q[4];
+                Vec<VEC> q[4];
                 if constexpr (NQ) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) q[i] = lds4(sb + (uint32_t)(i * ring.rowb));
+                    for (int i = 0; i < 4; ++i) q[i] = lds_vec<VEC>(sb + (uint32_t)(i * ring.rowb));
                 }
                 edge4(at, q, s);
                 u = 4;
             } else {
-                Vec<4> q{};
-                if constexpr (NQ) q = lds4(sb + (uint32_t)(u * ring.rowb));
+                Vec<VEC> q{};
+                if constexpr (NQ) q = lds_vec<VEC>(sb + (uint32_t)(u * ring.rowb));
                 edge1(at, q, s + u);
                 ++u;
             }
@@ -169,19 +185,25 @@ __device__ __forceinline__ void run_stream(Ring<NST, NQ> &ring, int s0, int len,
     ring.end();
 }
 
+// the words of a Philox call (4 columns of one column group) that belong to this lane's VEC columns
+template <int VEC>
+__device__ __forceinline__ void pick_words(const uint4 &t, int c, uint32_t (&bits)[VEC]) {
+    if constexpr (VEC == 4) {
+        bits[0] = t.x; bits[1] = t.y; bits[2] = t.z; bits[3] = t.w;
+    } else if constexpr (VEC == 2) {
+        bits[0] = (c & 2) ? t.z : t.x; bits[1] = (c & 2) ? t.w : t.y;
+    } else {
+        const int k = c & 3;
+        bits[0] = k == 0 ? t.x : (k == 1 ? t.y : (k == 2 ? t.z : t.w));
+    }
+}
 // dropout words for in-row position pos: refreshes `bits` at the word boundaries of the row's stream
-template <int DROP>
-__device__ __forceinline__ void rng_refresh(const MMConvParams &p, uint32_t rid, int pos, int c, uint32_t (&bits)[4]) {
+template <int DROP, int VEC>
+__device__ __forceinline__ void rng_refresh(const MMConvParams &p, uint32_t rid, int pos, int c, uint32_t (&bits)[VEC]) {
     if constexpr (DROP == FD_BIT) {
-        if ((pos & 31) == 0) {
-            const uint4 t = row_rng_bits1(p.drop, rid, (uint32_t)pos, (uint32_t)c);
-            bits[0] = t.x; bits[1] = t.y; bits[2] = t.z; bits[3] = t.w;
-        }
+        if ((pos & 31) == 0) pick_words<VEC>(row_rng_bits1(p.drop, rid, (uint32_t)pos, (uint32_t)c), c, bits);
     } else if constexpr (DROP == FD_BYTE) {
-        if ((pos & 3) == 0) {
-            const uint4 t = row_rng_bits8(p.drop, rid, (uint32_t)pos, (uint32_t)c);
-            bits[0] = t.x; bits[1] = t.y; bits[2] = t.z; bits[3] = t.w;
-        }
+        if ((pos & 3) == 0) pick_words<VEC>(row_rng_bits8(p.drop, rid, (uint32_t)pos, (uint32_t)c), c, bits);
     }
 }
 // non-zero iff column v of the edge at in-row position pos is kept
@@ -217,23 +239,23 @@ struct DivByDeg {
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-template <int NST, int WARPS, int DROP, bool MINMAX, bool SQ>
+template <int NST, int WARPS, int VEC, int DROP, bool MINMAX, bool SQ>
 __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_fwd_stream(const __grid_constant__ MMConvParams p) {
     extern __shared__ __align__(16) uint8_t smem_ring[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t gw = (int64_t)blockIdx.x * WARPS + warp, tw = (int64_t)gridDim.x * WARPS;
     const int64_t n_chunks = p.row_chunks ? p.n_chunks : tw;
-    const bool live = lane * 4 < p.ncols;
-    const int c = p.col0 + lane * 4;
+    const bool live = lane * VEC < p.ncols;
+    const int c = p.col0 + lane * VEC;
     const float scale = p.drop.scale;
     const uint32_t thr = p.drop.thr;
     // outputs of the common case (S == 1, every aggregator kind at most once): column offset of each kind in a
     // row of Y, or -1 (fill_params); anything else goes through the generic loop
     const bool simple_out = p.simple_out != 0;
 
-    Ring<NST, true> ring;
+    Ring<NST, true, VEC> ring;
     ring.rowb = p.ncols * 4;
-    ring.base = smem_addr(smem_ring) + (uint32_t)warp * (uint32_t)(NST * 4 * ring.rowb) + (live ? (uint32_t)lane * 16u : 0u);   // idle lanes stay inside the ring
+    ring.base = smem_addr(smem_ring) + (uint32_t)warp * (uint32_t)(NST * 4 * ring.rowb) + (live ? (uint32_t)(lane * VEC * 4) : 0u);   // idle lanes stay inside the ring
     ring.Qc = reinterpret_cast<const char *>(p.Q + c);
     ring.ldq_b = (uint32_t)p.ldq * 4u;
     ring.lane = lane; ring.live = live;
@@ -250,11 +272,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_fwd_stream(const __grid_
         int row = r0;
         int row_beg = s0, row_end = __ldg(p.rowptr + r0 + 1);
         int next_end = r0 + 2 <= p.n_rows ? __ldg(p.rowptr + r0 + 2) : 0x7fffffff;
-        Vec<4> pv{}, pv_next{};
+        Vec<VEC> pv{}, pv_next{};
         uint32_t rid = 0, rid_next = 0;
-        float sum[4], sq[4], mn[4], mx[4];
-        int amn[4], amx[4];
-        uint32_t bits[4] = {0u, 0u, 0u, 0u};
+        float sum[VEC], sq[VEC], mn[VEC], mx[VEC];
+        int amn[VEC], amx[VEC];
+        uint32_t bits[VEC] = {};
         int pos = 0;                                        // in-row position of the next edge
         // running output pointers (this lane's columns of row `row`)
         float *yp = p.Y + (int64_t)r0 * p.ldy + (p.T == 1 ? c : (c / p.F_in) * (p.S * p.A * p.F_in) + c % p.F_in);
@@ -264,21 +286,21 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_fwd_stream(const __grid_
         float *mean_p = p.stat_mean ? p.stat_mean + rowF : nullptr;
         float *var_p = p.stat_var ? p.stat_var + rowF : nullptr;
 
-        auto fetch_row_inputs = [&](int r, Vec<4> &pvv, uint32_t &rd) {      // P row (pre-scaled) and rng id of row r
-            pvv = Vec<4>{}; rd = 0;
+        auto fetch_row_inputs = [&](int r, Vec<VEC> &pvv, uint32_t &rd) {      // P row (pre-scaled) and rng id of row r
+            pvv = Vec<VEC>{}; rd = 0;
             if (r < r1) {
                 const int64_t prow = p.row_map ? (int64_t)__ldg(p.row_map + r) : (int64_t)r;
-                if (live) pvv = ld_vec_stream<4>(p.P + prow * p.ldp + c);
+                if (live) pvv = ld_vec_stream<VEC>(p.P + prow * p.ldp + c);
                 if (p.use_rng) rd = (uint32_t)(p.rng_row0 + (p.rng_row ? (int64_t)__ldg(p.rng_row + r) : (int64_t)r));
             }
             if constexpr (DROP == FD_BIT) {
 #pragma unroll
-                for (int v = 0; v < 4; ++v) pvv.v[v] *= 2.0f;
+                for (int v = 0; v < VEC; ++v) pvv.v[v] *= 2.0f;
             }
         };
         auto reset_acc = [&]() {
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
+            for (int v = 0; v < VEC; ++v) {
                 sum[v] = 0.0f; sq[v] = 0.0f; mn[v] = FLT_MAX; mx[v] = -FLT_MAX; amn[v] = -1; amx[v] = -1;
             }
             pos = 0;
@@ -288,9 +310,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_fwd_stream(const __grid_
             const int deg = row_end - row_beg;
             const int degc = deg > 1 ? deg : 1;                     // deg.clamp_(1), mma_conv.py:179
             const DivByDeg div((float)degc);
-            Vec<4> mean, var, sd, vmin, vmax, vsum;
+            Vec<VEC> mean, var, sd, vmin, vmax, vsum;
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
+            for (int v = 0; v < VEC; ++v) {
                 vsum.v[v] = sum[v];
                 mean.v[v] = div(sum[v]);                            // sum / count.clamp(min=1)
                 if constexpr (SQ) {
@@ -304,43 +326,43 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_fwd_stream(const __grid_
                 vmax.v[v] = (MINMAX && amx[v] >= 0) ? mx[v] : 0.0f;
             }
             if (simple_out) {
-                if (p.zoff[MMA_AGGR_SUM] >= 0) st_vec_stream<4>(yp + p.zoff[MMA_AGGR_SUM], vsum);
-                if (p.zoff[MMA_AGGR_MEAN] >= 0) st_vec_stream<4>(yp + p.zoff[MMA_AGGR_MEAN], mean);
+                if (p.zoff[MMA_AGGR_SUM] >= 0) st_vec_stream<VEC>(yp + p.zoff[MMA_AGGR_SUM], vsum);
+                if (p.zoff[MMA_AGGR_MEAN] >= 0) st_vec_stream<VEC>(yp + p.zoff[MMA_AGGR_MEAN], mean);
                 if constexpr (MINMAX) {
-                    if (p.zoff[MMA_AGGR_MIN] >= 0) st_vec_stream<4>(yp + p.zoff[MMA_AGGR_MIN], vmin);
-                    if (p.zoff[MMA_AGGR_MAX] >= 0) st_vec_stream<4>(yp + p.zoff[MMA_AGGR_MAX], vmax);
+                    if (p.zoff[MMA_AGGR_MIN] >= 0) st_vec_stream<VEC>(yp + p.zoff[MMA_AGGR_MIN], vmin);
+                    if (p.zoff[MMA_AGGR_MAX] >= 0) st_vec_stream<VEC>(yp + p.zoff[MMA_AGGR_MAX], vmax);
                 }
                 if constexpr (SQ) {
-                    if (p.zoff[MMA_AGGR_VAR] >= 0) st_vec_stream<4>(yp + p.zoff[MMA_AGGR_VAR], var);
-                    if (p.zoff[MMA_AGGR_STD] >= 0) st_vec_stream<4>(yp + p.zoff[MMA_AGGR_STD], sd);
+                    if (p.zoff[MMA_AGGR_VAR] >= 0) st_vec_stream<VEC>(yp + p.zoff[MMA_AGGR_VAR], var);
+                    if (p.zoff[MMA_AGGR_STD] >= 0) st_vec_stream<VEC>(yp + p.zoff[MMA_AGGR_STD], sd);
                 }
             } else {
                 float fac[MMA_MAX_SCALER];
                 scaler_factors(p, degc, fac);
                 for (int a = 0; a < p.A; ++a) {
                     const int kind = p.akind[a];
-                    Vec<4> val = kind == MMA_AGGR_SUM ? vsum : kind == MMA_AGGR_MEAN ? mean : kind == MMA_AGGR_MIN ? vmin
+                    Vec<VEC> val = kind == MMA_AGGR_SUM ? vsum : kind == MMA_AGGR_MEAN ? mean : kind == MMA_AGGR_MIN ? vmin
                                : kind == MMA_AGGR_MAX ? vmax : kind == MMA_AGGR_VAR ? var : sd;
                     for (int s = 0; s < p.S; ++s) {
 #pragma unroll
-                        for (int v = 0; v < 4; ++v) val.v[v] = __fmul_rn(val.v[v], fac[s]);       // cumulative (Q4)
-                        st_vec_stream<4>(yp + (int64_t)(s * p.A + a) * p.F_in, val);
+                        for (int v = 0; v < VEC; ++v) val.v[v] = __fmul_rn(val.v[v], fac[s]);       // cumulative (Q4)
+                        st_vec_stream<VEC>(yp + (int64_t)(s * p.A + a) * p.F_in, val);
                     }
                 }
             }
             if constexpr (MINMAX) {
-                int32_t o_mn[4], o_mx[4];
+                int32_t o_mn[VEC], o_mx[VEC];
 #pragma unroll
-                for (int v = 0; v < 4; ++v) {
+                for (int v = 0; v < VEC; ++v) {
                     o_mn[v] = amn[v] < 0 ? (int32_t)p.E_total : (p.args_local ? amn[v] : orig_edge_id(p, amn[v]));
                     o_mx[v] = amx[v] < 0 ? (int32_t)p.E_total : (p.args_local ? amx[v] : orig_edge_id(p, amx[v]));
                 }
-                if (amn_p) st_vec_i32_stream<4>(amn_p, o_mn);
-                if (amx_p) st_vec_i32_stream<4>(amx_p, o_mx);
+                if (amn_p) st_vec_i32_stream<VEC>(amn_p, o_mn);
+                if (amx_p) st_vec_i32_stream<VEC>(amx_p, o_mx);
             }
-            if (mean_p) st_vec_stream<4>(mean_p, mean);
+            if (mean_p) st_vec_stream<VEC>(mean_p, mean);
             if constexpr (SQ) {
-                if (var_p) st_vec_stream<4>(var_p, var);
+                if (var_p) st_vec_stream<VEC>(var_p, var);
             }
         };
         auto row_next = [&]() {
@@ -365,17 +387,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_fwd_stream(const __grid_
 
         if (len > 0) {
             ring.begin(p.col + s0, len);
-            run_stream<NST, true>(ring, s0, len, row_end, row_next,
-                [&](int at, const Vec<4> (&q)[4], int) {                    // 4 edges inside the row
-                    rng_refresh<DROP>(p, rid, pos, c, bits);
-                    uint32_t w[4];
+            run_stream<NST, true, VEC>(ring, s0, len, row_end, row_next,
+                [&](int at, const Vec<VEC> (&q)[4], int) {                    // 4 edges inside the row
+                    rng_refresh<DROP, VEC>(p, rid, pos, c, bits);
+                    uint32_t w[VEC];
                     const int sh = DROP == FD_BIT ? (pos & 31) : 0;
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) w[v] = bits[v] >> sh;
+                    for (int v = 0; v < VEC; ++v) w[v] = bits[v] >> sh;
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
 #pragma unroll
-                        for (int v = 0; v < 4; ++v) {
+                        for (int v = 0; v < VEC; ++v) {
                             const float x = fast_message<MSG_PQ, DROP>(pv.v[v], q[u].v[v], 0.0f, scale);
                             accumulate<false, DROP != FD_NONE, MINMAX, SQ>(x, keep_word<DROP>(w[v], u, thr), 1u, at + u,
                                                                            sum[v], sq[v], mn[v], mx[v], amn[v], amx[v]);
@@ -383,10 +405,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_fwd_stream(const __grid_
                     }
                     pos += 4;
                 },
-                [&](int at, const Vec<4> &q, int) {                         // one edge
-                    rng_refresh<DROP>(p, rid, pos, c, bits);
+                [&](int at, const Vec<VEC> &q, int) {                         // one edge
+                    rng_refresh<DROP, VEC>(p, rid, pos, c, bits);
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) {
+                    for (int v = 0; v < VEC; ++v) {
                         const float x = fast_message<MSG_PQ, DROP>(pv.v[v], q.v[v], 0.0f, scale);
                         accumulate<false, DROP != FD_NONE, MINMAX, SQ>(x, keep_at<DROP>(bits[v], pos, thr), 1u, at,
                                                                        sum[v], sq[v], mn[v], mx[v], amn[v], amx[v]);
@@ -407,21 +429,21 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_fwd_stream(const __grid_
 // ---------------------------------------------------------------------------------------------
 // backward, destination pass
 // ---------------------------------------------------------------------------------------------
-template <int NST, int WARPS, int DROP, bool NEEDM, bool LOCAL>
+template <int NST, int WARPS, int VEC, int DROP, bool NEEDM, bool LOCAL>
 __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_bwd_stream(const __grid_constant__ MMConvParams p) {
     extern __shared__ __align__(16) uint8_t smem_ring[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t gw = (int64_t)blockIdx.x * WARPS + warp, tw = (int64_t)gridDim.x * WARPS;
     const int64_t n_chunks = p.row_chunks ? p.n_chunks : tw;
-    const bool live = lane * 4 < p.ncols;
-    const int c = p.col0 + lane * 4;
+    const bool live = lane * VEC < p.ncols;
+    const int c = p.col0 + lane * VEC;
     const float scale = DROP == FD_BIT ? 2.0f : (DROP == FD_BYTE ? p.drop.scale : 1.0f);
     const uint32_t thr = p.drop.thr;
     const bool simple_out = p.simple_out != 0;
 
-    Ring<NST, NEEDM> ring;
+    Ring<NST, NEEDM, VEC> ring;
     ring.rowb = p.ncols * 4;
-    ring.base = smem_addr(smem_ring) + (uint32_t)warp * (uint32_t)(NST * 4 * ring.rowb) + (live ? (uint32_t)lane * 16u : 0u);   // idle lanes stay inside the ring
+    ring.base = smem_addr(smem_ring) + (uint32_t)warp * (uint32_t)(NST * 4 * ring.rowb) + (live ? (uint32_t)(lane * VEC * 4) : 0u);   // idle lanes stay inside the ring
     ring.Qc = reinterpret_cast<const char *>(p.Q + c);
     ring.ldq_b = (uint32_t)p.ldq * 4u;
     ring.lane = lane; ring.live = live;
@@ -438,10 +460,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_bwd_stream(const __grid_
 
         int row = r0;
         int row_beg = s0, row_end = __ldg(p.rowptr + r0 + 1);
-        Vec<4> base{}, gmin{}, gmax{}, alpha{}, pv{}, dp{};
-        int32_t amn[4], amx[4];
+        Vec<VEC> base{}, gmin{}, gmax{}, alpha{}, pv{}, dp{};
+        int32_t amn[VEC], amx[VEC];
         uint32_t rid = 0;
-        uint32_t bits[4] = {0u, 0u, 0u, 0u};
+        uint32_t bits[VEC] = {};
         int pos = 0;
         int64_t prow = 0;
         const float *dyp = p.dY + (int64_t)r0 * p.ldy + (p.T == 1 ? c : (c / p.F_in) * (p.S * p.A * p.F_in) + c % p.F_in);
@@ -449,9 +471,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_bwd_stream(const __grid_
 
         auto start_row = [&]() {          // folds dY of `row` into base / gmin / gmax / alpha (times the keep-scale)
             pos = 0;
-            base = Vec<4>{}; gmin = Vec<4>{}; gmax = Vec<4>{}; alpha = Vec<4>{}; pv = Vec<4>{}; dp = Vec<4>{};
+            base = Vec<VEC>{}; gmin = Vec<VEC>{}; gmax = Vec<VEC>{}; alpha = Vec<VEC>{}; pv = Vec<VEC>{}; dp = Vec<VEC>{};
 #pragma unroll
-            for (int v = 0; v < 4; ++v) { amn[v] = -1; amx[v] = -1; }
+            for (int v = 0; v < VEC; ++v) { amn[v] = -1; amx[v] = -1; }
             prow = p.row_map ? (int64_t)__ldg(p.row_map + row) : (int64_t)row;
             if (p.use_rng) rid = (uint32_t)(p.rng_row0 + (p.rng_row ? (int64_t)__ldg(p.rng_row + row) : (int64_t)row));
             if (!live) return;
@@ -459,44 +481,44 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_bwd_stream(const __grid_
             const int degc = deg > 1 ? deg : 1;
             const float degf = (float)degc;
             const float rdeg = 1.0f / degf;
-            Vec<4> mean{}, var{};
+            Vec<VEC> mean{}, var{};
             if constexpr (NEEDM) {
-                mean = ld_vec_stream<4>(p.c_mean + rowF);
-                var = ld_vec_stream<4>(p.c_var + rowF);
+                mean = ld_vec_stream<VEC>(p.c_mean + rowF);
+                var = ld_vec_stream<VEC>(p.c_var + rowF);
             }
             if (simple_out) {
                 // every kind at most once, S == 1: straight-line fold
                 if (p.zoff[MMA_AGGR_SUM] >= 0) {
-                    const Vec<4> d = ld_vec_stream<4>(dyp + p.zoff[MMA_AGGR_SUM]);
+                    const Vec<VEC> d = ld_vec_stream<VEC>(dyp + p.zoff[MMA_AGGR_SUM]);
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) base.v[v] += d.v[v];
+                    for (int v = 0; v < VEC; ++v) base.v[v] += d.v[v];
                 }
                 if (p.zoff[MMA_AGGR_MEAN] >= 0) {
-                    const Vec<4> d = ld_vec_stream<4>(dyp + p.zoff[MMA_AGGR_MEAN]);
+                    const Vec<VEC> d = ld_vec_stream<VEC>(dyp + p.zoff[MMA_AGGR_MEAN]);
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) base.v[v] += d.v[v] * rdeg;
+                    for (int v = 0; v < VEC; ++v) base.v[v] += d.v[v] * rdeg;
                 }
                 if (p.zoff[MMA_AGGR_MIN] >= 0) {
-                    gmin = ld_vec_stream<4>(dyp + p.zoff[MMA_AGGR_MIN]);
-                    ld_vec_i32_as<4>(p.c_arg_min + rowF, amn);
+                    gmin = ld_vec_stream<VEC>(dyp + p.zoff[MMA_AGGR_MIN]);
+                    ld_vec_i32_as<VEC>(p.c_arg_min + rowF, amn);
                 }
                 if (p.zoff[MMA_AGGR_MAX] >= 0) {
-                    gmax = ld_vec_stream<4>(dyp + p.zoff[MMA_AGGR_MAX]);
-                    ld_vec_i32_as<4>(p.c_arg_max + rowF, amx);
+                    gmax = ld_vec_stream<VEC>(dyp + p.zoff[MMA_AGGR_MAX]);
+                    ld_vec_i32_as<VEC>(p.c_arg_max + rowF, amx);
                 }
                 if constexpr (NEEDM) {
                     if (p.zoff[MMA_AGGR_VAR] >= 0) {    // var = E[m^2] - E[m]^2 -> d/dm_e = 2 (m_e - mean) / cnt
-                        const Vec<4> d = ld_vec_stream<4>(dyp + p.zoff[MMA_AGGR_VAR]);
+                        const Vec<VEC> d = ld_vec_stream<VEC>(dyp + p.zoff[MMA_AGGR_VAR]);
 #pragma unroll
-                        for (int v = 0; v < 4; ++v) {
+                        for (int v = 0; v < VEC; ++v) {
                             const float k = 2.0f * d.v[v] * rdeg;
                             alpha.v[v] += k; base.v[v] -= k * mean.v[v];
                         }
                     }
                     if (p.zoff[MMA_AGGR_STD] >= 0) {    // std = sqrt(relu(var) + 1e-5); relu'(0) = 0
-                        const Vec<4> d = ld_vec_stream<4>(dyp + p.zoff[MMA_AGGR_STD]);
+                        const Vec<VEC> d = ld_vec_stream<VEC>(dyp + p.zoff[MMA_AGGR_STD]);
 #pragma unroll
-                        for (int v = 0; v < 4; ++v) {
+                        for (int v = 0; v < VEC; ++v) {
                             if (var.v[v] > 0.0f) {
                                 const float k = d.v[v] * rdeg * rsqrtf(var.v[v] + 1e-5f);
                                 alpha.v[v] += k; base.v[v] -= k * mean.v[v];
@@ -510,15 +532,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_bwd_stream(const __grid_
                 for (int s = 1; s < p.S; ++s) fac[s] *= fac[s - 1];
                 bool has_min = false, has_max = false;
                 for (int a = 0; a < p.A; ++a) {
-                    Vec<4> dz{};
+                    Vec<VEC> dz{};
                     for (int s = 0; s < p.S; ++s) {
-                        const Vec<4> d = ld_vec_stream<4>(dyp + (int64_t)(s * p.A + a) * p.F_in);
+                        const Vec<VEC> d = ld_vec_stream<VEC>(dyp + (int64_t)(s * p.A + a) * p.F_in);
 #pragma unroll
-                        for (int v = 0; v < 4; ++v) dz.v[v] += d.v[v] * fac[s];
+                        for (int v = 0; v < VEC; ++v) dz.v[v] += d.v[v] * fac[s];
                     }
                     const int kind = p.akind[a];
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) {
+                    for (int v = 0; v < VEC; ++v) {
                         const float gg = dz.v[v];
                         if (kind == MMA_AGGR_SUM) base.v[v] += gg;
                         else if (kind == MMA_AGGR_MEAN) base.v[v] += gg / degf;
@@ -535,18 +557,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_bwd_stream(const __grid_
                     has_min |= kind == MMA_AGGR_MIN;
                     has_max |= kind == MMA_AGGR_MAX;
                 }
-                if (has_min) ld_vec_i32_as<4>(p.c_arg_min + rowF, amn);
-                if (has_max) ld_vec_i32_as<4>(p.c_arg_max + rowF, amx);
+                if (has_min) ld_vec_i32_as<VEC>(p.c_arg_min + rowF, amn);
+                if (has_max) ld_vec_i32_as<VEC>(p.c_arg_max + rowF, amx);
             }
-            if (NEEDM && p.P) pv = ld_vec_stream<4>(p.P + prow * p.ldp + c);
+            if (NEEDM && p.P) pv = ld_vec_stream<VEC>(p.P + prow * p.ldp + c);
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
+            for (int v = 0; v < VEC; ++v) {
                 base.v[v] *= scale; gmin.v[v] *= scale; gmax.v[v] *= scale; alpha.v[v] *= scale;
                 if constexpr (DROP == FD_BIT) pv.v[v] *= 2.0f;
             }
         };
         auto finish_row = [&]() {
-            if (p.dP && live) st_vec_stream<4>(p.dP + prow * p.lddp + c, dp);
+            if (p.dP && live) st_vec_stream<VEC>(p.dP + prow * p.lddp + c, dp);
         };
         auto row_next = [&]() {
             finish_row();
@@ -575,13 +597,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_bwd_stream(const __grid_
             if constexpr (!LOCAL) eid.init(load_eid);
             else { eid.cur = 0; eid.nxt = 0; }
 
-            auto one_edge = [&](int at, int s, const Vec<4> &q, const uint32_t (&kw)[4]) {
+            auto one_edge = [&](int at, int s, const Vec<VEC> &q, const uint32_t (&kw)[VEC]) {
                 const int gs = gslot.get(s);
                 int id = at;
                 if constexpr (!LOCAL) id = eid.get(s);
-                Vec<4> gr;
+                Vec<VEC> gr;
 #pragma unroll
-                for (int v = 0; v < 4; ++v) {
+                for (int v = 0; v < VEC; ++v) {
                     float t = base.v[v];
                     if constexpr (NEEDM) {
                         const float x = fast_message<MSG_PQ, DROP>(pv.v[v], q.v[v], 0.0f, scale);
@@ -589,31 +611,31 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_bwd_stream(const __grid_
                     }
                     route_grad<false>(t, id, amn[v], amx[v], gmin.v[v], gmax.v[v], kw[v], 1u, gr.v[v], dp.v[v]);
                 }
-                if (live && Gc) st_vec_stream<4>(reinterpret_cast<float *>(Gc + (uint64_t)(uint32_t)gs * ldg_b), gr);
+                if (live && Gc) st_vec_stream<VEC>(reinterpret_cast<float *>(Gc + (uint64_t)(uint32_t)gs * ldg_b), gr);
             };
 
             ring.begin(p.col + s0, len);
-            run_stream<NST, NEEDM>(ring, s0, len, row_end, row_next,
-                [&](int at, const Vec<4> (&q)[4], int s) {
-                    rng_refresh<DROP>(p, rid, pos, c, bits);
-                    uint32_t w[4];
+            run_stream<NST, NEEDM, VEC>(ring, s0, len, row_end, row_next,
+                [&](int at, const Vec<VEC> (&q)[4], int s) {
+                    rng_refresh<DROP, VEC>(p, rid, pos, c, bits);
+                    uint32_t w[VEC];
                     const int sh = DROP == FD_BIT ? (pos & 31) : 0;
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) w[v] = bits[v] >> sh;
+                    for (int v = 0; v < VEC; ++v) w[v] = bits[v] >> sh;
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        uint32_t kw[4];
+                        uint32_t kw[VEC];
 #pragma unroll
-                        for (int v = 0; v < 4; ++v) kw[v] = keep_word<DROP>(w[v], u, thr);
+                        for (int v = 0; v < VEC; ++v) kw[v] = keep_word<DROP>(w[v], u, thr);
                         one_edge(at + u, s + u, q[u], kw);
                     }
                     pos += 4;
                 },
-                [&](int at, const Vec<4> &q, int s) {
-                    rng_refresh<DROP>(p, rid, pos, c, bits);
-                    uint32_t kw[4];
+                [&](int at, const Vec<VEC> &q, int s) {
+                    rng_refresh<DROP, VEC>(p, rid, pos, c, bits);
+                    uint32_t kw[VEC];
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) kw[v] = keep_at<DROP>(bits[v], pos, thr);
+                    for (int v = 0; v < VEC; ++v) kw[v] = keep_at<DROP>(bits[v], pos, thr);
                     one_edge(at, s, q, kw);
                     ++pos;
                 },
