@@ -99,6 +99,16 @@ int mma_invert_perm(const int32_t *perm, int64_t E, int32_t *inv, mma_stream_t s
  *                       row_chunks[n_chunks] = n_rows), chunks of about equal cost (edges + ~6 per row),
  *                       many more chunks than SMs x 16 warps; they are dealt round-robin to the warps.
  *                       NULL: one chunk per warp found by a binary search over rowptr (poorer balance).
+ *   vrowptr [n_vrows+1], seg_tab [n_vrows][4], split_tab [n_split][4], seg_ws : optional handling of very long
+ *                       rows (skewed degree distributions) in the persistent kernels.  vrowptr is a VIRTUAL row
+ *                       pointer over the same CSR slots in which every row longer than a segment length L
+ *                       (a multiple of 32) is cut into ceil(deg / L) segments; seg_tab[v] = {real row, in-row
+ *                       position of the segment's first edge, partial slot (numbered 0.. over all segments of
+ *                       split rows, -1 for an unsplit row), 0}; split_tab[i] = {real row, first slot, number of
+ *                       segments, 0}; seg_ws: workspace of 6*F floats (forward) / F floats (backward) per slot.
+ *                       Segments are walked by different warps and merged in segment order by a second kernel
+ *                       (min/max and their arg indices stay bit-exact).  row_chunks then partition the VIRTUAL
+ *                       rows.  NULL: every row is walked by one warp.
  *   P [n_rows, F] ld ldp | Q [n_src, F] ld ldq | R [E, F] ld ldr, ORIGINAL edge order | any may be NULL
  *   keep [E, F] ld ldk : explicit keep-scale (0 or 1/(1-p)), original edge order, or NULL
  *   p_drop, seed      : if keep == NULL and p_drop > 0: in-kernel Philox4x32-10 dropout keyed by
@@ -132,6 +142,8 @@ int mmconv_aggregate_fwd(const int32_t *rowptr, const int32_t *col, const int32_
                          const int32_t *edge_gid, int64_t E_total, const int32_t *row_map,
                          const int32_t *rng_row, int64_t rng_row0,
                          const int32_t *row_chunks, int64_t n_chunks,
+                         const int32_t *vrowptr, int64_t n_vrows, const int32_t *seg_tab,
+                         const int32_t *split_tab, int64_t n_split, float *seg_ws,
                          int64_t n_rows, int64_t E,
                          const float *P, int64_t ldp, const float *Q, int64_t ldq,
                          const float *R, int64_t ldr, const float *keep, int64_t ldk,
@@ -152,6 +164,8 @@ int mmconv_aggregate_bwd_dst(const int32_t *rowptr, const int32_t *col, const in
                              const int32_t *edge_gid, int64_t E_total, const int32_t *row_map,
                              const int32_t *rng_row, int64_t rng_row0,
                              const int32_t *row_chunks, int64_t n_chunks,
+                             const int32_t *vrowptr, int64_t n_vrows, const int32_t *seg_tab,
+                             const int32_t *split_tab, int64_t n_split, float *seg_ws,
                              int64_t n_rows, int64_t E,
                              const float *P, int64_t ldp, const float *Q, int64_t ldq,
                              const float *R, int64_t ldr, const float *keep, int64_t ldk,

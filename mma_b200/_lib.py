@@ -30,10 +30,12 @@ _SIGS = {
     "mma_csr_build_workspace_bytes": ([_i64, _i64, C.POINTER(C.c_size_t)], C.c_int),
     "mma_csr_build": ([_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, C.c_size_t, _vp], C.c_int),
     "mma_invert_perm": ([_vp, _i64, _vp, _vp], C.c_int),
-    "mmconv_aggregate_fwd": ([_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64,
+    "mmconv_aggregate_fwd": ([_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp,
+                              _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64,
                               _vp, _i64, _f32, _u64, _vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _i64,
                               _vp, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp], C.c_int),
-    "mmconv_aggregate_bwd_dst": ([_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64,
+    "mmconv_aggregate_bwd_dst": ([_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp,
+                                  _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64,
                                   _vp, _i64, _f32, _u64, _vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _i64,
                                   _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp],
                                  C.c_int),

@@ -37,6 +37,10 @@ enum { MSG_PQ = 0, MSG_PQR = 1, MSG_R = 2, MSG_GENERIC = 3 };
 struct MMConvParams {
     const int32_t *rowptr, *col, *perm, *gid, *row_map, *rng_row, *row_chunks;
     int64_t n_rows, E, E_total, rng_row0, n_chunks;
+    // long rows cut into segments (stream kernels only, see mmconv_stream.cuh)
+    const int32_t *vrowptr, *seg_tab, *split_tab;
+    int64_t n_vrows, n_split;
+    float *seg_ws;
     int use_rng, args_local;
     int simple_out;          // S == 1 and every aggregator kind at most once: zoff[kind] = its column offset in a Y row (-1: absent)
     int zoff[6];
@@ -793,7 +797,9 @@ __global__ void __launch_bounds__(256, 2) mmconv_bwd_fast(const __grid_constant_
 // ----------------------------------------------------------------------------------------
 static int fill_params(MMConvParams &p, const int32_t *rowptr, const int32_t *col, const int32_t *perm,
                        const int32_t *gid, int64_t E_total, const int32_t *row_map, const int32_t *rng_row,
-                       int64_t rng_row0, const int32_t *row_chunks, int64_t n_chunks, int64_t n_rows, int64_t E,
+                       int64_t rng_row0, const int32_t *row_chunks, int64_t n_chunks,
+                       const int32_t *vrowptr, int64_t n_vrows, const int32_t *seg_tab, const int32_t *split_tab,
+                       int64_t n_split, float *seg_ws, int64_t n_rows, int64_t E,
                        const float *P, int64_t ldp, const float *Q, int64_t ldq,
                        const float *R, int64_t ldr, const float *keep, int64_t ldk, float p_drop, uint64_t seed,
                        const uint64_t *seed_dev,
@@ -812,6 +818,10 @@ static int fill_params(MMConvParams &p, const int32_t *rowptr, const int32_t *co
     p.rng_row = rng_row; p.rng_row0 = rng_row0;
     if (row_chunks && n_chunks < 1) return MMA_ERR_INVALID;
     p.row_chunks = row_chunks; p.n_chunks = row_chunks ? n_chunks : 0;
+    if (vrowptr && (n_vrows < n_rows || !seg_tab || n_split < 0 || (n_split > 0 && (!split_tab || !seg_ws))))
+        return MMA_ERR_INVALID;
+    p.vrowptr = vrowptr; p.n_vrows = vrowptr ? n_vrows : 0; p.seg_tab = vrowptr ? seg_tab : nullptr;
+    p.split_tab = vrowptr ? split_tab : nullptr; p.n_split = vrowptr ? n_split : 0; p.seg_ws = vrowptr ? seg_ws : nullptr;
     p.E_total = gid ? E_total : E;
     p.P = P; p.Q = Q; p.R = R; p.keep = keep; p.ldp = ldp; p.ldq = ldq; p.ldr = ldr; p.ldk = ldk;
     p.drop = make_dropout(p_drop, seed, seed_dev);
@@ -950,6 +960,8 @@ extern "C" int mmconv_aggregate_fwd(const int32_t *rowptr, const int32_t *col, c
                                     const int32_t *edge_gid, int64_t E_total, const int32_t *row_map,
                                     const int32_t *rng_row, int64_t rng_row0,
                                     const int32_t *row_chunks, int64_t n_chunks,
+                                    const int32_t *vrowptr, int64_t n_vrows, const int32_t *seg_tab,
+                                    const int32_t *split_tab, int64_t n_split, float *seg_ws,
                                     int64_t n_rows, int64_t E, const float *P, int64_t ldp,
                                     const float *Q, int64_t ldq, const float *R, int64_t ldr,
                                     const float *keep, int64_t ldk, float p_drop, uint64_t seed,
@@ -961,7 +973,7 @@ extern "C" int mmconv_aggregate_fwd(const int32_t *rowptr, const int32_t *col, c
                                     mma_stream_t stream) {
     MMConvParams p;
     int rc = fill_params(p, rowptr, col, perm, edge_gid, E_total, row_map, rng_row, rng_row0, row_chunks, n_chunks,
-                         n_rows, E, P, ldp,
+                         vrowptr, n_vrows, seg_tab, split_tab, n_split, seg_ws, n_rows, E, P, ldp,
                          Q, ldq, R, ldr, keep, ldk, p_drop, seed, seed_dev, T, F_in, A, aggr_kinds, S, scaler_kinds,
                          scale_tab, tab_stride, flags);
     if (rc != MMA_OK) return rc;
@@ -1004,6 +1016,13 @@ extern "C" int mmconv_aggregate_fwd(const int32_t *rowptr, const int32_t *col, c
             else e = launch_fwd_stream<6, 16, 1, FD_BIT>(p, minmax, sq, st);
         }
         MMA_CUDA_CHECK(e);
+        if (p.n_split > 0) {                            // merge the segments of the split rows, emit those rows
+            const unsigned g = (unsigned)p.n_split;
+            if (minmax && sq) stream::mmconv_fwd_merge<true, true><<<g, 128, 0, st>>>(p);
+            else if (minmax) stream::mmconv_fwd_merge<true, false><<<g, 128, 0, st>>>(p);
+            else if (sq) stream::mmconv_fwd_merge<false, true><<<g, 128, 0, st>>>(p);
+            else stream::mmconv_fwd_merge<false, false><<<g, 128, 0, st>>>(p);
+        }
     } else if (vec == 4 && !keep && (msg == MSG_PQ || msg == MSG_PQR)) {
         // fast kernels: 128-bit columns, message and dropout mode fixed at compile time
         const int fd = fast_drop_mode(p.drop);
@@ -1036,6 +1055,8 @@ extern "C" int mmconv_aggregate_bwd_dst(const int32_t *rowptr, const int32_t *co
                                         const int32_t *edge_gid, int64_t E_total, const int32_t *row_map,
                                         const int32_t *rng_row, int64_t rng_row0,
                                         const int32_t *row_chunks, int64_t n_chunks,
+                                        const int32_t *vrowptr, int64_t n_vrows, const int32_t *seg_tab,
+                                        const int32_t *split_tab, int64_t n_split, float *seg_ws,
                                         int64_t n_rows, int64_t E, const float *P, int64_t ldp,
                                         const float *Q, int64_t ldq, const float *R, int64_t ldr,
                                         const float *keep, int64_t ldk, float p_drop, uint64_t seed,
@@ -1048,7 +1069,7 @@ extern "C" int mmconv_aggregate_bwd_dst(const int32_t *rowptr, const int32_t *co
                                         int col0, int ncols, int flags, mma_stream_t stream) {
     MMConvParams p;
     int rc = fill_params(p, rowptr, col, perm, edge_gid, E_total, row_map, rng_row, rng_row0, row_chunks, n_chunks,
-                         n_rows, E, P, ldp,
+                         vrowptr, n_vrows, seg_tab, split_tab, n_split, seg_ws, n_rows, E, P, ldp,
                          Q, ldq, R, ldr, keep, ldk, p_drop, seed, seed_dev, T, F_in, A, aggr_kinds, S, scaler_kinds,
                          scale_tab, tab_stride, flags);
     if (rc != MMA_OK) return rc;
@@ -1094,6 +1115,7 @@ extern "C" int mmconv_aggregate_bwd_dst(const int32_t *rowptr, const int32_t *co
             else e = launch_bwd_stream<6, 16, 1, FD_BIT>(p, needm, st);
         }
         MMA_CUDA_CHECK(e);
+        if (p.n_split > 0) stream::mmconv_bwd_merge<<<(unsigned)p.n_split, 128, 0, st>>>(p);
     } else if (vec == 4 && !keep && (!needm || msg == MSG_PQ || msg == MSG_PQR)) {
         const int fd = fast_drop_mode(p.drop);
         if (needm && msg == MSG_PQR) {

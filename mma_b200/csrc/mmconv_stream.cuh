@@ -66,14 +66,119 @@ __device__ __forceinline__ int first_row_at(const int32_t *rowptr, int64_t n_row
     return (int)lo;
 }
 
-// rows [r0, r1) of chunk i
-__device__ __forceinline__ void chunk_rows(const MMConvParams &p, int64_t i, int64_t n_chunks, int &r0, int &r1) {
+// IEEE-correct a / y for the row's degree y (integer valued, 1 <= y <= 2^24) with the reciprocal shared by
+// all columns: r = 1/y refined once; q = a*r corrected by one residual step is the correctly rounded
+// quotient whenever nothing under/overflows, which the exponent test guarantees; otherwise __fdiv_rn.
+struct DivByDeg {
+    float y, r;
+    __device__ __forceinline__ explicit DivByDeg(float y_) : y(y_) {
+        float r0;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(y_));
+        const float e = __fmaf_rn(-y_, r0, 1.0f);
+        r = __fmaf_rn(r0, e, r0);
+    }
+    __device__ __forceinline__ float operator()(float a) const {
+        const uint32_t ex = (__float_as_uint(a) >> 23) & 0xFFu;
+        if (ex - 40u < 176u) {                       // 2^-87 <= |a| < 2^89: no intermediate can leave the normal range
+            const float q0 = __fmul_rn(a, r);
+            const float rem = __fmaf_rn(-y, q0, a);
+            return __fmaf_rn(r, rem, q0);
+        }
+        return __fdiv_rn(a, y);
+    }
+};
+
+// (virtual) rows [r0, r1) of chunk i; rp / n_rows: the row pointer the stream walks
+__device__ __forceinline__ void chunk_rows(const MMConvParams &p, const int32_t *rp, int64_t n_rows, int64_t i,
+                                           int64_t n_chunks, int &r0, int &r1) {
     if (p.row_chunks) {
         r0 = __ldg(p.row_chunks + i); r1 = __ldg(p.row_chunks + i + 1);
     } else {
-        const int64_t total = p.E + kRowCost * p.n_rows;
-        r0 = first_row_at(p.rowptr, p.n_rows, (total * i) / n_chunks);
-        r1 = (i + 1 == n_chunks) ? (int)p.n_rows : first_row_at(p.rowptr, p.n_rows, (total * (i + 1)) / n_chunks);
+        const int64_t total = p.E + kRowCost * n_rows;
+        r0 = first_row_at(rp, n_rows, (total * i) / n_chunks);
+        r1 = (i + 1 == n_chunks) ? (int)n_rows : first_row_at(rp, n_rows, (total * (i + 1)) / n_chunks);
+    }
+}
+
+// Long rows.  A row of a skewed graph can hold a large share of all edges; walked by one warp it would set
+// the kernel's duration.  The caller may therefore pass a VIRTUAL row pointer in which every row longer than
+// a segment length (a multiple of 32) is cut into segments: seg_tab[v] = {real row, in-row position of the
+// segment's first edge, partial slot or -1 for an unsplit row, 0}.  A segment is walked like a row (same
+// dropout positions, same edge order) but ends by writing its partial state to seg_ws[slot]; a small second
+// kernel merges the partials of each split row IN SEGMENT ORDER (strict comparisons, so the first occurrence
+// still wins and min/max stay bit-exact; sums differ from the sequential order only by rounding) and emits
+// the row.
+struct RowDesc { int real, pos0, slot; };
+__device__ __forceinline__ RowDesc row_desc(const MMConvParams &p, int v) {
+    RowDesc d{v, 0, -1};
+    if (p.seg_tab) {
+        const int4 t = __ldg(reinterpret_cast<const int4 *>(p.seg_tab) + v);
+        d.real = t.x; d.pos0 = t.y; d.slot = t.z;
+    }
+    return d;
+}
+
+// aggregates of one finished row -> Y / arg indices / saved statistics (this lane's VEC columns)
+template <int VEC, bool MINMAX, bool SQ>
+__device__ __forceinline__ void emit_row(const MMConvParams &p, bool simple_out, int deg, const float (&sum)[VEC],
+                                         const float (&sq)[VEC], const float (&mn)[VEC], const float (&mx)[VEC],
+                                         const int (&amn)[VEC], const int (&amx)[VEC], float *yp, int32_t *amn_p,
+                                         int32_t *amx_p, float *mean_p, float *var_p) {
+    const int degc = deg > 1 ? deg : 1;                     // deg.clamp_(1), mma_conv.py:179
+    const DivByDeg div((float)degc);
+    Vec<VEC> mean, var, sd, vmin, vmax, vsum;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        vsum.v[v] = sum[v];
+        mean.v[v] = div(sum[v]);                            // sum / count.clamp(min=1)
+        if constexpr (SQ) {
+            const float msq = div(sq[v]);
+            var.v[v] = __fsub_rn(msq, __fmul_rn(mean.v[v], mean.v[v]));         // mma_conv.py:170, no FMA
+            sd.v[v] = sqrtf(__fadd_rn(fmaxf(var.v[v], 0.0f), 1e-5f));           // mma_conv.py:172
+        } else {
+            var.v[v] = 0.0f; sd.v[v] = 0.0f;
+        }
+        vmin.v[v] = (MINMAX && amn[v] >= 0) ? mn[v] : 0.0f;                      // empty row -> 0
+        vmax.v[v] = (MINMAX && amx[v] >= 0) ? mx[v] : 0.0f;
+    }
+    if (simple_out) {
+        if (p.zoff[MMA_AGGR_SUM] >= 0) st_vec_stream<VEC>(yp + p.zoff[MMA_AGGR_SUM], vsum);
+        if (p.zoff[MMA_AGGR_MEAN] >= 0) st_vec_stream<VEC>(yp + p.zoff[MMA_AGGR_MEAN], mean);
+        if constexpr (MINMAX) {
+            if (p.zoff[MMA_AGGR_MIN] >= 0) st_vec_stream<VEC>(yp + p.zoff[MMA_AGGR_MIN], vmin);
+            if (p.zoff[MMA_AGGR_MAX] >= 0) st_vec_stream<VEC>(yp + p.zoff[MMA_AGGR_MAX], vmax);
+        }
+        if constexpr (SQ) {
+            if (p.zoff[MMA_AGGR_VAR] >= 0) st_vec_stream<VEC>(yp + p.zoff[MMA_AGGR_VAR], var);
+            if (p.zoff[MMA_AGGR_STD] >= 0) st_vec_stream<VEC>(yp + p.zoff[MMA_AGGR_STD], sd);
+        }
+    } else {
+        float fac[MMA_MAX_SCALER];
+        scaler_factors(p, degc, fac);
+        for (int a = 0; a < p.A; ++a) {
+            const int kind = p.akind[a];
+            Vec<VEC> val = kind == MMA_AGGR_SUM ? vsum : kind == MMA_AGGR_MEAN ? mean : kind == MMA_AGGR_MIN ? vmin
+                       : kind == MMA_AGGR_MAX ? vmax : kind == MMA_AGGR_VAR ? var : sd;
+            for (int s = 0; s < p.S; ++s) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) val.v[v] = __fmul_rn(val.v[v], fac[s]);       // cumulative (Q4)
+                st_vec_stream<VEC>(yp + (int64_t)(s * p.A + a) * p.F_in, val);
+            }
+        }
+    }
+    if constexpr (MINMAX) {
+        int32_t o_mn[VEC], o_mx[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            o_mn[v] = amn[v] < 0 ? (int32_t)p.E_total : (p.args_local ? amn[v] : orig_edge_id(p, amn[v]));
+            o_mx[v] = amx[v] < 0 ? (int32_t)p.E_total : (p.args_local ? amx[v] : orig_edge_id(p, amx[v]));
+        }
+        if (amn_p) st_vec_i32_stream<VEC>(amn_p, o_mn);
+        if (amx_p) st_vec_i32_stream<VEC>(amx_p, o_mx);
+    }
+    if (mean_p) st_vec_stream<VEC>(mean_p, mean);
+    if constexpr (SQ) {
+        if (var_p) st_vec_stream<VEC>(var_p, var);
     }
 }
 
@@ -214,28 +319,6 @@ __device__ __forceinline__ uint32_t keep_at(uint32_t word, int pos, uint32_t thr
     else return 1u;
 }
 
-// IEEE-correct a / y for the row's degree y (integer valued, 1 <= y <= 2^24) with the reciprocal shared by
-// all columns: r = 1/y refined once; q = a*r corrected by one residual step is the correctly rounded
-// quotient whenever nothing under/overflows, which the exponent test guarantees; otherwise __fdiv_rn.
-struct DivByDeg {
-    float y, r;
-    __device__ __forceinline__ explicit DivByDeg(float y_) : y(y_) {
-        float r0;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(y_));
-        const float e = __fmaf_rn(-y_, r0, 1.0f);
-        r = __fmaf_rn(r0, e, r0);
-    }
-    __device__ __forceinline__ float operator()(float a) const {
-        const uint32_t ex = (__float_as_uint(a) >> 23) & 0xFFu;
-        if (ex - 40u < 176u) {                       // 2^-87 <= |a| < 2^89: no intermediate can leave the normal range
-            const float q0 = __fmul_rn(a, r);
-            const float rem = __fmaf_rn(-y, q0, a);
-            return __fmaf_rn(r, rem, q0);
-        }
-        return __fdiv_rn(a, y);
-    }
-};
-
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
@@ -259,39 +342,40 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_fwd_stream(const __grid_
     ring.Qc = reinterpret_cast<const char *>(p.Q + c);
     ring.ldq_b = (uint32_t)p.ldq * 4u;
     ring.lane = lane; ring.live = live;
+    const int32_t *rp = p.vrowptr ? p.vrowptr : p.rowptr;      // the (virtual) row boundaries walked by the stream
+    const int64_t n_rows = p.vrowptr ? p.n_vrows : p.n_rows;
+    const int ycol = p.T == 1 ? c : (c / p.F_in) * (p.S * p.A * p.F_in) + c % p.F_in;
 
 #pragma unroll 1
     for (int64_t chunk = gw; chunk < n_chunks; chunk += tw) {
         int r0, r1;
-        chunk_rows(p, chunk, n_chunks, r0, r1);
+        chunk_rows(p, rp, n_rows, chunk, n_chunks, r0, r1);
         if (r0 >= r1) continue;
-        const int s0 = __ldg(p.rowptr + r0);
-        const int len = __ldg(p.rowptr + r1) - s0;
+        const int s0 = __ldg(rp + r0);
+        const int len = __ldg(rp + r1) - s0;
 
         // ---- per-row state; the next row's inputs are fetched one row ahead ----
         int row = r0;
-        int row_beg = s0, row_end = __ldg(p.rowptr + r0 + 1);
-        int next_end = r0 + 2 <= p.n_rows ? __ldg(p.rowptr + r0 + 2) : 0x7fffffff;
+        int row_beg = s0, row_end = __ldg(rp + r0 + 1);
+        int next_end = r0 + 2 <= n_rows ? __ldg(rp + r0 + 2) : 0x7fffffff;
         Vec<VEC> pv{}, pv_next{};
         uint32_t rid = 0, rid_next = 0;
+        RowDesc rd{}, rd_next{};
         float sum[VEC], sq[VEC], mn[VEC], mx[VEC];
         int amn[VEC], amx[VEC];
         uint32_t bits[VEC] = {};
         int pos = 0;                                        // in-row position of the next edge
-        // running output pointers (this lane's columns of row `row`)
-        float *yp = p.Y + (int64_t)r0 * p.ldy + (p.T == 1 ? c : (c / p.F_in) * (p.S * p.A * p.F_in) + c % p.F_in);
-        const int64_t rowF = (int64_t)r0 * p.F + c;
-        int32_t *amn_p = p.arg_min ? p.arg_min + rowF : nullptr;
-        int32_t *amx_p = p.arg_max ? p.arg_max + rowF : nullptr;
-        float *mean_p = p.stat_mean ? p.stat_mean + rowF : nullptr;
-        float *var_p = p.stat_var ? p.stat_var + rowF : nullptr;
+        float *yp = nullptr;                                // running output pointers (this lane's columns of the row)
+        int32_t *amn_p = nullptr, *amx_p = nullptr;
+        float *mean_p = nullptr, *var_p = nullptr;
 
-        auto fetch_row_inputs = [&](int r, Vec<VEC> &pvv, uint32_t &rd) {      // P row (pre-scaled) and rng id of row r
-            pvv = Vec<VEC>{}; rd = 0;
+        auto fetch_row_inputs = [&](int r, Vec<VEC> &pvv, uint32_t &rdid, RowDesc &d) {   // P row (pre-scaled), rng id
+            pvv = Vec<VEC>{}; rdid = 0; d = RowDesc{r, 0, -1};
             if (r < r1) {
-                const int64_t prow = p.row_map ? (int64_t)__ldg(p.row_map + r) : (int64_t)r;
+                d = row_desc(p, r);
+                const int64_t prow = p.row_map ? (int64_t)__ldg(p.row_map + d.real) : (int64_t)d.real;
                 if (live) pvv = ld_vec_stream<VEC>(p.P + prow * p.ldp + c);
-                if (p.use_rng) rd = (uint32_t)(p.rng_row0 + (p.rng_row ? (int64_t)__ldg(p.rng_row + r) : (int64_t)r));
+                if (p.use_rng) rdid = (uint32_t)(p.rng_row0 + (p.rng_row ? (int64_t)__ldg(p.rng_row + d.real) : (int64_t)d.real));
             }
             if constexpr (DROP == FD_BIT) {
 #pragma unroll
@@ -303,86 +387,65 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_fwd_stream(const __grid_
             for (int v = 0; v < VEC; ++v) {
                 sum[v] = 0.0f; sq[v] = 0.0f; mn[v] = FLT_MAX; mx[v] = -FLT_MAX; amn[v] = -1; amx[v] = -1;
             }
-            pos = 0;
+            pos = rd.pos0;
+        };
+        auto point_at = [&](int real) {
+            yp = p.Y + (int64_t)real * p.ldy + ycol;
+            const int64_t rowF = (int64_t)real * p.F + c;
+            amn_p = p.arg_min ? p.arg_min + rowF : nullptr;
+            amx_p = p.arg_max ? p.arg_max + rowF : nullptr;
+            mean_p = p.stat_mean ? p.stat_mean + rowF : nullptr;
+            var_p = p.stat_var ? p.stat_var + rowF : nullptr;
         };
         auto finish_row = [&]() {
             if (!live) return;
-            const int deg = row_end - row_beg;
-            const int degc = deg > 1 ? deg : 1;                     // deg.clamp_(1), mma_conv.py:179
-            const DivByDeg div((float)degc);
-            Vec<VEC> mean, var, sd, vmin, vmax, vsum;
+            if (rd.slot >= 0) {                             // a segment of a split row: partial state -> workspace
+                float *w = p.seg_ws + (int64_t)rd.slot * 6 * p.F + c;
+                Vec<VEC> t;
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                vsum.v[v] = sum[v];
-                mean.v[v] = div(sum[v]);                            // sum / count.clamp(min=1)
-                if constexpr (SQ) {
-                    const float msq = div(sq[v]);
-                    var.v[v] = __fsub_rn(msq, __fmul_rn(mean.v[v], mean.v[v]));         // mma_conv.py:170, no FMA
-                    sd.v[v] = sqrtf(__fadd_rn(fmaxf(var.v[v], 0.0f), 1e-5f));           // mma_conv.py:172
-                } else {
-                    var.v[v] = 0.0f; sd.v[v] = 0.0f;
-                }
-                vmin.v[v] = (MINMAX && amn[v] >= 0) ? mn[v] : 0.0f;                      // empty row -> 0
-                vmax.v[v] = (MINMAX && amx[v] >= 0) ? mx[v] : 0.0f;
-            }
-            if (simple_out) {
-                if (p.zoff[MMA_AGGR_SUM] >= 0) st_vec_stream<VEC>(yp + p.zoff[MMA_AGGR_SUM], vsum);
-                if (p.zoff[MMA_AGGR_MEAN] >= 0) st_vec_stream<VEC>(yp + p.zoff[MMA_AGGR_MEAN], mean);
-                if constexpr (MINMAX) {
-                    if (p.zoff[MMA_AGGR_MIN] >= 0) st_vec_stream<VEC>(yp + p.zoff[MMA_AGGR_MIN], vmin);
-                    if (p.zoff[MMA_AGGR_MAX] >= 0) st_vec_stream<VEC>(yp + p.zoff[MMA_AGGR_MAX], vmax);
-                }
-                if constexpr (SQ) {
-                    if (p.zoff[MMA_AGGR_VAR] >= 0) st_vec_stream<VEC>(yp + p.zoff[MMA_AGGR_VAR], var);
-                    if (p.zoff[MMA_AGGR_STD] >= 0) st_vec_stream<VEC>(yp + p.zoff[MMA_AGGR_STD], sd);
-                }
-            } else {
-                float fac[MMA_MAX_SCALER];
-                scaler_factors(p, degc, fac);
-                for (int a = 0; a < p.A; ++a) {
-                    const int kind = p.akind[a];
-                    Vec<VEC> val = kind == MMA_AGGR_SUM ? vsum : kind == MMA_AGGR_MEAN ? mean : kind == MMA_AGGR_MIN ? vmin
-                               : kind == MMA_AGGR_MAX ? vmax : kind == MMA_AGGR_VAR ? var : sd;
-                    for (int s = 0; s < p.S; ++s) {
+                for (int v = 0; v < VEC; ++v) t.v[v] = sum[v];
+                st_vec<VEC>(w, t);
 #pragma unroll
-                        for (int v = 0; v < VEC; ++v) val.v[v] = __fmul_rn(val.v[v], fac[s]);       // cumulative (Q4)
-                        st_vec_stream<VEC>(yp + (int64_t)(s * p.A + a) * p.F_in, val);
-                    }
-                }
-            }
-            if constexpr (MINMAX) {
-                int32_t o_mn[VEC], o_mx[VEC];
+                for (int v = 0; v < VEC; ++v) t.v[v] = sq[v];
+                st_vec<VEC>(w + p.F, t);
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) {
-                    o_mn[v] = amn[v] < 0 ? (int32_t)p.E_total : (p.args_local ? amn[v] : orig_edge_id(p, amn[v]));
-                    o_mx[v] = amx[v] < 0 ? (int32_t)p.E_total : (p.args_local ? amx[v] : orig_edge_id(p, amx[v]));
-                }
-                if (amn_p) st_vec_i32_stream<VEC>(amn_p, o_mn);
-                if (amx_p) st_vec_i32_stream<VEC>(amx_p, o_mx);
+                for (int v = 0; v < VEC; ++v) t.v[v] = mn[v];
+                st_vec<VEC>(w + 2 * p.F, t);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) t.v[v] = mx[v];
+                st_vec<VEC>(w + 3 * p.F, t);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) t.v[v] = __int_as_float(amn[v]);
+                st_vec<VEC>(w + 4 * p.F, t);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) t.v[v] = __int_as_float(amx[v]);
+                st_vec<VEC>(w + 5 * p.F, t);
+                return;
             }
-            if (mean_p) st_vec_stream<VEC>(mean_p, mean);
-            if constexpr (SQ) {
-                if (var_p) st_vec_stream<VEC>(var_p, var);
-            }
+            emit_row<VEC, MINMAX, SQ>(p, simple_out, row_end - row_beg, sum, sq, mn, mx, amn, amx, yp, amn_p, amx_p,
+                                      mean_p, var_p);
         };
         auto row_next = [&]() {
             finish_row();
             ++row;
-            yp += p.ldy;
-            if (amn_p) amn_p += p.F;
-            if (amx_p) amx_p += p.F;
-            if (mean_p) mean_p += p.F;
-            if (var_p) var_p += p.F;
+            if (rd_next.real != rd.real) {                  // segments of one row share the output row
+                yp += p.ldy;
+                if (amn_p) amn_p += p.F;
+                if (amx_p) amx_p += p.F;
+                if (mean_p) mean_p += p.F;
+                if (var_p) var_p += p.F;
+            }
             row_beg = row_end;
             row_end = next_end;
-            next_end = row + 2 <= p.n_rows ? __ldg(p.rowptr + row + 2) : 0x7fffffff;
-            pv = pv_next; rid = rid_next;
-            fetch_row_inputs(row + 1, pv_next, rid_next);
+            next_end = row + 2 <= n_rows ? __ldg(rp + row + 2) : 0x7fffffff;
+            pv = pv_next; rid = rid_next; rd = rd_next;
+            fetch_row_inputs(row + 1, pv_next, rid_next, rd_next);
             reset_acc();
         };
 
-        fetch_row_inputs(row, pv, rid);
-        fetch_row_inputs(row + 1, pv_next, rid_next);
+        fetch_row_inputs(row, pv, rid, rd);
+        fetch_row_inputs(row + 1, pv_next, rid_next, rd_next);
+        point_at(rd.real);
         reset_acc();
 
         if (len > 0) {
@@ -449,35 +512,43 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_bwd_stream(const __grid_
     ring.lane = lane; ring.live = live;
     char *Gc = p.G ? reinterpret_cast<char *>(p.G + c) : nullptr;
     const uint32_t ldg_b = (uint32_t)p.ldg * 4u;
+    const int32_t *rp = p.vrowptr ? p.vrowptr : p.rowptr;      // the (virtual) row boundaries walked by the stream
+    const int64_t n_rows = p.vrowptr ? p.n_vrows : p.n_rows;
+    const int ycol = p.T == 1 ? c : (c / p.F_in) * (p.S * p.A * p.F_in) + c % p.F_in;
 
 #pragma unroll 1
     for (int64_t chunk = gw; chunk < n_chunks; chunk += tw) {
         int r0, r1;
-        chunk_rows(p, chunk, n_chunks, r0, r1);
+        chunk_rows(p, rp, n_rows, chunk, n_chunks, r0, r1);
         if (r0 >= r1) continue;
-        const int s0 = __ldg(p.rowptr + r0);
-        const int len = __ldg(p.rowptr + r1) - s0;
+        const int s0 = __ldg(rp + r0);
+        const int len = __ldg(rp + r1) - s0;
 
         int row = r0;
-        int row_beg = s0, row_end = __ldg(p.rowptr + r0 + 1);
+        int row_beg = s0, row_end = __ldg(rp + r0 + 1);
         Vec<VEC> base{}, gmin{}, gmax{}, alpha{}, pv{}, dp{};
         int32_t amn[VEC], amx[VEC];
         uint32_t rid = 0;
         uint32_t bits[VEC] = {};
         int pos = 0;
         int64_t prow = 0;
-        const float *dyp = p.dY + (int64_t)r0 * p.ldy + (p.T == 1 ? c : (c / p.F_in) * (p.S * p.A * p.F_in) + c % p.F_in);
-        int64_t rowF = (int64_t)r0 * p.F + c;
+        RowDesc rd{};
+        const float *dyp = nullptr;
+        int64_t rowF = 0;
 
         auto start_row = [&]() {          // folds dY of `row` into base / gmin / gmax / alpha (times the keep-scale)
-            pos = 0;
+            rd = row_desc(p, row);
+            pos = rd.pos0;
             base = Vec<VEC>{}; gmin = Vec<VEC>{}; gmax = Vec<VEC>{}; alpha = Vec<VEC>{}; pv = Vec<VEC>{}; dp = Vec<VEC>{};
 #pragma unroll
             for (int v = 0; v < VEC; ++v) { amn[v] = -1; amx[v] = -1; }
-            prow = p.row_map ? (int64_t)__ldg(p.row_map + row) : (int64_t)row;
-            if (p.use_rng) rid = (uint32_t)(p.rng_row0 + (p.rng_row ? (int64_t)__ldg(p.rng_row + row) : (int64_t)row));
+            prow = p.row_map ? (int64_t)__ldg(p.row_map + rd.real) : (int64_t)rd.real;
+            if (p.use_rng) rid = (uint32_t)(p.rng_row0 + (p.rng_row ? (int64_t)__ldg(p.rng_row + rd.real) : (int64_t)rd.real));
             if (!live) return;
-            const int deg = row_end - row_beg;
+            dyp = p.dY + (int64_t)rd.real * p.ldy + ycol;
+            rowF = (int64_t)rd.real * p.F + c;
+            // a segment of a split row needs the degree of the whole row
+            const int deg = rd.slot >= 0 ? __ldg(p.rowptr + rd.real + 1) - __ldg(p.rowptr + rd.real) : row_end - row_beg;
             const int degc = deg > 1 ? deg : 1;
             const float degf = (float)degc;
             const float rdeg = 1.0f / degf;
@@ -568,15 +639,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_bwd_stream(const __grid_
             }
         };
         auto finish_row = [&]() {
-            if (p.dP && live) st_vec_stream<VEC>(p.dP + prow * p.lddp + c, dp);
+            if (!live) return;
+            if (rd.slot >= 0) st_vec<VEC>(p.seg_ws + (int64_t)rd.slot * p.F + c, dp);      // partial dP of a segment
+            else if (p.dP) st_vec_stream<VEC>(p.dP + prow * p.lddp + c, dp);
         };
         auto row_next = [&]() {
             finish_row();
             ++row;
-            dyp += p.ldy;
-            rowF += p.F;
             row_beg = row_end;
-            row_end = __ldg(p.rowptr + row + 1);
+            row_end = __ldg(rp + row + 1);
             start_row();
         };
 
@@ -649,6 +720,58 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_bwd_stream(const __grid_
             if (row + 1 >= r1) { finish_row(); break; }
             row_next();
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// split rows: merge the segments' partial states in segment order
+// ---------------------------------------------------------------------------------------------
+// forward: one block per split row, a thread per 4 columns.  split_tab[i] = {real row, first slot, segments, 0}
+template <bool MINMAX, bool SQ>
+__global__ void __launch_bounds__(128) mmconv_fwd_merge(const __grid_constant__ MMConvParams p) {
+    const int4 t = __ldg(reinterpret_cast<const int4 *>(p.split_tab) + blockIdx.x);
+    const int real = t.x, slot0 = t.y, nseg = t.z;
+    const int deg = __ldg(p.rowptr + real + 1) - __ldg(p.rowptr + real);
+    for (int c = p.col0 + threadIdx.x * 4; c < p.col0 + p.ncols; c += blockDim.x * 4) {
+        float sum[4], sq[4], mn[4], mx[4];
+        int amn[4], amx[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) { sum[v] = 0.f; sq[v] = 0.f; mn[v] = FLT_MAX; mx[v] = -FLT_MAX; amn[v] = -1; amx[v] = -1; }
+        for (int k = 0; k < nseg; ++k) {
+            const float *w = p.seg_ws + (int64_t)(slot0 + k) * 6 * p.F + c;
+            const Vec<4> ps = ld_vec<4>(w), pq = ld_vec<4>(w + p.F), pmn = ld_vec<4>(w + 2 * p.F), pmx = ld_vec<4>(w + 3 * p.F);
+            const Vec<4> pan = ld_vec<4>(w + 4 * p.F), pax = ld_vec<4>(w + 5 * p.F);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                sum[v] = __fadd_rn(sum[v], ps.v[v]);
+                sq[v] = __fadd_rn(sq[v], pq.v[v]);
+                const int an = __float_as_int(pan.v[v]), ax = __float_as_int(pax.v[v]);
+                if (an >= 0 && pmn.v[v] < mn[v]) { mn[v] = pmn.v[v]; amn[v] = an; }     // strict: the earlier segment wins ties
+                if (ax >= 0 && pmx.v[v] > mx[v]) { mx[v] = pmx.v[v]; amx[v] = ax; }
+            }
+        }
+        const int ycol = p.T == 1 ? c : (c / p.F_in) * (p.S * p.A * p.F_in) + c % p.F_in;
+        const int64_t rowF = (int64_t)real * p.F + c;
+        emit_row<4, MINMAX, SQ>(p, p.simple_out != 0, deg, sum, sq, mn, mx, amn, amx, p.Y + (int64_t)real * p.ldy + ycol,
+                                p.arg_min ? p.arg_min + rowF : nullptr, p.arg_max ? p.arg_max + rowF : nullptr,
+                                p.stat_mean ? p.stat_mean + rowF : nullptr, p.stat_var ? p.stat_var + rowF : nullptr);
+    }
+}
+
+// backward: dP of a split row = sum of its segments' partial dP, in segment order
+__global__ void __launch_bounds__(128) mmconv_bwd_merge(const __grid_constant__ MMConvParams p) {
+    const int4 t = __ldg(reinterpret_cast<const int4 *>(p.split_tab) + blockIdx.x);
+    const int real = t.x, slot0 = t.y, nseg = t.z;
+    if (!p.dP) return;
+    const int64_t prow = p.row_map ? (int64_t)__ldg(p.row_map + real) : (int64_t)real;
+    for (int c = p.col0 + threadIdx.x * 4; c < p.col0 + p.ncols; c += blockDim.x * 4) {
+        Vec<4> acc{};
+        for (int k = 0; k < nseg; ++k) {
+            const Vec<4> d = ld_vec<4>(p.seg_ws + (int64_t)(slot0 + k) * p.F + c);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc.v[v] += d.v[v];
+        }
+        st_vec_stream<4>(p.dP + prow * p.lddp + c, acc);
     }
 }
 

@@ -57,11 +57,17 @@ def k1_forward(graph: Graph, P, Q, R, keep, *, T: int, F_in: int, akinds, skinds
     dev = graph.device
     ak, sk = _lib.i32_array(akinds), _lib.i32_array(skinds)
     chunks = graph.k1_chunks()
+    seg = graph.k1_segments()
+    seg_ws = (torch.empty((seg.n_slots, 6, T * F_in), dtype=torch.float32, device=dev)
+              if seg is not None and seg.n_slots else None)
     with _lib.kernel_scope("mmconv_aggregate_fwd", dev):
         _lib.check(_lib.lib().mmconv_aggregate_fwd(
             _lib.ptr(graph.rowptr), _lib.ptr(graph.col), _lib.ptr(graph.perm), _lib.ptr(graph.gid), graph.E_total,
             _lib.ptr(graph.row_map), _lib.ptr(graph.rng_row), int(graph.rng_row0), _lib.ptr(chunks),
-            0 if chunks is None else chunks.numel() - 1, graph.n_dst, graph.E,
+            0 if chunks is None else chunks.numel() - 1,
+            None if seg is None else _lib.ptr(seg.vrowptr), 0 if seg is None else seg.n_vrows,
+            None if seg is None else _lib.ptr(seg.seg_tab), None if seg is None else _lib.ptr(seg.split_tab),
+            0 if seg is None else seg.n_split, _lib.ptr(seg_ws), graph.n_dst, graph.E,
             _lib.ptr(P), _ld(P), (_lib.ptr(Q) if q_ptr is None else q_ptr), (_ld(Q) if ldq is None else ldq),
             _lib.ptr(R), _ld(R), _lib.ptr(keep), _ld(keep),
             float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.ptr(seed_dev), T, F_in, len(akinds), ak, len(skinds), sk,
@@ -78,11 +84,17 @@ def k1_backward_dst(graph: Graph, P, Q, R, keep, *, T: int, F_in: int, akinds, s
     dev = graph.device
     ak, sk = _lib.i32_array(akinds), _lib.i32_array(skinds)
     chunks = graph.k1_chunks()
+    seg = graph.k1_segments()
+    seg_ws = (torch.empty((seg.n_slots, T * F_in), dtype=torch.float32, device=dev)
+              if seg is not None and seg.n_slots else None)
     with _lib.kernel_scope("mmconv_aggregate_bwd_dst", dev):
         _lib.check(_lib.lib().mmconv_aggregate_bwd_dst(
             _lib.ptr(graph.rowptr), _lib.ptr(graph.col), _lib.ptr(graph.perm), _lib.ptr(graph.gid), graph.E_total,
             _lib.ptr(graph.row_map), _lib.ptr(graph.rng_row), int(graph.rng_row0), _lib.ptr(chunks),
-            0 if chunks is None else chunks.numel() - 1, graph.n_dst, graph.E,
+            0 if chunks is None else chunks.numel() - 1,
+            None if seg is None else _lib.ptr(seg.vrowptr), 0 if seg is None else seg.n_vrows,
+            None if seg is None else _lib.ptr(seg.seg_tab), None if seg is None else _lib.ptr(seg.split_tab),
+            0 if seg is None else seg.n_split, _lib.ptr(seg_ws), graph.n_dst, graph.E,
             _lib.ptr(P), _ld(P), (_lib.ptr(Q) if q_ptr is None else q_ptr), (_ld(Q) if ldq is None else ldq),
             _lib.ptr(R), _ld(R), _lib.ptr(keep), _ld(keep),
             float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.ptr(seed_dev), T, F_in, len(akinds), ak, len(skinds), sk,

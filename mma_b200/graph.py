@@ -124,16 +124,53 @@ class Graph:
     K1_ROW_COST = 6          # a row costs about this many edges in the K1 kernels (epilogue, per-row loads)
     K1_CHUNKS_PER_WARP = 16
 
+    K1_MAX_SEG = 4096        # rows longer than this are cut into segments of this many edges (multiple of 32)
+
+    def k1_segments(self):
+        """Virtual rows for the persistent K1 kernels (include/mma_b200.h, `vrowptr` / `seg_tab` / `split_tab`):
+        rows longer than K1_MAX_SEG edges are cut into segments walked by different warps.  None when no row
+        is that long (one host sync for the maximum degree, once per graph)."""
+        if "_k1_seg" in self.__dict__:
+            return self.__dict__["_k1_seg"]
+        seg = None
+        L = int(self.K1_MAX_SEG)
+        if L % 32 != 0 or L < 32:
+            raise ValueError("K1_MAX_SEG must be a positive multiple of 32")
+        if self.max_deg > L:
+            dev, n = self.device, self.n_dst
+            rp = self.rowptr.to(torch.int64)
+            deg = rp[1:] - rp[:-1]
+            segs = ((deg + L - 1) // L).clamp_(min=1)
+            first_v = torch.cumsum(segs, 0) - segs
+            vrow_row = torch.repeat_interleave(torch.arange(n, device=dev), segs)
+            n_v = int(vrow_row.numel())
+            pos0 = (torch.arange(n_v, device=dev) - first_v[vrow_row]) * L
+            split = segs[vrow_row] > 1
+            slot = torch.where(split, torch.cumsum(split.to(torch.int64), 0) - 1, torch.full_like(pos0, -1))
+            zeros = torch.zeros_like(pos0)
+            rows_split = torch.nonzero(segs > 1).flatten()
+            seg = type("K1Segments", (), {})()
+            seg.vrowptr = torch.cat([rp[vrow_row] + pos0, rp[-1:]]).to(torch.int32).contiguous()
+            seg.seg_tab = torch.stack([vrow_row, pos0, slot, zeros], 1).to(torch.int32).contiguous()
+            seg.split_tab = torch.stack([rows_split, slot[first_v[rows_split]], segs[rows_split],
+                                         torch.zeros_like(rows_split)], 1).to(torch.int32).contiguous()
+            seg.n_vrows, seg.n_split, seg.n_slots = n_v, int(rows_split.numel()), int(split.sum().item())
+        self.__dict__["_k1_seg"] = seg
+        return seg
+
     def k1_chunks(self) -> Optional[Tensor]:
         """Work partition of the persistent K1 kernels (include/mma_b200.h, `row_chunks`): int32
-        [n_chunks + 1] row boundaries of chunks of about equal cost (edges + K1_ROW_COST per row),
-        K1_CHUNKS_PER_WARP chunks per resident warp, dealt round-robin in the kernel.  Built once per graph."""
+        [n_chunks + 1] boundaries of chunks of (virtual, see k1_segments) rows of about equal cost (edges +
+        K1_ROW_COST per row), K1_CHUNKS_PER_WARP chunks per resident warp, dealt round-robin in the kernel.
+        Built once per graph."""
         ch = self.__dict__.get("_k1_chunks")
         if ch is None:
-            n = self.n_dst
+            seg = self.k1_segments()
+            n = self.n_dst if seg is None else seg.n_vrows
+            rowptr = self.rowptr if seg is None else seg.vrowptr
             sms = torch.cuda.get_device_properties(self.device).multi_processor_count
             n_chunks = max(1, min(sms * 16 * self.K1_CHUNKS_PER_WARP, n // 8))
-            cost = self.rowptr.to(torch.int64) + self.K1_ROW_COST * torch.arange(n + 1, device=self.device)
+            cost = rowptr.to(torch.int64) + self.K1_ROW_COST * torch.arange(n + 1, device=self.device)
             targets = (torch.arange(n_chunks + 1, device=self.device, dtype=torch.int64) * int(cost[-1].item())) // n_chunks
             ch = torch.searchsorted(cost, targets, right=False).clamp_(max=n).to(torch.int32)
             ch[0], ch[-1] = 0, n

@@ -32,7 +32,7 @@ def test_argument_validation_without_gpu():
     assert l.mma_csr_build_workspace_bytes(2**31, 4, ctypes.byref(n)) == _lib.ERR_UNSUPPORTED
     ak = _lib.i32_array([0]); sk = _lib.i32_array([0])
     # all data pointers NULL -> invalid, before any CUDA call
-    rc = l.mmconv_aggregate_fwd(None, None, None, None, 0, None, None, 0, None, 0, 4, 0, None, 0, None, 0, None, 0, None, 0,
+    rc = l.mmconv_aggregate_fwd(None, None, None, None, 0, None, None, 0, None, 0, None, 0, None, None, 0, None, 4, 0, None, 0, None, 0, None, 0, None, 0,
                                 0.0, 0, None, 1, 4, 1, ak, 1, sk, None, 0, None, 0, None, None, None, None, 0, 0, 0, None)
     assert rc == _lib.ERR_INVALID
     assert l.mma_dropout_keep_scale_rows(None, None, None, 0, 4, 4, 0.5, 0, 4, None, 4, None) == _lib.ERR_INVALID
