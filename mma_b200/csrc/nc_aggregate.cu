@@ -38,16 +38,37 @@ struct NcParams {
     int64_t n_groups;
 };
 
-__device__ __forceinline__ bool nc_locate(const NcParams &p, int64_t &row, int &c, int vec) {
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t group = tid >> p.lanes_log2;
-    if (group >= p.n_groups) return false;
-    const int sub = (int)(tid & ((1 << p.lanes_log2) - 1));
-    row = group / p.chunks;
-    const int chunk = (int)(group - row * p.chunks);
-    c = ((chunk << p.lanes_log2) + sub) * vec;
-    return c < p.F;
+// One WARP per (row, chunk of columns).  The L = 2^lanes_log2 lanes that cover the chunk's columns form a
+// sub-group; the 32 / L sub-groups of the warp take the row's neighbours round-robin (sub-group s: neighbours
+// s, s + nsub, ...), and their partial sums are combined by a fixed xor-butterfly at the end -- a fixed
+// summation tree, so results stay bit-reproducible.  These graphs are small and L2 resident: the kernel lasts as
+// long as its longest neighbour list, which this cuts by the number of sub-groups (8x at F = 16).
+struct NcLane { int64_t row; int c, sub, nsub, L; bool live; };
+__device__ __forceinline__ NcLane nc_locate(const NcParams &p, int vec) {
+    NcLane t;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    t.L = 1 << p.lanes_log2;
+    t.nsub = 32 >> p.lanes_log2;
+    t.sub = lane >> p.lanes_log2;
+    const bool real = warp < p.n_groups;
+    t.row = real ? warp / p.chunks : 0;
+    const int chunk = real ? (int)(warp - t.row * p.chunks) : 0;
+    t.c = ((chunk << p.lanes_log2) + (lane & (t.L - 1))) * vec;
+    t.live = real && t.c < p.F;
+    if (!t.live) t.c = 0;               // idle lanes run along on valid addresses; they never store
+    return t;
 }
+template <int VEC>
+__device__ __forceinline__ void nc_combine(Vec<VEC> &a, int L) {      // sum over the warp's sub-groups
+    for (int off = L; off < 32; off <<= 1) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) a.v[v] += __shfl_xor_sync(0xffffffffu, a.v[v], off);
+    }
+}
+
+// neighbours in flight per batch, bounded by the registers the gathered rows need (rows = rows per neighbour)
+__host__ __device__ constexpr int nc_batch(int rows) { return rows <= 2 ? 8 : (rows <= 5 ? 4 : 2); }
 
 __device__ __forceinline__ float sigmoidf(float x) { return 1.0f / (1.0f + expf(-x)); }
 
@@ -66,8 +87,9 @@ __device__ __forceinline__ Vec<VEC> nc_keep(const NcParams &p, int a, int e, int
 // ---------------------------------------------------------------------------- forward
 template <int VEC, int A>
 __global__ void __launch_bounds__(256) nc_fwd_kernel(const __grid_constant__ NcParams p) {
-    int64_t row; int c;
-    if (!nc_locate(p, row, c, VEC)) return;
+    const NcLane t = nc_locate(p, VEC);
+    const int64_t row = t.row;
+    const int c = t.c;
     const int beg = __ldg(p.ptr + row), end = __ldg(p.ptr + row + 1);
     const Vec<VEC> xi = ld_vec<VEC>(p.X + row * p.ldx + c);
     Vec<VEC> pa[A], S[A];
@@ -77,12 +99,10 @@ __global__ void __launch_bounds__(256) nc_fwd_kernel(const __grid_constant__ NcP
 #pragma unroll
         for (int v = 0; v < VEC; ++v) S[a].v[v] = 0.0f;
     }
-    for (int pos = beg; pos < end; ++pos) {
-        const int64_t j = __ldg(p.idx + pos);
-        const Vec<VEC> xj = ld_vec_stream<VEC>(p.X + j * p.ldx + c);
-        Vec<VEC> qa[A];
-#pragma unroll
-        for (int a = 0; a < A; ++a) qa[a] = ld_vec_stream<VEC>(p.QA + j * p.ldqa + a * p.F + c);
+    // The graphs of this path are small and L2 resident: the kernel's duration is the latency chain of its
+    // longest neighbour list.  Neighbours are therefore taken U at a time -- all indices, then all gathered rows
+    // of the batch in flight together -- and consumed in list order (same summation order as before).
+    auto edge = [&](int pos, const Vec<VEC> &xj, const Vec<VEC> (&qa)[A]) {
 #pragma unroll
         for (int a = 0; a < A; ++a) {
             bool has;
@@ -95,7 +115,35 @@ __global__ void __launch_bounds__(256) nc_fwd_kernel(const __grid_constant__ NcP
                 S[a].v[v] = __fadd_rn(S[a].v[v], __fmul_rn(mk, xj.v[v]));
             }
         }
+    };
+    constexpr int U = nc_batch(A);
+    const int st = t.nsub;
+    int pos = beg + t.sub;
+    for (; pos + (U - 1) * st < end; pos += U * st) {
+        int64_t j[U];
+        Vec<VEC> xj[U], qa[U][A];
+#pragma unroll
+        for (int u = 0; u < U; ++u) j[u] = __ldg(p.idx + pos + u * st);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            xj[u] = ld_vec_stream<VEC>(p.X + j[u] * p.ldx + c);
+#pragma unroll
+            for (int a = 0; a < A; ++a) qa[u][a] = ld_vec_stream<VEC>(p.QA + j[u] * p.ldqa + a * p.F + c);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) edge(pos + u * st, xj[u], qa[u]);
     }
+    for (; pos < end; pos += st) {
+        const int64_t j = __ldg(p.idx + pos);
+        const Vec<VEC> xj = ld_vec_stream<VEC>(p.X + j * p.ldx + c);
+        Vec<VEC> qa[A];
+#pragma unroll
+        for (int a = 0; a < A; ++a) qa[a] = ld_vec_stream<VEC>(p.QA + j * p.ldqa + a * p.F + c);
+        edge(pos, xj, qa);
+    }
+#pragma unroll
+    for (int a = 0; a < A; ++a) nc_combine<VEC>(S[a], t.L);
+    if (!t.live || t.sub != 0) return;
     const float D = (float)(end - beg);     // len(add_all[i]); D = 0 divides by zero like the reference (Q9)
 #pragma unroll
     for (int a = 0; a < A; ++a) {
@@ -121,8 +169,10 @@ __global__ void __launch_bounds__(256) nc_fwd_kernel(const __grid_constant__ NcP
 // ---------------------------------------------------------------------------- backward, dst pass
 template <int VEC, int A>
 __global__ void __launch_bounds__(256) nc_bwd_dst_kernel(const __grid_constant__ NcParams p) {
-    int64_t row; int c;
-    if (!nc_locate(p, row, c, VEC)) return;
+    const NcLane t = nc_locate(p, VEC);
+    const int64_t row = t.row;
+    const int c = t.c;
+    const bool writer = t.live && t.sub == 0;
     const int beg = __ldg(p.ptr + row), end = __ldg(p.ptr + row + 1);
     const float D = (float)(end - beg);
     const Vec<VEC> xi = ld_vec<VEC>(p.X + row * p.ldx + c);
@@ -153,15 +203,10 @@ __global__ void __launch_bounds__(256) nc_bwd_dst_kernel(const __grid_constant__
             dx.v[v] += gx;
             dpa[a].v[v] = 0.0f;
         }
-        st_vec<VEC>(p.gS_w + row * ((int64_t)A * p.F) + a * p.F + c, gS[a]);
+        if (writer) st_vec<VEC>(p.gS_w + row * ((int64_t)A * p.F) + a * p.F + c, gS[a]);
     }
-    st_vec<VEC>(p.dXdir + row * p.lddx + c, dx);
-    for (int pos = beg; pos < end; ++pos) {
-        const int64_t j = __ldg(p.idx + pos);
-        const Vec<VEC> xj = ld_vec_stream<VEC>(p.X + j * p.ldx + c);
-        Vec<VEC> qa[A];
-#pragma unroll
-        for (int a = 0; a < A; ++a) qa[a] = ld_vec_stream<VEC>(p.QA + j * p.ldqa + a * p.F + c);
+    if (writer) st_vec<VEC>(p.dXdir + row * p.lddx + c, dx);
+    auto edge = [&](int pos, const Vec<VEC> &xj, const Vec<VEC> (&qa)[A]) {
 #pragma unroll
         for (int a = 0; a < A; ++a) {
             bool has;
@@ -174,7 +219,35 @@ __global__ void __launch_bounds__(256) nc_bwd_dst_kernel(const __grid_constant__
                 dpa[a].v[v] += d;
             }
         }
+    };
+    constexpr int U = nc_batch(A);
+    const int st = t.nsub;
+    int pos = beg + t.sub;
+    for (; pos + (U - 1) * st < end; pos += U * st) {
+        int64_t j[U];
+        Vec<VEC> xj[U], qa[U][A];
+#pragma unroll
+        for (int u = 0; u < U; ++u) j[u] = __ldg(p.idx + pos + u * st);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            xj[u] = ld_vec_stream<VEC>(p.X + j[u] * p.ldx + c);
+#pragma unroll
+            for (int a = 0; a < A; ++a) qa[u][a] = ld_vec_stream<VEC>(p.QA + j[u] * p.ldqa + a * p.F + c);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) edge(pos + u * st, xj[u], qa[u]);
     }
+    for (; pos < end; pos += st) {
+        const int64_t j = __ldg(p.idx + pos);
+        const Vec<VEC> xj = ld_vec_stream<VEC>(p.X + j * p.ldx + c);
+        Vec<VEC> qa[A];
+#pragma unroll
+        for (int a = 0; a < A; ++a) qa[a] = ld_vec_stream<VEC>(p.QA + j * p.ldqa + a * p.F + c);
+        edge(pos, xj, qa);
+    }
+#pragma unroll
+    for (int a = 0; a < A; ++a) nc_combine<VEC>(dpa[a], t.L);
+    if (!writer) return;
 #pragma unroll
     for (int a = 0; a < A; ++a) st_vec<VEC>(p.dPA + row * p.lddpa + a * p.F + c, dpa[a]);
 }
@@ -182,8 +255,9 @@ __global__ void __launch_bounds__(256) nc_bwd_dst_kernel(const __grid_constant__
 // ---------------------------------------------------------------------------- backward, src pass
 template <int VEC, int A>
 __global__ void __launch_bounds__(256) nc_bwd_src_kernel(const __grid_constant__ NcParams p) {
-    int64_t j; int c;
-    if (!nc_locate(p, j, c, VEC)) return;
+    const NcLane t = nc_locate(p, VEC);
+    const int64_t j = t.row;
+    const int c = t.c;
     const int beg = __ldg(p.ptr + j), end = __ldg(p.ptr + j + 1);
     const Vec<VEC> xj = ld_vec<VEC>(p.X + j * p.ldx + c);
     Vec<VEC> qa[A], dqa[A], dx{};
@@ -193,15 +267,7 @@ __global__ void __launch_bounds__(256) nc_bwd_src_kernel(const __grid_constant__
 #pragma unroll
         for (int v = 0; v < VEC; ++v) dqa[a].v[v] = 0.0f;
     }
-    for (int k = beg; k < end; ++k) {
-        const int64_t i = __ldg(p.idx + k);
-        const int e = __ldg(p.eid + k);
-        Vec<VEC> pa[A], gs[A];
-#pragma unroll
-        for (int a = 0; a < A; ++a) {
-            pa[a] = ld_vec_stream<VEC>(p.PA + i * p.ldpa + a * p.F + c);
-            gs[a] = ld_vec_stream<VEC>(p.gS_r + i * ((int64_t)A * p.F) + a * p.F + c);
-        }
+    auto edge = [&](int e, const Vec<VEC> (&pa)[A], const Vec<VEC> (&gs)[A]) {
 #pragma unroll
         for (int a = 0; a < A; ++a) {
             bool has;
@@ -218,7 +284,42 @@ __global__ void __launch_bounds__(256) nc_bwd_src_kernel(const __grid_constant__
                 dqa[a].v[v] += d;
             }
         }
+    };
+    constexpr int U = nc_batch(2 * A);
+    const int st = t.nsub;
+    int k = beg + t.sub;
+    for (; k + (U - 1) * st < end; k += U * st) {
+        int64_t i[U];
+        int e[U];
+        Vec<VEC> pa[U][A], gs[U][A];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { i[u] = __ldg(p.idx + k + u * st); e[u] = __ldg(p.eid + k + u * st); }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+            for (int a = 0; a < A; ++a) {
+                pa[u][a] = ld_vec_stream<VEC>(p.PA + i[u] * p.ldpa + a * p.F + c);
+                gs[u][a] = ld_vec_stream<VEC>(p.gS_r + i[u] * ((int64_t)A * p.F) + a * p.F + c);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) edge(e[u], pa[u], gs[u]);
     }
+    for (; k < end; k += st) {
+        const int64_t i = __ldg(p.idx + k);
+        const int e = __ldg(p.eid + k);
+        Vec<VEC> pa[A], gs[A];
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            pa[a] = ld_vec_stream<VEC>(p.PA + i * p.ldpa + a * p.F + c);
+            gs[a] = ld_vec_stream<VEC>(p.gS_r + i * ((int64_t)A * p.F) + a * p.F + c);
+        }
+        edge(e, pa, gs);
+    }
+#pragma unroll
+    for (int a = 0; a < A; ++a) nc_combine<VEC>(dqa[a], t.L);
+    nc_combine<VEC>(dx, t.L);
+    if (!t.live || t.sub != 0) return;
 #pragma unroll
     for (int a = 0; a < A; ++a) st_vec<VEC>(p.dQA + j * p.lddqa + a * p.F + c, dqa[a]);
     st_vec<VEC>(p.dXnbr + j * p.lddx + c, dx);
@@ -264,7 +365,7 @@ static inline bool ok4(const void *ptr, int64_t ld) { return ptr == nullptr || (
 #define NC_DISPATCH(KERNEL)                                                              \
     do {                                                                                 \
         const int block = 256;                                                           \
-        const int64_t grid = ((p.n_groups << p.lanes_log2) + block - 1) / block;         \
+        const int64_t grid = (p.n_groups * 32 + block - 1) / block;  /* one warp per group */ \
         if (grid > INT32_MAX) return MMA_ERR_UNSUPPORTED;                                \
         cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);                        \
         switch (vec * 16 + p.A) {                                                        \
