@@ -478,29 +478,46 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_con
                 const int valid = x.row_end - r;            // rows of this block inside the slab (>= 32: all)
                 mbar_wait(full_bar(s), (it / WG_NR) & 1u);
                 mbar_wait(lo_empty(sl), ((it / WG_NL) & 1u) ^ 1u);
+                if (p.mode == 1 && valid >= BK) {
+                    // the common case, kept lean (the converter warps set the pace of this kernel): a full block of
+                    // 32 rows, raw operand as hi (the tensor core ignores the low 13 mantissa bits), lo = x - trunc(x)
 #pragma unroll
-                for (int op = 0; op < 2; ++op) {
-                    float4 *a = reinterpret_cast<float4 *>(smem + s * RAW_BYTES + op * A_BYTES);
-                    float4 *alo = reinterpret_cast<float4 *>(smem + (lo_base - smem_base) + sl * RAW_BYTES + op * A_BYTES);
-                    float4 v[8];
+                    for (int op = 0; op < 2; ++op) {
+                        const float4 *a = reinterpret_cast<const float4 *>(smem + s * RAW_BYTES + op * A_BYTES);
+                        float4 *alo = reinterpret_cast<float4 *>(smem + (lo_base - smem_base) + sl * RAW_BYTES + op * A_BYTES);
+                        float4 v[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int idx = i * 128 + ct;       // 16-byte chunk; box g = idx/256, row = (idx/8) % 32
-                        v[i] = a[idx];
-                        if (((idx >> 3) & 31) >= valid) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int i = 0; i < 8; ++i) v[i] = a[i * 128 + ct];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            alo[i * 128 + ct] = make_float4(v[i].x - tf32_hi(v[i].x), v[i].y - tf32_hi(v[i].y),
+                                                            v[i].z - tf32_hi(v[i].z), v[i].w - tf32_hi(v[i].w));
                     }
+                } else {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int idx = i * 128 + ct;
-                        if (p.mode == 0) {
-                            const float4 h = make_float4(tf32_rna(v[i].x), tf32_rna(v[i].y), tf32_rna(v[i].z), tf32_rna(v[i].w));
-                            alo[idx] = make_float4(tf32_rna(v[i].x - h.x), tf32_rna(v[i].y - h.y), tf32_rna(v[i].z - h.z),
-                                                   tf32_rna(v[i].w - h.w));
-                            a[idx] = h;
-                        } else {
-                            const float4 h = make_float4(tf32_hi(v[i].x), tf32_hi(v[i].y), tf32_hi(v[i].z), tf32_hi(v[i].w));
-                            if (p.mode != 2) alo[idx] = make_float4(v[i].x - h.x, v[i].y - h.y, v[i].z - h.z, v[i].w - h.w);
-                            if (valid < BK) a[idx] = h;
+                    for (int op = 0; op < 2; ++op) {
+                        float4 *a = reinterpret_cast<float4 *>(smem + s * RAW_BYTES + op * A_BYTES);
+                        float4 *alo = reinterpret_cast<float4 *>(smem + (lo_base - smem_base) + sl * RAW_BYTES + op * A_BYTES);
+                        float4 v[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int idx = i * 128 + ct;       // 16-byte chunk; box g = idx/256, row = (idx/8) % 32
+                            v[i] = a[idx];
+                            if (((idx >> 3) & 31) >= valid) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int idx = i * 128 + ct;
+                            if (p.mode == 0) {
+                                const float4 h = make_float4(tf32_rna(v[i].x), tf32_rna(v[i].y), tf32_rna(v[i].z), tf32_rna(v[i].w));
+                                alo[idx] = make_float4(tf32_rna(v[i].x - h.x), tf32_rna(v[i].y - h.y), tf32_rna(v[i].z - h.z),
+                                                       tf32_rna(v[i].w - h.w));
+                                a[idx] = h;
+                            } else {
+                                const float4 h = make_float4(tf32_hi(v[i].x), tf32_hi(v[i].y), tf32_hi(v[i].z), tf32_hi(v[i].w));
+                                if (p.mode != 2) alo[idx] = make_float4(v[i].x - h.x, v[i].y - h.y, v[i].z - h.z, v[i].w - h.w);
+                                if (valid < BK) a[idx] = h;
+                            }
                         }
                     }
                 }
