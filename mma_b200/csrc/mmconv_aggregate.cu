@@ -545,6 +545,9 @@ __device__ __forceinline__ float fast_message(float pvv, float q, float r, float
 #define MMA_ACC_HEAD "{\n\t.reg .pred kb, kp, ok, lt, gt;\n\t.reg .f32 xx, xm;\n\tsetp.ne.b32 kb, %7, 0;\n\t"
 #define MMA_ACC_CHK "setp.ne.b32 ok, %8, 0;\n\tand.pred kp, kb, ok;\n\t"
 #define MMA_ACC_SUM(KP) "@" KP " add.rn.f32 %0, %0, %6;\n\t"
+// x*x is rounded BEFORE it is added, like the reference's scatter(inputs * inputs): var = E[x^2] - E[x]^2 cancels
+// to ~0 on rows of (nearly) equal messages and std = sqrt(relu(var) + 1e-5) magnifies a 1-ulp difference in the sum
+// of squares by ~10^2 there -- an FFMA here (tried) breaks the 1e-5 bar on std and its gradient.
 #define MMA_ACC_SQ(KP) "mul.rn.f32 xx, %6, %6;\n\t@" KP " add.rn.f32 %1, %1, xx;\n\t"
 #define MMA_ACC_XM_DROP "and.b32 xm, %6, 0x80000000;\n\tselp.f32 xm, %6, xm, kb;\n\t"
 #define MMA_ACC_XM_NODROP "mov.f32 xm, %6;\n\t"
