@@ -153,19 +153,34 @@ class _FusedMMAConv(torch.autograd.Function):
         W1hi, W1lo = tg.split_weight(W1)
         PQX = tg.linear(x, W1hi, W1lo, 2 * F + Co, bias=b1, name="gemm_mask_proj")                  # [n, 2F+Co], node order
         P, Q, XW = PQX[:, :F], PQX[:, F:2 * F], PQX[:, 2 * F:]
+        gathered = None
         if sg is not None:
-            # the one exchange of the forward: every rank's Q rows (the halo of a random graph is ~all of
-            # Q), rank-major padded layout that the shard's source indices already address
-            from .parallel import all_gather_rows
-            Q = all_gather_rows(Q.contiguous(), sg.max_rows, sg.group)
+            # the one exchange of the forward: every rank's Q rows (the halo of a random graph is ~all of Q),
+            # rank-major padded layout that the shard's source indices already address.  It runs on the
+            # communication stream under the weight-space algebra below (tiny kernels, no SM pressure).
+            from .parallel import all_gather_rows, _comm_stream
+            comm, cur = _comm_stream(dev), torch.cuda.current_stream(dev)
+            Qc = Q.contiguous()
+            comm.wait_stream(cur)
+            with torch.cuda.stream(comm):
+                Qg = all_gather_rows(Qc, sg.max_rows, sg.group)
+                done = torch.cuda.Event(); done.record(comm)
+            Qc.record_stream(comm)
+            gathered = (Qg, done)
+        # composed weight of every degree range: W_c(d) = W_lin W_eff(d) = sum_s c_s(d) (W_lin W_s): S small products,
+        # then a weighted sum over the ranges (no [B, F_out, K] batched product)
+        WlWy = torch.matmul(Wl, Wy.view(Fo, S, K).permute(1, 0, 2))                                 # [S, Co, K]
+        Wc = hi = lo = None
+        if plan.big:
+            Wc = torch.einsum("sb,sck->bck", plan.cum_big, WlWy).contiguous()                       # [B, Co, K]
+            hi, lo = tg.split_weight(Wc.view(-1, K))
+        if gathered is not None:
+            Q, done = gathered
+            torch.cuda.current_stream(dev).wait_event(done)
+            Q.record_stream(torch.cuda.current_stream(dev))
         Z, arg_min, arg_max, mean, var = _k1_fwd(graph, P, Q, R, keep, F, akinds, p_drop, seed, seed_dev)   # sorted rows
         out = torch.empty((n, Co), dtype=torch.float32, device=dev)
-        Ws = Wy.view(Fo, S, K)
-        Weff = Wc = None
         if plan.big:
-            Weff = torch.einsum("sb,osk->bok", plan.cum_big, Ws).contiguous()                       # [B, Fo, K]
-            Wc = torch.matmul(Wl, Weff).contiguous()                                                # [B, Co, K]
-            hi, lo = tg.split_weight(Wc.view(-1, K))
             tg.linear(Z, hi, lo, Co, tile_tab=plan.tile_tab, out=out, out_map=graph.row_map, add=XW,
                       name="gemm_post_grouped")                                                     # rows -> node order
         if plan.tail_idx is not None:
@@ -179,13 +194,13 @@ class _FusedMMAConv(torch.autograd.Function):
         ctx.has_R, ctx.has_b = R is not None, (bm is not None, bp is not None, bl is not None)
         need_sq = 4 in akinds or 5 in akinds
         Qsave = Q if (sg is not None and need_sq) else None       # gathered Q, kept so the backward does not re-gather
-        ctx.save_for_backward(x, PQX, Z, Wm, Wp, bp, Wl, Weff, Wc, R, keep, arg_min, arg_max, mean, var, Qsave,
+        ctx.save_for_backward(x, PQX, Z, Wm, Wp, bp, Wl, Wc, R, keep, arg_min, arg_max, mean, var, Qsave,
                               seed_dev)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
-        (x, PQX, Z, Wm, Wp, bp, Wl, Weff, Wc, R, keep, arg_min, arg_max, mean, var, Qsave,
+        (x, PQX, Z, Wm, Wp, bp, Wl, Wc, R, keep, arg_min, arg_max, mean, var, Qsave,
          seed_dev) = ctx.saved_tensors
         graph, sg, plan = ctx.graph, ctx.sg, ctx.plan
         F, akinds, p_drop, seed, _ = ctx.cfg
@@ -244,9 +259,11 @@ class _FusedMMAConv(torch.autograd.Function):
         if plan.big:
             part = tg.wgrad_partials(dO, Z, plan.slabs, plan.slabs.shape[0], name="gemm_post_wgrad")
             dWc = tg.reduce_slabs_segmented(part, plan.seg_ptr)                                     # [B, Co, K]
-            dWl = dWl + torch.einsum("bck,bok->co", dWc, Weff)
-            dWeff = torch.matmul(Wl.t(), dWc)                                                       # [B, Fo, K]
-            dWy = torch.einsum("sb,bok->osk", plan.cum_big, dWeff).reshape(Fo, S * K)
+            # W_c(d) = sum_s c_s(d) W_lin W_s  ->  D_s = sum_d c_s(d) dW_c(d);  dW_lin += sum_s D_s W_s^T,  dW_s = W_lin^T D_s
+            D = torch.einsum("sb,bck->sck", plan.cum_big, dWc)                                      # [S, Co, K]
+            Ws = Wy.view(Fo, S, K).permute(1, 0, 2)                                                 # [S, Fo, K]
+            dWl = dWl + torch.matmul(D, Ws.transpose(1, 2)).sum(0)
+            dWy = torch.matmul(Wl.t(), D).permute(1, 0, 2).reshape(Fo, S * K)
         if plan.tail_idx is not None:
             ti = plan.tail_idx
             Zt = Z.index_select(0, ti)
