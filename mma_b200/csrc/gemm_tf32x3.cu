@@ -12,14 +12,16 @@
 // call; activations are split INSIDE the kernel by a converter warpgroup working on the TMA-filled
 // shared-memory tile, so no extra pass over HBM is needed.
 //
-// One persistent CTA per SM, 320 threads, warp-specialised:
-//   warp 0      TMA producer     A tile [128 x 32] fp32 (+ pre-split B_hi/B_lo tiles [128 x 32]) per stage
-//   warp 1      MMA issuer       one thread issues 12 tcgen05.mma.kind::tf32 (M=128,N=128,K=8) per stage
-//   warps 2-5   converter        A -> (A_hi in place, A_lo) in shared memory, fence.proxy.async
-//   warps 6-9   epilogue         TMEM -> registers -> swizzled smem transpose -> coalesced global stores
-//                                with optional bias, row-indexed addend and output-row scatter
-// Pipelines: smem full/conv/empty (3 stages) and TMEM full/empty (2 accumulators of 128 columns),
-// so the epilogue of tile i overlaps the main loop of tile i+1.
+// One persistent CTA per SM, warp-specialised (linear: 352 threads; wgrad: 320):
+//   warp 0      TMA producer     raw activation tiles [128 x 32] fp32 (from HBM) into a deep ring
+//   warp 10     TMA producer     (linear only) pre-split weight tiles B_hi/B_lo [128 x 32] (from L2), shallow ring
+//   warp 1      MMA issuer       one thread issues 12 tcgen05.mma.kind::tf32 (M=128,N=128,K=8) per 32-wide K block
+//   warps 2-5   converter        A -> A_lo tile (and, in mode 0, the rounded hi in place), fence.proxy.async
+//   warps 6-9   epilogue         TMEM -> registers -> 256-bit global stores (a thread owns one row of the tile:
+//                                32 consecutive columns = one full 128-byte line), with optional bias,
+//                                row-indexed addend and output-row scatter
+// Pipelines: raw / lo / weight rings with full+empty mbarriers each, and TMEM full/empty (2 accumulators of
+// 128 + 128 columns), so the epilogue of tile i overlaps the main loop of tile i+1.
 #include "common.cuh"
 #include "tc_common.cuh"
 

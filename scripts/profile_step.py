@@ -46,16 +46,34 @@ def step():
     return g
 
 
-for _ in range(3):
-    step()
+use_graph = "--graph" in sys.argv
+conv.device_seed = use_graph
+side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(side):
+    for _ in range(3):
+        step()
+torch.cuda.current_stream().wait_stream(side)
+torch.cuda.synchronize()
+run = step
+if use_graph:
+    cg = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(cg):
+        step()
+    run = cg.replay
+    for _ in range(3):
+        run()
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for _ in range(3):
-        step()
+        run()
     torch.cuda.synchronize()
 if rank == 0:
     print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=32, max_name_column_width=60))
 if world > 1:
-    dist.destroy_process_group()
+    torch.cuda.synchronize(); dist.barrier()
+    if use_graph:
+        cg.reset()
+    sys.stdout.flush()
+    os._exit(0)
