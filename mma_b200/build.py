@@ -3,6 +3,7 @@ from __future__ import annotations
 
 import os
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
@@ -26,9 +27,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
-          [os.path.join(CSRC, s) for s in SOURCES]
-    subprocess.check_call(cmd)
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_one(src: str) -> str:
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        subprocess.check_call([nvcc] + flags + ["-c", os.path.join(CSRC, src), "-o", obj])
+        return obj
+
+    # one nvcc per translation unit, side by side (the two big ones dominate: ~1 min instead of ~2.5)
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+        objs = list(pool.map(compile_one, SOURCES))
+    subprocess.check_call([nvcc, "-shared", "-Xcompiler", "-fPIC", "-o", LIB] + objs)
     return LIB
 
 
