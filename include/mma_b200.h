@@ -192,7 +192,7 @@ int mma_segment_sum_rows(const int32_t *ptr, const int32_t *idx, const float *va
 
 /* Row gather with fused column sums (the row permutation x[node_perm] of the degree-sorted layer
  * interior and the bias gradient sum_r dOut[r] in one pass):
- *   out[r, :] = src[idx[r], :]   r < n_out (idx NULL = identity), F % 4 == 0;
+ *   out[r, :] = src[idx[r], :]   r < n_out (idx NULL = identity), F % 4 == 0; out NULL = column sums only;
  *   colsum_part [n_parts, F] (optional): part p holds the column sums of rows [p*per, (p+1)*per),
  *   per = ceil(n_out / n_parts); reduce them in order with mma_reduce_slabs (no atomics). */
 int mma_gather_rows(const float *src, int64_t lds, const int32_t *idx, int64_t n_out, int F,

@@ -84,14 +84,14 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float *__restric
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                __stcs(reinterpret_cast<float4 *>(out + (r + u) * ldo + c), v[u]);
+                if (out) __stcs(reinterpret_cast<float4 *>(out + (r + u) * ldo + c), v[u]);
                 acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
             }
         }
         for (; r < r1; ++r) {
             const int64_t j = idx ? (int64_t)__ldg(idx + r) : r;
             const float4 v = __ldcs(reinterpret_cast<const float4 *>(src + j * lds + c));
-            __stcs(reinterpret_cast<float4 *>(out + r * ldo + c), v);
+            if (out) __stcs(reinterpret_cast<float4 *>(out + r * ldo + c), v);
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
         if (colsum_part) *reinterpret_cast<float4 *>(colsum_part + part * F + c) = acc;
@@ -104,8 +104,8 @@ using namespace mma;
 
 extern "C" int mma_gather_rows(const float *src, int64_t lds, const int32_t *idx, int64_t n_out, int F,
                                float *out, int64_t ldo, float *colsum_part, int64_t n_parts, mma_stream_t stream) {
-    if (!src || !out || n_out < 0 || F < 1 || n_parts < 1) return MMA_ERR_INVALID;
-    if ((F % 4) != 0 || (lds % 4) != 0 || (ldo % 4) != 0 || !aligned16(src) || !aligned16(out) || !aligned16(colsum_part))
+    if (!src || (!out && !colsum_part) || n_out < 0 || F < 1 || n_parts < 1) return MMA_ERR_INVALID;
+    if ((F % 4) != 0 || (lds % 4) != 0 || (out && (ldo % 4) != 0) || !aligned16(src) || !aligned16(out) || !aligned16(colsum_part))
         return MMA_ERR_UNSUPPORTED;
     if (n_parts * 32 > (int64_t)INT32_MAX * 256) return MMA_ERR_UNSUPPORTED;
     const int64_t threads = n_parts * 32;

@@ -4,7 +4,7 @@ GPU next to the oracle port of the reference on this box's host cores.  Run on a
 Topologies come from tests/golden/planetoid_topology.pt (the real Cora / Pubmed graphs); features and weights are
 synthetic."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import mma_b200
 from mma_b200.node_classification.layers import MMA
