@@ -39,7 +39,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     # one nvcc per translation unit, side by side (the two big ones dominate: ~1 min instead of ~2.5)
     with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
         objs = list(pool.map(compile_one, SOURCES))
-    subprocess.check_call([nvcc, "-shared", "-Xcompiler", "-fPIC", "-o", LIB] + objs)
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", LIB] + objs)
     return LIB
 
 

@@ -296,7 +296,7 @@ class _FusedMMAConv(torch.autograd.Function):
         dWl = dWl + dWcx @ Wx.t()
         dWp = torch.cat([Wl.t() @ dWcx, dWy if dWy is not None else torch.zeros_like(Wy)], dim=1)
         has_bm, has_bp, has_bl = ctx.has_b
-        dbm = dPQ[:, :F].sum(0) if has_bm else None
+        dbm = (tg.colsum(dPQ[:, :F]) if F % 4 == 0 else dPQ[:, :F].sum(0)) if has_bm else None
         dbp = dbc @ Wl if has_bp else None
         return dx, dWm, dbm, dWp, dbp, dWl, (dbc if has_bl else None), dR, None, None, None, None
 

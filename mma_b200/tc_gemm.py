@@ -171,3 +171,18 @@ def gather_rows_colsum(src: Tensor, idx32: Tensor) -> Tuple[Tensor, Tensor]:
         _lib.check(_lib.lib().mma_gather_rows(_lib.ptr(src), src.stride(0), _lib.ptr(idx32), n, F, _lib.ptr(out), F,
                                               _lib.ptr(part), parts, _lib.stream_ptr(dev)), "mma_gather_rows")
     return out, reduce_slabs(part)
+
+
+def colsum(src: Tensor) -> Tensor:
+    """src.sum(0) of a (possibly strided) fp32 [n, F] view in one streaming pass: per-part partial sums
+    (mma_gather_rows with out = NULL) + fixed-order mma_reduce_slabs -- deterministic, no atomics."""
+    dev = _lib.require_cuda(src)
+    n, F = src.shape
+    if src.dtype != torch.float32 or src.stride(1) != 1 or F % 4 != 0 or src.stride(0) % 4 != 0 or src.data_ptr() % 16:
+        raise RuntimeError("colsum: src must be fp32 with unit column stride, 16-byte aligned rows, F % 4 == 0")
+    parts = max(1, min(GATHER_PARTS, (n + 63) // 64))
+    part = torch.empty((parts, F), dtype=torch.float32, device=dev)
+    with _lib.kernel_scope("mma_gather_rows", dev):
+        _lib.check(_lib.lib().mma_gather_rows(_lib.ptr(src), src.stride(0), None, n, F, None, 0,
+                                              _lib.ptr(part), parts, _lib.stream_ptr(dev)), "mma_gather_rows")
+    return reduce_slabs(part)
