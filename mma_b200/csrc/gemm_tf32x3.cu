@@ -22,6 +22,7 @@
 //                                row-indexed addend and output-row scatter
 // Pipelines: raw / lo / weight rings with full+empty mbarriers each, and TMEM full/empty (2 accumulators of
 // 128 + 128 columns), so the epilogue of tile i overlaps the main loop of tile i+1.
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -322,6 +323,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_kernel(const __grid_con
             const Tile tl = locate_tile(p, t);
             const uint32_t buf = ti & 1u;
             mbar_wait(tfull_bar(buf), (ti >> 1) & 1u);
+            __syncwarp();            // reconverge before the .sync.aligned tcgen05.ld
             tc_fence_after();
             const int n_chunks = min(4, (p.N - tl.n0 + 31) / 32);
             for (int c = 0; c < n_chunks; ++c) {
@@ -334,6 +336,221 @@ __global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_kernel(const __grid_con
                 }
                 store_chunk(stg, r, lane, tl.row0 + wq * 32, tl.row_end, tl.n0 + c * 32, p.N, p.C, p.ldc, p.out_map,
                             p.bias, p.add, p.ldadd, p.add_in);
+                __syncwarp();
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------
+// Short-K variant (K <= 128, many output columns): the activation tile stays RESIDENT IN TENSOR MEMORY.
+//
+// The kernel above is bound by shared-memory bandwidth: per 32-wide K block it moves 16 KB (TMA write) +
+// 32 KB (converter) + 96 KB (three MMAs reading A and B) through shared memory, and it does so again for every
+// 128-column output tile of the same rows.  For the two GEMMs with K = 128 and 384 / 640 output columns (the
+// mask projection and the dgrad of the post transform) this variant
+//   * converts a [128 x K] activation tile ONCE per row block: TMA -> shared memory -> registers (a thread owns
+//     a row) -> hi / lo written with tcgen05.st into tensor-memory columns [0,128) / [128,256);
+//   * issues the MMAs with the A operand read FROM TENSOR MEMORY (tcgen05.mma [d], [a], b_desc): only the
+//     weight tiles cross shared memory;
+//   * walks the output columns in 64-wide sub-tiles that all reuse the resident A; two accumulator pairs
+//     (main + correction, 64 + 64 columns each) at columns [256,512), one per epilogue warpgroup, so the
+//     epilogue of sub-tile j overlaps the MMAs of sub-tile j + 1.
+// The K-block slots of A are released one by one while the LAST sub-tile of a row block is being issued, so
+// the converter refills them for the next row block under the tail of the current one.
+//   warp 0 TMA (activations) | warp 1 MMA issuer | warps 2-5 converter | warps 6-9, 10-13 epilogue | warp 14 TMA (weights)
+// ------------------------------------------------------------------------------------------
+constexpr int AR_BN = 64;                                  // output columns per sub-tile
+constexpr int AR_B_BYTES = AR_BN * BK * 4;                 // 8 KB per half (hi or lo)
+constexpr int AR_NA = 4, AR_NB = 8, AR_MAX_KB = 4;
+constexpr int AR_BAR_BYTES = 512;
+constexpr int AR_SMEM_BYTES = AR_NA * A_BYTES + AR_NB * 2 * AR_B_BYTES + AR_BAR_BYTES + 1024;
+constexpr int AR_THREADS = 480;
+static_assert(AR_SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory per CTA");
+
+__global__ void __launch_bounds__(AR_THREADS, 1) gemm_nt_ares_kernel(const __grid_constant__ NtParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t b_base = smem_base + AR_NA * A_BYTES;
+    const uint32_t bar_base = b_base + AR_NB * 2 * AR_B_BYTES;
+    auto a_full = [&](int i) { return bar_base + 8u * i; };
+    auto a_empty = [&](int i) { return bar_base + 8u * (AR_NA + i); };
+    auto atm_full = [&](int i) { return bar_base + 8u * (2 * AR_NA + i); };
+    auto atm_empty = [&](int i) { return bar_base + 8u * (2 * AR_NA + AR_MAX_KB + i); };
+    auto b_full = [&](int i) { return bar_base + 8u * (2 * AR_NA + 2 * AR_MAX_KB + i); };
+    auto b_empty = [&](int i) { return bar_base + 8u * (2 * AR_NA + 2 * AR_MAX_KB + AR_NB + i); };
+    constexpr int kTBar = 2 * AR_NA + 2 * AR_MAX_KB + 2 * AR_NB;
+    auto tfull_bar = [&](int b) { return bar_base + 8u * (kTBar + b); };
+    auto tempty_bar = [&](int b) { return bar_base + 8u * (kTBar + 2 + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (kTBar + 4);
+    static_assert(8 * (kTBar + 4) + 4 <= AR_BAR_BYTES, "barrier block too small");
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem + (tmem_slot - smem_base));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_kb = p.num_kb;                            // <= AR_MAX_KB
+    const int n_sub = (p.N + AR_BN - 1) / AR_BN;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.map_a0); tma_prefetch_desc(&p.map_bhi); tma_prefetch_desc(&p.map_blo);
+        for (int i = 0; i < AR_NA; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 4); }
+        for (int i = 0; i < AR_MAX_KB; ++i) { mbar_init(atm_full(i), 4); mbar_init(atm_empty(i), 1); }
+        for (int i = 0; i < AR_NB; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    constexpr uint32_t A_HI_COL = 0, A_LO_COL = 128, ACC_COL = 256;     // acc buffer b: main at ACC_COL + 128 b, corr + 64
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer: activations (HBM)
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t t = blockIdx.x; t < p.n_tiles_m; t += gridDim.x) {
+                const Tile tl = locate_tile(p, t * p.n_tiles_n);
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int sa = it % AR_NA;
+                    mbar_wait(a_empty(sa), ((it / AR_NA) & 1u) ^ 1u);
+                    mbar_expect_tx(a_full(sa), A_BYTES);
+                    tma_load_2d(smem_base + sa * A_BYTES, &p.map_a0, a_full(sa), kb * BK, (int)tl.row0);
+                }
+            }
+        }
+    } else if (warp == 14) {
+        // ===================================================================== TMA producer: weights (L2)
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t t = blockIdx.x; t < p.n_tiles_m; t += gridDim.x) {
+                const Tile tl = locate_tile(p, t * p.n_tiles_n);
+                for (int j = 0; j < n_sub; ++j) {
+                    for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                        const int sb = it % AR_NB;
+                        mbar_wait(b_empty(sb), ((it / AR_NB) & 1u) ^ 1u);
+                        const uint32_t dst = b_base + sb * 2 * AR_B_BYTES;
+                        mbar_expect_tx(b_full(sb), 2 * AR_B_BYTES);
+                        tma_load_2d(dst, &p.map_bhi, b_full(sb), kb * BK, tl.b_off + j * AR_BN);
+                        tma_load_2d(dst + AR_B_BYTES, &p.map_blo, b_full(sb), kb * BK, tl.b_off + j * AR_BN);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(BM, AR_BN, 0, 0);
+            uint32_t itb = 0, si = 0, mt = 0;
+            for (int64_t t = blockIdx.x; t < p.n_tiles_m; t += gridDim.x, ++mt) {
+                for (int j = 0; j < n_sub; ++j, ++si) {
+                    const uint32_t buf = si & 1u;
+                    mbar_wait(tempty_bar(buf), ((si >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_main = tmem_base + ACC_COL + buf * 128u, d_corr = d_main + 64u;
+                    for (int kb = 0; kb < num_kb; ++kb, ++itb) {
+                        const int sb = itb % AR_NB;
+                        if (j == 0) mbar_wait(atm_full(kb), mt & 1u);
+                        mbar_wait(b_full(sb), (itb / AR_NB) & 1u);
+                        tc_fence_after();
+                        const uint32_t pb = b_base + sb * 2 * AR_B_BYTES;
+#pragma unroll
+                        for (int k = 0; k < BK / 8; ++k) {
+                            const uint32_t a_hi = tmem_base + A_HI_COL + kb * BK + k * 8;
+                            const uint32_t a_lo = tmem_base + A_LO_COL + kb * BK + k * 8;
+                            const uint64_t b_hi = umma_desc_sw128(pb + k * 32, 16, 1024);
+                            const uint64_t b_lo = umma_desc_sw128(pb + AR_B_BYTES + k * 32, 16, 1024);
+                            const uint32_t first = (kb | k) != 0;
+                            umma_tf32_ts(d_corr, a_lo, b_hi, idesc, first);
+                            umma_tf32_ts(d_corr, a_hi, b_lo, idesc, 1u);
+                            umma_tf32_ts(d_main, a_hi, b_hi, idesc, first);
+                        }
+                        tc_commit(b_empty(sb));
+                        if (j == n_sub - 1) tc_commit(atm_empty(kb));      // the converter may refill this K block
+                    }
+                    tc_commit(tfull_bar(buf));
+                }
+            }
+        }
+    } else if (warp < 6) {
+        // ===================================================================== converter: smem row -> (hi, lo) in TMEM
+        const int wq = warp & 3;                             // TMEM lane quarter this warp may access
+        const int row = wq * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+        uint32_t it = 0, mt = 0;
+        for (int64_t t = blockIdx.x; t < p.n_tiles_m; t += gridDim.x, ++mt) {
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const int sa = it % AR_NA;
+                mbar_wait(a_full(sa), (it / AR_NA) & 1u);
+                const uint8_t *arow = smem + sa * A_BYTES + row * 128;
+                uint32_t hi[32], lo[32];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {                // 128-byte swizzle: 16-byte chunk c of row r sits at c ^ (r & 7)
+                    const float4 v = *reinterpret_cast<const float4 *>(arow + ((c ^ (row & 7)) << 4));
+                    const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float h = tf32_hi(x[e]);
+                        hi[4 * c + e] = __float_as_uint(h);
+                        lo[4 * c + e] = __float_as_uint(x[e] - h);
+                    }
+                }
+                mbar_wait(atm_empty(kb), (mt & 1u) ^ 1u);
+                __syncwarp();        // lanes leave the spin loop one by one; tcgen05.st is .sync.aligned
+                tc_fence_after();
+                tmem_st_32x32(tmem_base + lane_addr + A_HI_COL + kb * BK, hi);
+                tmem_st_32x32(tmem_base + lane_addr + A_LO_COL + kb * BK, lo);
+                // Release the raw tile only now: the tcgen05.st instructions READ the registers the LDS.128 filled,
+                // so the loads have completed.  An arrive issued right after the loads can overtake them (the
+                // mbarrier unit does not queue behind LDS traffic that waits for shared-memory bandwidth) and let
+                // the next TMA write land on rows that are still being read.
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_empty(sa));
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(atm_full(kb));
+            }
+        }
+    } else if (warp < 14) {
+        // ===================================================================== epilogue (two warpgroups, one per buffer)
+        const int wq = warp & 3;
+        const uint32_t g = (uint32_t)(warp - 6) >> 2;        // accumulator buffer this warpgroup drains
+        const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+        uint32_t si = 0;
+        for (int64_t t = blockIdx.x; t < p.n_tiles_m; t += gridDim.x) {
+            const Tile tl = locate_tile(p, t * p.n_tiles_n);
+            for (int j = 0; j < n_sub; ++j, ++si) {
+                if ((si & 1u) != g) continue;
+                mbar_wait(tfull_bar(g), (si >> 1) & 1u);
+                __syncwarp();        // reconverge before the .sync.aligned tcgen05.ld
+                tc_fence_after();
+                const uint32_t acc = tmem_base + lane_addr + ACC_COL + g * 128u;
+#pragma unroll 1
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t r[32];
+                    {
+                        uint32_t cr[32];
+                        tmem_ld_32x32(acc + c * 32, r);
+                        tmem_ld_32x32(acc + 64 + c * 32, cr);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(cr[i]));
+                    }
+                    if (c == 1) {                            // accumulator fully read: hand the buffer back
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty_bar(g));
+                    }
+                    store_chunk(nullptr, r, lane, tl.row0 + wq * 32, tl.row_end, j * AR_BN + c * 32, p.N, p.C, p.ldc,
+                                p.out_map, p.bias, p.add, p.ldadd, p.add_in);
+                    __syncwarp();
+                }
                 __syncwarp();
             }
         }
@@ -536,6 +753,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_con
             const Unit x = locate(u);
             const uint32_t buf = ti & 1u;
             mbar_wait(tfull_bar(buf), (ti >> 1) & 1u);
+            __syncwarp();            // reconverge before the .sync.aligned tcgen05.ld
             tc_fence_after();
             float *out = p.part + (int64_t)x.slot * p.N * p.K;
             const int n_chunks = min(4, (p.K - x.k0 + 31) / 32);
@@ -694,11 +912,22 @@ extern "C" int mma_linear_tf32x3(const float *A0, int64_t lda0, int K0, const fl
     if (p.n_tiles_m < 1) return tile_tab ? MMA_OK : MMA_ERR_INVALID;
     p.C = C; p.ldc = ldc; p.out_map = out_map; p.bias = bias; p.add = add; p.ldadd = ldadd;
     p.add_in = (mode_flags & MMA_GEMM_ADD_BY_INPUT_ROW) ? 1 : 0;
-    MMA_CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NT_SMEM_BYTES));
     int sms = 0, dev = 0;
     MMA_CUDA_CHECK(cudaGetDevice(&dev));
     MMA_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
+    // short K, several 128-column tiles per row block: keep the activation tile resident in tensor memory
+    static const bool ares_on = [] { const char *e = getenv("MMA_GEMM_ARES"); return !(e && e[0] == '0'); }();
+    if (ares_on && mode == 1 && K1 == 0 && p.num_kb <= AR_MAX_KB && N >= 2 * BN) {
+        if ((rc = make_map_2d(&p.map_bhi, Bhi, b_rows, K0, ldb, AR_BN, BK)) != MMA_OK) return rc;
+        if ((rc = make_map_2d(&p.map_blo, Blo, b_rows, K0, ldb, AR_BN, BK)) != MMA_OK) return rc;
+        MMA_CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_ares_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AR_SMEM_BYTES));
+        const unsigned grid = (unsigned)(p.n_tiles_m < sms ? p.n_tiles_m : sms);
+        gemm_nt_ares_kernel<<<grid, AR_THREADS, AR_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+        MMA_LAUNCH_CHECK();
+        return MMA_OK;
+    }
+    MMA_CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NT_SMEM_BYTES));
     const int64_t n_tiles = p.n_tiles_m * p.n_tiles_n;
     const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
     gemm_nt_kernel<<<grid, NT_THREADS, NT_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(p);

@@ -13,7 +13,10 @@ def relerr(a, ref):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (1000, 128, 128), (4096, 256, 640), (5000, 384, 136),
-                                   (333, 20, 100), (1, 4, 4), (129, 132, 36)])
+                                   (333, 20, 100), (1, 4, 4), (129, 132, 36),
+                                   # K <= 128 and N >= 256: the variant with the activation tile resident in tensor memory
+                                   (4096, 384, 128), (77777, 640, 128), (1000, 256, 96), (300, 320, 100), (129, 260, 32),
+                                   (200000, 384, 128)])
 def test_linear_vs_fp64(M, N, K):
     from mma_b200 import tc_gemm as tg
     g = torch.Generator().manual_seed(M + N + K)
@@ -76,6 +79,37 @@ def test_grouped_scatter_add_two_sources():
     seg = tg.reduce_slabs_segmented(part, torch.tensor([0, 2, 3], dtype=torch.int32).cuda())
     assert relerr(seg[0], Gc[:1003].t() @ A1[:1003].double()) < REL
     assert relerr(seg[1], Gc[1003:].t() @ A1[1003:].double()) < REL
+
+
+def test_grouped_scatter_add_resident_a():
+    """The tensor-memory-resident variant (K <= 128, N >= 256) with everything the epilogue can fuse: one weight
+    per row range (tile table), bias, row-indexed addend (by output and by input row) and output-row scatter."""
+    from mma_b200 import tc_gemm as tg
+    torch.manual_seed(1)
+    M, K, N = 3000, 128, 640
+    A = torch.randn(M, K).cuda()
+    Ws = (torch.randn(3, N, K) / 11).cuda()
+    b = torch.randn(N).cuda()
+    perm = torch.randperm(M).cuda().int()
+    add = torch.randn(M, N).cuda()
+    segs = [(0, 1000, 0), (1000, 1100, 2), (1100, 3000, 1)]
+    tab = torch.tensor([(r, hi_, w * N, 0) for lo_, hi_, w in segs for r in range(lo_, hi_, 128)], dtype=torch.int32).cuda()
+    hi, lo = tg.split_weight(Ws.view(3 * N, K))
+    ref = torch.empty(M, N, dtype=torch.float64).cuda()
+    for lo_, hi_, w in segs:
+        ref[lo_:hi_] = A[lo_:hi_].double() @ Ws[w].double().t()
+    ref += b.double()
+    for by_input in (False, True):
+        C = tg.linear(A, hi, lo, N, tile_tab=tab, out_map=perm, add=add, bias=b, add_by_input_row=by_input)
+        full = torch.empty_like(ref)
+        full[perm.long()] = ref + (add.double() if by_input else 0)
+        if not by_input:
+            full += add.double()
+        assert relerr(C, full) < REL
+    # same numbers as the streaming kernel to fp32 rounding, and deterministic
+    C1 = tg.linear(A, hi, lo, N, tile_tab=tab)
+    assert torch.equal(C1, tg.linear(A, hi, lo, N, tile_tab=tab))
+    assert relerr(C1, ref - b.double()) < REL
 
 
 def test_no_cpu_path():
