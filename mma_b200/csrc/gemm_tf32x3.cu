@@ -52,6 +52,8 @@ constexpr int TMEM_COLS = 512;   // 2 tiles in flight x (main + correction) accu
 
 struct alignas(64) NtParams {
     CUtensorMap map_a0, map_a1, map_bhi, map_blo;
+    CUtensorMap map_c;          // output as [32 rows x 32 columns] boxes (resident-A variant, plain row-major output)
+    int tma_store;              // 1: full tiles leave through shared memory + TMA tile stores
     int kb_split, num_kb;       // k-blocks [0,kb_split) read map_a0, [kb_split,num_kb) read map_a1
     int n_tiles_n;
     int mode;                   // 0: 3xTF32, hi written back explicitly; 1: 3xTF32, raw A as hi; 2: 1xTF32
@@ -347,28 +349,36 @@ __global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_kernel(const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------
-// Short-K variant (K <= 128, many output columns): the activation tile stays RESIDENT IN TENSOR MEMORY.
+// Short-K variant (K <= 128, several 128-column tiles per row block): the activation tile stays RESIDENT IN
+// TENSOR MEMORY.
 //
-// The kernel above is bound by shared-memory bandwidth: per 32-wide K block it moves 16 KB (TMA write) +
-// 32 KB (converter) + 96 KB (three MMAs reading A and B) through shared memory, and it does so again for every
-// 128-column output tile of the same rows.  For the two GEMMs with K = 128 and 384 / 640 output columns (the
-// mask projection and the dgrad of the post transform) this variant
+// The kernel above is bound by shared-memory bandwidth: per tcgen05.mma it moves ~16 KB through shared memory
+// (A and B operand reads of three MMAs, the converter's read + write, the TMA fills) = ~135 cycles per MMA where
+// the tensor core needs 64, and it repeats the conversion of A for every 128-column tile of the same rows.  For
+// the two GEMMs with K = 128 and 384 / 640 output columns (mask projection, dgrad of the post transform) this
+// variant
 //   * converts a [128 x K] activation tile ONCE per row block: TMA -> shared memory -> registers (a thread owns
 //     a row) -> hi / lo written with tcgen05.st into tensor-memory columns [0,128) / [128,256);
 //   * issues the MMAs with the A operand read FROM TENSOR MEMORY (tcgen05.mma [d], [a], b_desc): only the
 //     weight tiles cross shared memory;
-//   * walks the output columns in 64-wide sub-tiles that all reuse the resident A; two accumulator pairs
-//     (main + correction, 64 + 64 columns each) at columns [256,512), one per epilogue warpgroup, so the
-//     epilogue of sub-tile j overlaps the MMAs of sub-tile j + 1.
+//   * walks the output columns in 128-wide sub-tiles that all reuse the resident A.  K <= 128 means at most 48
+//     accumulations per element, so ONE accumulator serves the three 3xTF32 terms (the streaming kernel keeps the
+//     cross terms apart because its chains reach 240); the two 128-column accumulators at columns [256,512)
+//     belong to one epilogue warpgroup each, so the epilogue of sub-tile j overlaps the MMAs of sub-tile j + 1.
+//     (64-column sub-tiles with a separate correction accumulator were measured first: 92 cycles per N = 64 MMA,
+//     slower than the streaming kernel; N = 128 MMAs take ~115 cycles.)
 // The K-block slots of A are released one by one while the LAST sub-tile of a row block is being issued, so
-// the converter refills them for the next row block under the tail of the current one.
+// the converter refills them for the next row block under the tail of the current one.  Full tiles of a plain
+// row-major output leave through swizzled shared-memory staging + TMA tile stores.
 //   warp 0 TMA (activations) | warp 1 MMA issuer | warps 2-5 converter | warps 6-9, 10-13 epilogue | warp 14 TMA (weights)
+// Measured at M = 2M: K=128 -> 384 columns 1.30 -> 1.00 ms, K=128 -> 640 columns 2.10 -> 1.61 ms.
 // ------------------------------------------------------------------------------------------
-constexpr int AR_BN = 64;                                  // output columns per sub-tile
-constexpr int AR_B_BYTES = AR_BN * BK * 4;                 // 8 KB per half (hi or lo)
-constexpr int AR_NA = 4, AR_NB = 8, AR_MAX_KB = 4;
+constexpr int AR_BN = 128;                                 // output columns per sub-tile
+constexpr int AR_B_BYTES = AR_BN * BK * 4;                 // 16 KB per half (hi or lo)
+constexpr int AR_NA = 4, AR_NB = 4, AR_MAX_KB = 4;
 constexpr int AR_BAR_BYTES = 512;
-constexpr int AR_SMEM_BYTES = AR_NA * A_BYTES + AR_NB * 2 * AR_B_BYTES + AR_BAR_BYTES + 1024;
+constexpr int AR_STG_BYTES = 8 * 4096;                     // per epilogue warp: one [32 x 32] fp32 staging tile
+constexpr int AR_SMEM_BYTES = AR_NA * A_BYTES + AR_NB * 2 * AR_B_BYTES + AR_STG_BYTES + AR_BAR_BYTES + 1024;
 constexpr int AR_THREADS = 480;
 static_assert(AR_SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory per CTA");
 
@@ -377,7 +387,8 @@ __global__ void __launch_bounds__(AR_THREADS, 1) gemm_nt_ares_kernel(const __gri
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
     const uint32_t b_base = smem_base + AR_NA * A_BYTES;
-    const uint32_t bar_base = b_base + AR_NB * 2 * AR_B_BYTES;
+    const uint32_t stg_base = b_base + AR_NB * 2 * AR_B_BYTES;
+    const uint32_t bar_base = stg_base + AR_STG_BYTES;
     auto a_full = [&](int i) { return bar_base + 8u * i; };
     auto a_empty = [&](int i) { return bar_base + 8u * (AR_NA + i); };
     auto atm_full = [&](int i) { return bar_base + 8u * (2 * AR_NA + i); };
@@ -397,6 +408,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) gemm_nt_ares_kernel(const __gri
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.map_a0); tma_prefetch_desc(&p.map_bhi); tma_prefetch_desc(&p.map_blo);
+        if (p.tma_store) tma_prefetch_desc(&p.map_c);
         for (int i = 0; i < AR_NA; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 4); }
         for (int i = 0; i < AR_MAX_KB; ++i) { mbar_init(atm_full(i), 4); mbar_init(atm_empty(i), 1); }
         for (int i = 0; i < AR_NB; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
@@ -408,7 +420,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) gemm_nt_ares_kernel(const __gri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
-    constexpr uint32_t A_HI_COL = 0, A_LO_COL = 128, ACC_COL = 256;     // acc buffer b: main at ACC_COL + 128 b, corr + 64
+    constexpr uint32_t A_HI_COL = 0, A_LO_COL = 128, ACC_COL = 256;     // accumulator of buffer b at ACC_COL + 128 b
 
     if (warp == 0) {
         // ===================================================================== TMA producer: activations (HBM)
@@ -452,7 +464,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) gemm_nt_ares_kernel(const __gri
                     const uint32_t buf = si & 1u;
                     mbar_wait(tempty_bar(buf), ((si >> 1) & 1u) ^ 1u);
                     tc_fence_after();
-                    const uint32_t d_main = tmem_base + ACC_COL + buf * 128u, d_corr = d_main + 64u;
+                    const uint32_t d_main = tmem_base + ACC_COL + buf * 128u;
                     for (int kb = 0; kb < num_kb; ++kb, ++itb) {
                         const int sb = itb % AR_NB;
                         if (j == 0) mbar_wait(atm_full(kb), mt & 1u);
@@ -466,9 +478,12 @@ __global__ void __launch_bounds__(AR_THREADS, 1) gemm_nt_ares_kernel(const __gri
                             const uint64_t b_hi = umma_desc_sw128(pb + k * 32, 16, 1024);
                             const uint64_t b_lo = umma_desc_sw128(pb + AR_B_BYTES + k * 32, 16, 1024);
                             const uint32_t first = (kb | k) != 0;
-                            umma_tf32_ts(d_corr, a_lo, b_hi, idesc, first);
-                            umma_tf32_ts(d_corr, a_hi, b_lo, idesc, 1u);
-                            umma_tf32_ts(d_main, a_hi, b_hi, idesc, first);
+                            // K <= 128: at most 48 accumulations per element, so one accumulator serves all three
+                            // terms (the streaming kernel keeps a second one for the cross terms because its chains
+                            // reach 240); that leaves room for 128-column sub-tiles next to the resident A
+                            umma_tf32_ts(d_main, a_lo, b_hi, idesc, first);
+                            umma_tf32_ts(d_main, a_hi, b_lo, idesc, 1u);
+                            umma_tf32_ts(d_main, a_hi, b_hi, idesc, 1u);
                         }
                         tc_commit(b_empty(sb));
                         if (j == n_sub - 1) tc_commit(atm_empty(kb));      // the converter may refill this K block
@@ -522,9 +537,15 @@ __global__ void __launch_bounds__(AR_THREADS, 1) gemm_nt_ares_kernel(const __gri
         const int wq = warp & 3;
         const uint32_t g = (uint32_t)(warp - 6) >> 2;        // accumulator buffer this warpgroup drains
         const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
-        uint32_t si = 0;
+        // Full tiles of a plain row-major output leave through shared memory and the TMA unit: a thread owns a ROW of
+        // the accumulator, so direct global stores cost one LSU wavefront per lane and instruction (the l1tex data pipe
+        // was ~80 % busy with them); staging the 32 x 32 chunk in the 128-byte-swizzled layout (4 wavefronts per
+        // instruction) and one TMA tile store per chunk takes the global stores off the LSU altogether.
+        const uint32_t my_stg = stg_base + (uint32_t)(warp - 6) * 4096u;
+        uint32_t si = 0, n_staged = 0;
         for (int64_t t = blockIdx.x; t < p.n_tiles_m; t += gridDim.x) {
             const Tile tl = locate_tile(p, t * p.n_tiles_n);
+            const bool via_tma = p.tma_store && tl.row0 + BM <= tl.row_end;
             for (int j = 0; j < n_sub; ++j, ++si) {
                 if ((si & 1u) != g) continue;
                 mbar_wait(tfull_bar(g), (si >> 1) & 1u);
@@ -532,28 +553,51 @@ __global__ void __launch_bounds__(AR_THREADS, 1) gemm_nt_ares_kernel(const __gri
                 tc_fence_after();
                 const uint32_t acc = tmem_base + lane_addr + ACC_COL + g * 128u;
 #pragma unroll 1
-                for (int c = 0; c < 2; ++c) {
+                for (int c = 0; c < AR_BN / 32; ++c) {
                     uint32_t r[32];
-                    {
-                        uint32_t cr[32];
-                        tmem_ld_32x32(acc + c * 32, r);
-                        tmem_ld_32x32(acc + 64 + c * 32, cr);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(cr[i]));
-                    }
-                    if (c == 1) {                            // accumulator fully read: hand the buffer back
+                    tmem_ld_32x32(acc + c * 32, r);
+                    tmem_ld_wait();
+                    if (c == AR_BN / 32 - 1) {               // accumulator fully read: hand the buffer back
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(tempty_bar(g));
                     }
-                    store_chunk(nullptr, r, lane, tl.row0 + wq * 32, tl.row_end, j * AR_BN + c * 32, p.N, p.C, p.ldc,
-                                p.out_map, p.bias, p.add, p.ldadd, p.add_in);
+                    const int col0 = j * AR_BN + c * 32;
+                    if (!via_tma) {
+                        store_chunk(nullptr, r, lane, tl.row0 + wq * 32, tl.row_end, col0, p.N, p.C, p.ldc,
+                                    p.out_map, p.bias, p.add, p.ldadd, p.add_in);
+                        __syncwarp();
+                        continue;
+                    }
+                    if (col0 >= p.N) continue;
+                    const uint32_t sbuf = my_stg;
+                    if (lane == 0) tma_store_wait_read<0>();      // the previous tile store has read the buffer
                     __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                               __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                        if (p.bias && col0 + 4 * q + 4 <= p.N) {
+                            const float4 bb = __ldg(reinterpret_cast<const float4 *>(p.bias + col0) + q);
+                            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+                        }
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sbuf + lane * 128u +
+                                                                                       ((uint32_t)(q ^ (lane & 7)) << 4)),
+                                     "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                                     : "memory");
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&p.map_c, sbuf, col0, (int)(tl.row0 + wq * 32));   // columns >= N, rows >= M: clipped
+                        tma_store_commit();
+                    }
+                    ++n_staged;
                 }
                 __syncwarp();
             }
         }
+        if (lane == 0) tma_store_wait_read<0>();             // shared memory must outlive the last tile stores
     }
 
     tc_fence_before();
@@ -921,6 +965,8 @@ extern "C" int mma_linear_tf32x3(const float *A0, int64_t lda0, int K0, const fl
     if (ares_on && mode == 1 && K1 == 0 && p.num_kb <= AR_MAX_KB && N >= 2 * BN) {
         if ((rc = make_map_2d(&p.map_bhi, Bhi, b_rows, K0, ldb, AR_BN, BK)) != MMA_OK) return rc;
         if ((rc = make_map_2d(&p.map_blo, Blo, b_rows, K0, ldb, AR_BN, BK)) != MMA_OK) return rc;
+        static const bool tma_st = [] { const char *e = getenv("MMA_GEMM_TMA_STORE"); return !(e && e[0] == '0'); }();
+        p.tma_store = (tma_st && !out_map && !add && make_map_2d(&p.map_c, C, M, N, ldc, 32, 32) == MMA_OK) ? 1 : 0;
         MMA_CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_ares_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AR_SMEM_BYTES));
         const unsigned grid = (unsigned)(p.n_tiles_m < sms ? p.n_tiles_m : sms);
         gemm_nt_ares_kernel<<<grid, AR_THREADS, AR_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(p);
