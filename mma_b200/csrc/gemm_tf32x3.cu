@@ -457,7 +457,9 @@ __global__ void __launch_bounds__(AR_THREADS, 1) gemm_nt_ares_kernel(const __gri
     } else if (warp == 1) {
         // ===================================================================== MMA issuer
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_tf32(BM, AR_BN, 0, 0);
+            constexpr int AR_SPLIT = 1;                      // column slices per sub-tile issued as separate MMAs (see below)
+            constexpr int AR_HN = AR_BN / AR_SPLIT;
+            constexpr uint32_t idesc = umma_idesc_tf32(BM, AR_HN, 0, 0);
             uint32_t itb = 0, si = 0, mt = 0;
             for (int64_t t = blockIdx.x; t < p.n_tiles_m; t += gridDim.x, ++mt) {
                 for (int j = 0; j < n_sub; ++j, ++si) {
@@ -475,15 +477,22 @@ __global__ void __launch_bounds__(AR_THREADS, 1) gemm_nt_ares_kernel(const __gri
                         for (int k = 0; k < BK / 8; ++k) {
                             const uint32_t a_hi = tmem_base + A_HI_COL + kb * BK + k * 8;
                             const uint32_t a_lo = tmem_base + A_LO_COL + kb * BK + k * 8;
-                            const uint64_t b_hi = umma_desc_sw128(pb + k * 32, 16, 1024);
-                            const uint64_t b_lo = umma_desc_sw128(pb + AR_B_BYTES + k * 32, 16, 1024);
                             const uint32_t first = (kb | k) != 0;
                             // K <= 128: at most 48 accumulations per element, so one accumulator serves all three
                             // terms (the streaming kernel keeps a second one for the cross terms because its chains
                             // reach 240); that leaves room for 128-column sub-tiles next to the resident A
-                            umma_tf32_ts(d_main, a_lo, b_hi, idesc, first);
-                            umma_tf32_ts(d_main, a_hi, b_lo, idesc, 1u);
-                            umma_tf32_ts(d_main, a_hi, b_hi, idesc, 1u);
+                            // AR_SPLIT = 2 (two alternating N = 64 slices, i.e. independent accumulator chains) was
+                            // measured SLOWER (1.00 -> 1.26 ms): the cost is per instruction (~70 cycles + 0.36 per
+                            // column), not the dependence between consecutive MMAs, so wide MMAs win.
+#pragma unroll
+                            for (int term = 0; term < 3; ++term) {
+#pragma unroll
+                                for (int h = 0; h < AR_SPLIT; ++h) {
+                                    const uint32_t boff = (uint32_t)h * AR_HN * 128u;           // AR_HN weight rows of 128 B
+                                    const uint64_t bd = umma_desc_sw128((term == 1 ? pb + AR_B_BYTES : pb) + boff + k * 32, 16, 1024);
+                                    umma_tf32_ts(d_main + h * AR_HN, term == 0 ? a_lo : a_hi, bd, idesc, term == 0 ? first : 1u);
+                                }
+                            }
                         }
                         tc_commit(b_empty(sb));
                         if (j == n_sub - 1) tc_commit(atm_empty(kb));      // the converter may refill this K block
