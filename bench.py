@@ -37,10 +37,32 @@ CONFIGS = {
     # name: (nodes, edges, hidden)
     "c4": (2_000_000, 32_000_000, 128),
     "c4s": (125_000, 2_000_000, 128),      # the 1/16 sub-graph (CPU-baseline size), for quick checks
+    # config 5 (8-GPU load-balance stress, not the bench line): power-law in-degrees (alpha = 2.1, capped at 10^6),
+    # hidden 64, destination ranges balanced by in-edge count
+    "c5": (10_000_000, 200_000_000, 64),
+    "c5s": (1_250_000, 25_000_000, 64),    # one eighth of it, for dry runs
 }
+
+
+def powerlaw_edges(N, E, dev, seed=42, alpha=2.1):
+    """In-degree of the node of rank r proportional to r^(-1/(alpha-1)), scaled to ~E edges, largest degree capped at
+    E/200 (10^6 for config 5); the ranks are dealt to RANDOM node ids (ids carry no locality, as in a hashed id
+    space), sources uniform.  Returns (src, dst) int64 on `dev`."""
+    g = torch.Generator(device=dev).manual_seed(seed)
+    cap = max(E // 200, 1)
+    r = torch.arange(1, N + 1, device=dev, dtype=torch.float64)
+    w = r.pow(-1.0 / (alpha - 1.0))
+    deg = (w / w.sum() * E).clamp(max=cap)
+    deg = (deg * (E / deg.sum())).clamp(max=cap).round().long()
+    ids = torch.randperm(N, device=dev, generator=g)
+    dst = torch.repeat_interleave(ids, deg)
+    del r, w, deg, ids
+    dst = dst[torch.randperm(dst.numel(), device=dev, generator=g)]
+    src = torch.randint(0, N, (dst.numel(),), device=dev, generator=g)
+    return src, dst
 METRIC = "MultiMaskConv fwd+bwd edges/sec"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
-# workload at N = 1 (profiles/r1z_ncu_full_selected.csv)
+# workload at N = 1 (profiles/r1z_ncu_full_selected.csv; the forward kernel re-captured in r1f_ncu_full_selected.csv)
 NCU_TRAFFIC_C4 = {"mmconv_aggregate_fwd": 25.85e9, "mmconv_aggregate_bwd_dst": 43.95e9, "mma_segment_sum_rows": 17.41e9}
 
 
@@ -186,7 +208,10 @@ def main():
     N, E, F = CONFIGS[args.config]
     A, S = len(AGGR), len(SCAL)
     warm = max(args.warmup, 3) if args.impl != "reference" else args.warmup
-    cfg = {"workload": f"config 4: uniform random graph N={N} E={E} hidden={F}, MMAConv fwd+bwd, aggregators "
+    skewed = args.config.startswith("c5")
+    cfg = {"workload": (f"config 5: power-law graph (alpha 2.1, max in-degree {E // 200}) N={N} E~{E} hidden={F}, "
+                        if skewed else f"config 4: uniform random graph N={N} E={E} hidden={F}, ") +
+                       f"MMAConv fwd+bwd, aggregators "
                        f"{','.join(AGGR)} x scalers {','.join(SCAL)}, towers=1, dropout {args.dropout}",
            "nodes": N, "edges": E, "hidden": F, "aggregators": AGGR, "scalers": SCAL,
            "parallelism": f"dst-range x{world}" if world > 1 else "single GPU",
@@ -226,8 +251,13 @@ def main():
 
     torch.manual_seed(42)
     gen = torch.Generator(device=dev).manual_seed(42)
-    src = torch.randint(0, N, (E,), generator=gen, device=dev)
-    dst = torch.randint(0, N, (E,), generator=gen, device=dev)
+    if skewed:
+        src, dst = powerlaw_edges(N, E, dev)
+        E = int(dst.numel())
+        cfg["edges"] = E
+    else:
+        src = torch.randint(0, N, (E,), generator=gen, device=dev)
+        dst = torch.randint(0, N, (E,), generator=gen, device=dev)
     deg = torch.bincount(dst, minlength=N)
     hist = torch.bincount(deg).cpu()
     max_deg = int(deg.max().item())
@@ -238,7 +268,9 @@ def main():
     conv.comm_slices = args.slices
     conv.global_max_deg = max_deg
     if world > 1:
-        graph = ShardedGraph(src, dst, N, rank, world, balance="nodes")
+        graph = ShardedGraph(src, dst, N, rank, world, balance="edges" if skewed else "nodes")
+        cfg["partition"] = {"balance": "edges" if skewed else "nodes", "rows": graph.rows, "edges": graph.E,
+                            "max_rows": graph.max_rows}
         rows = graph.rows
         graph.local.build_transpose()
     else:
@@ -400,7 +432,7 @@ def main():
 
     # ---------------- roofline of the dominant kernel ----------------
     peak, peak_kind = peaks()
-    n_loc, e_loc = N // world, E // world
+    n_loc, e_loc = (graph.rows, graph.E) if world > 1 else (N, E)
     S_mat = 1                               # scaler blocks materialised by K1 (folded into the post GEMM)
     ab = algo_bytes(n_loc, e_loc, F, A, S_mat, 2, True)
     per_kernel = {}
@@ -421,7 +453,7 @@ def main():
         roofline = {"bound": "hbm", "kernel": dom, "achieved": d["GBps"], "peak": peak, "unit": "GB/s",
                     "frac": d["GBps"] / peak,
                     "traffic": NCU_TRAFFIC_C4.get(dom) if (args.config == "c4" and world == 1) else None,
-                    "traffic_source": "profiles/r1z_ncu_full_selected.csv (ncu --set full, bytes per launch)",
+                    "traffic_source": "profiles/r1z_ncu_full_selected.csv, r1f_ncu_full_selected.csv (ncu --set full, bytes per launch)",
                     "peak_kind": peak_kind,
                     "launch_ms": d["ms_per_launch"], "share_of_step": d["ms_per_step"] / ms}
     agg_ms = sum(v["ms_per_step"] for k, v in per_kernel.items()

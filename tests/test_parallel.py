@@ -73,6 +73,28 @@ def test_partition_bounds_single_process():
     assert sum(s.stop - s.start for s in _slices(100, 3)) == 100
 
 
+def test_config5_partition_balances_edges_and_rows():
+    """config 5's generator (bench.py): power-law in-degrees dealt to random node ids.  Destination ranges balanced by
+    in-edge count must then also hold similar row counts -- the all-gathered Q layout is padded to the largest range."""
+    import bench
+    from mma_b200.parallel import partition_bounds
+    N, E, world = 40_000, 800_000, 8
+    src, dst = bench.powerlaw_edges(N, E, torch.device("cpu"))
+    deg = torch.bincount(dst, minlength=N)
+    assert abs(dst.numel() - E) < 0.02 * E and int(deg.max()) == E // 200          # the capped hubs are there
+    assert int(src.max()) < N and int(dst.max()) < N
+    b = partition_bounds(dst, N, world, "edges")
+    csum = torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(deg, 0)])
+    edges = [int(csum[b[r + 1]] - csum[b[r]]) for r in range(world)]
+    rows = [b[r + 1] - b[r] for r in range(world)]
+    assert max(edges) <= 1.05 * dst.numel() / world, edges
+    assert max(rows) <= 1.35 * N / world, rows                                      # padding of the exchange stays small
+    # by node count the shard that drew the largest hubs would carry visibly more edges
+    bn = partition_bounds(dst, N, world, "nodes")
+    en = [int(csum[bn[r + 1]] - csum[bn[r]]) for r in range(world)]
+    assert max(en) > max(edges)
+
+
 def _gpu_worker(rank, world, port, n, E, Fd, p_drop):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
