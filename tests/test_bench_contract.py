@@ -1,0 +1,37 @@
+"""bench.py's reference arm (`--impl reference`: the oracle port of the reference layer on the host cores) on the
+small configuration: the JSON line carries the keys the driver reads.  The GPU arm needs a B200 and is run by the
+driver; its algorithmic-byte formulas are checked here against the figures quoted in DESIGN.md."""
+import json
+import os
+import subprocess
+import sys
+
+from conftest import ROOT
+
+
+def test_reference_arm_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "c4s",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "MultiMaskConv fwd+bwd edges/sec" and d["unit"] == "edges/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["dtype"] == "f32" and d["data"] == "synthetic"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_algorithmic_bytes_match_design():
+    sys.path.insert(0, ROOT)
+    import bench
+    N, E, F = bench.CONFIGS["c4"]
+    ab = bench.algo_bytes(N, E, F, A=5, S=1, n_mm=2, std=True)
+    # 26.76 GB (K1 forward), 44.4 GB (destination pass), 17.4 GB (transpose pass); SURVEY 8(d) with S = 1
+    assert abs(ab["mmconv_aggregate_fwd"] / 1e9 - 26.76) < 0.01
+    assert abs(ab["mmconv_aggregate_bwd_dst"] / 1e9 - 44.42) < 0.01
+    assert abs(ab["mma_segment_sum_rows"] / 1e9 - 17.42) < 0.01
+    assert abs((ab["fwd"] + ab["bwd"]) / 1e9 - 67.1) < 0.1
+    s4 = bench.algo_bytes(N, E, F, A=5, S=4, n_mm=2, std=True)
+    assert abs((s4["fwd"] + s4["bwd"]) / 1e9 - 97.8) < 0.2            # SURVEY's figure with the scaler blocks materialised
