@@ -276,7 +276,11 @@ int mma_tf32_split(const float *w, float *hi, float *lo, int64_t n, mma_stream_t
  *   bias [N], add (indexed like C, i.e. by OUTPUT row, may alias C; with MMA_GEMM_ADD_BY_INPUT_ROW
  *     or-ed into `mode`: indexed by the input row r) optional.
  *   mode 0 = 3xTF32 (hi written back), 1 = 3xTF32 (raw operand as hi), 2 = plain TF32 (not fp32-accurate).
- *   max_ctas <= 0: one persistent CTA per SM. */
+ *   max_ctas <= 0: one persistent CTA per SM.
+ *   Kernel choice: mode 1 with one source, K0 <= 128 and N >= 256 runs the variant that keeps the [128 x K]
+ *   activation tile resident in tensor memory (one accumulator for the three terms; full tiles of a plain
+ *   row-major output leave through TMA tile stores); everything else the streaming kernel.  Environment
+ *   switches for A/B runs, read once per process: MMA_GEMM_ARES=0 (always stream), MMA_GEMM_TMA_STORE=0. */
 #define MMA_GEMM_ADD_BY_INPUT_ROW 4
 
 int mma_linear_tf32x3(const float *A0, int64_t lda0, int K0, const float *A1, int64_t lda1, int K1,
