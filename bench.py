@@ -123,9 +123,13 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
 
-    def stop(self):
+    def stop(self, windows=()):
+        """windows: [(label, t0, t1)] in time.time() seconds, tried in order; the first one that holds a sample is
+        summarised (nvidia-smi delivers ~10 samples/s, so a timed region of a few tens of ms -- 8 GPUs -- may hold
+        none: the next window then adds the per-kernel timing pass and the e2e steps that follow it under the
+        same load)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -133,8 +137,14 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        picked, label = [ln for _, ln in self.lines], "whole run"
+        for lab, t0, t1 in windows:
+            inside = [ln for t, ln in self.lines if t0 <= t <= t1]
+            if inside:
+                picked, label = inside, lab
+                break
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in picked:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -148,7 +158,7 @@ class ClockSampler:
         sm.sort()
         hi = [v for v in sm if v >= 0.5 * max(sm)] if sm else []
         return {"sm_mhz": (hi[len(hi) // 2] if hi else None), "sm_max_mhz": (max(mx) if mx else None),
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": label}
 
 
 # ------------------------------------------------------------------------------------------
@@ -304,6 +314,9 @@ def main():
     # graph, so every replay draws a fresh mask exactly like an eager call.
     use_graph = not args.no_graph
     conv.device_seed = use_graph
+    sampler = ClockSampler(local_rank)          # started early: nvidia-smi needs ~1 s before its first sample
+    if rank == 0:
+        sampler.start()
     side = torch.cuda.Stream(device=dev)
     side.wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.stream(side):
@@ -332,17 +345,15 @@ def main():
         run()
     barrier()
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_timed0 = time.time()
     e0.record()
     for _ in range(args.steps):
         run()
     e1.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    t_timed1 = time.time()
     ms = e0.elapsed_time(e1) / args.steps
     if world > 1:
         t = torch.tensor([ms], device=dev)
@@ -410,6 +421,11 @@ def main():
                "h2d_bytes_per_step": rows * F * 4 * world, "d2h_bytes_per_step": 4 * world,
                "note": "x uploaded from pinned host memory every step on a copy stream (double-buffered under the "
                        "previous step), loss read back every step"}
+
+    clocks = None
+    if rank == 0:
+        clocks = sampler.stop([("timed region", t_timed0, t_timed1),
+                               ("timed region + per-kernel timing pass + e2e steps", t_timed0, time.time())])
 
     def finish():
         """Tears the run down without dist.destroy_process_group(): destroying a communicator that a live CUDA
