@@ -207,12 +207,15 @@ int mma_gather_rows(const float *src, int64_t lds, const int32_t *idx, int64_t n
  *   OUT[a,i,c] = combine_a(X[i,c], S[a,i,c], D_i) (sum/mean/max/min/none)
  *   PA, QA [N, A*F] ld ldpa/ldqa; X [N,F] ld ldx; keep [A, E, F] contiguous or NULL; OUT, S_out [A, N, F]
  *   edge id for dropout/keep = CSR position (neighbour-list order, as the reference consumes it).
+ *   seed_dev (optional, device pointer): when set, the Philox key is read from device memory at run time
+ *   instead of `seed`, so that a launch captured in a CUDA graph draws a fresh mask on every replay
+ *   (same convention as mmconv_aggregate_fwd).
  * ---------------------------------------------------------------------- */
 int mma_nc_aggregate_fwd(const int32_t *rowptr, const int32_t *col, int64_t N, int64_t E,
                          const float *X, int64_t ldx, const float *PA, int64_t ldpa,
                          const float *QA, int64_t ldqa, int F, int A,
                          const int32_t *act_kinds, const int32_t *comb_kinds,
-                         const float *keep, float p_drop, uint64_t seed,
+                         const float *keep, float p_drop, uint64_t seed, const uint64_t *seed_dev,
                          float *OUT, float *S_out, mma_stream_t stream);
 
 /* K2 backward, destination pass: from dOUT [A,N,F] computes
@@ -224,7 +227,7 @@ int mma_nc_aggregate_bwd_dst(const int32_t *rowptr, const int32_t *col, int64_t 
                              const float *X, int64_t ldx, const float *PA, int64_t ldpa,
                              const float *QA, int64_t ldqa, int F, int A,
                              const int32_t *act_kinds, const int32_t *comb_kinds,
-                             const float *keep, float p_drop, uint64_t seed,
+                             const float *keep, float p_drop, uint64_t seed, const uint64_t *seed_dev,
                              const float *S_saved, const float *dOUT,
                              float *gS, float *dXdir, float *dPA, int64_t lddpa,
                              mma_stream_t stream);
@@ -237,7 +240,7 @@ int mma_nc_aggregate_bwd_src(const int32_t *colptr, const int32_t *row, const in
                              const float *X, int64_t ldx, const float *PA, int64_t ldpa,
                              const float *QA, int64_t ldqa, int F, int A,
                              const int32_t *act_kinds,
-                             const float *keep, float p_drop, uint64_t seed,
+                             const float *keep, float p_drop, uint64_t seed, const uint64_t *seed_dev,
                              const float *gS, float *dQA, int64_t lddqa, float *dXnbr, int64_t lddx,
                              mma_stream_t stream);
 

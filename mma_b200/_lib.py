@@ -42,11 +42,11 @@ _SIGS = {
     "mma_gather_rows": ([_vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp, _i64, _vp], C.c_int),
     "mma_segment_sum_rows": ([_vp, _vp, _vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp], C.c_int),
     "mma_nc_aggregate_fwd": ([_vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32,
-                              _vp, _vp, _vp, _f32, _u64, _vp, _vp, _vp], C.c_int),
+                              _vp, _vp, _vp, _f32, _u64, _vp, _vp, _vp, _vp], C.c_int),
     "mma_nc_aggregate_bwd_dst": ([_vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32,
-                                  _vp, _vp, _vp, _f32, _u64, _vp, _vp, _vp, _vp, _vp, _i64, _vp], C.c_int),
+                                  _vp, _vp, _vp, _f32, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp], C.c_int),
     "mma_nc_aggregate_bwd_src": ([_vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32,
-                                  _vp, _vp, _f32, _u64, _vp, _vp, _i64, _vp, _i64, _vp], C.c_int),
+                                  _vp, _vp, _f32, _u64, _vp, _vp, _vp, _i64, _vp, _i64, _vp], C.c_int),
     "mma_dropout_keep_scale": ([_f32, _u64, _u32, _i64, _i32, _vp, _i64, _vp], C.c_int),
     "mma_dropout_keep_scale_rows": ([_vp, _vp, _vp, _i64, _i64, _i64, _f32, _u64, _i32, _vp, _i64, _vp], C.c_int),
     "mma_tf32_split": ([_vp, _vp, _vp, _i64, _vp], C.c_int),

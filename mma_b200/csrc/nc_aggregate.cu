@@ -327,7 +327,8 @@ __global__ void __launch_bounds__(256) nc_bwd_src_kernel(const __grid_constant__
 
 static int nc_fill(NcParams &p, const int32_t *ptr, const int32_t *idx, int64_t N, int64_t E, const float *X,
                    int64_t ldx, const float *PA, int64_t ldpa, const float *QA, int64_t ldqa, int F, int A,
-                   const int32_t *act, const int32_t *comb, const float *keep, float p_drop, uint64_t seed) {
+                   const int32_t *act, const int32_t *comb, const float *keep, float p_drop, uint64_t seed,
+                   const uint64_t *seed_dev) {
     if (!ptr || (E > 0 && !idx) || !X || !PA || !QA || N < 0 || E < 0 || F < 1 || A < 1 || !act) return MMA_ERR_INVALID;
     if (A > MMA_MAX_AGGR) return MMA_ERR_UNSUPPORTED;
     if (N >= INT32_MAX || E >= INT32_MAX) return MMA_ERR_UNSUPPORTED;
@@ -344,7 +345,7 @@ static int nc_fill(NcParams &p, const int32_t *ptr, const int32_t *idx, int64_t 
         }
     }
     p.keep = keep;
-    p.drop = make_dropout(p_drop, seed);
+    p.drop = make_dropout(p_drop, seed, seed_dev);
     p.use_philox = (!keep && p_drop > 0.0f) ? 1 : 0;
     return MMA_OK;
 }
@@ -397,10 +398,11 @@ using namespace mma;
 extern "C" int mma_nc_aggregate_fwd(const int32_t *rowptr, const int32_t *col, int64_t N, int64_t E,
                                     const float *X, int64_t ldx, const float *PA, int64_t ldpa,
                                     const float *QA, int64_t ldqa, int F, int A, const int32_t *act_kinds,
-                                    const int32_t *comb_kinds, const float *keep, float p_drop, uint64_t seed,
+                                    const int32_t *comb_kinds, const float *keep, float p_drop, uint64_t seed, const uint64_t *seed_dev,
                                     float *OUT, float *S_out, mma_stream_t stream) {
     NcParams p;
-    int rc = nc_fill(p, rowptr, col, N, E, X, ldx, PA, ldpa, QA, ldqa, F, A, act_kinds, comb_kinds, keep, p_drop, seed);
+    int rc = nc_fill(p, rowptr, col, N, E, X, ldx, PA, ldpa, QA, ldqa, F, A, act_kinds, comb_kinds, keep, p_drop, seed,
+                     seed_dev);
     if (rc != MMA_OK) return rc;
     if (!OUT || !comb_kinds) return MMA_ERR_INVALID;
     p.OUT = OUT; p.S_out = S_out;
@@ -414,11 +416,12 @@ extern "C" int mma_nc_aggregate_fwd(const int32_t *rowptr, const int32_t *col, i
 extern "C" int mma_nc_aggregate_bwd_dst(const int32_t *rowptr, const int32_t *col, int64_t N, int64_t E,
                                         const float *X, int64_t ldx, const float *PA, int64_t ldpa,
                                         const float *QA, int64_t ldqa, int F, int A, const int32_t *act_kinds,
-                                        const int32_t *comb_kinds, const float *keep, float p_drop, uint64_t seed,
+                                        const int32_t *comb_kinds, const float *keep, float p_drop, uint64_t seed, const uint64_t *seed_dev,
                                         const float *S_saved, const float *dOUT, float *gS, float *dXdir,
                                         float *dPA, int64_t lddpa, mma_stream_t stream) {
     NcParams p;
-    int rc = nc_fill(p, rowptr, col, N, E, X, ldx, PA, ldpa, QA, ldqa, F, A, act_kinds, comb_kinds, keep, p_drop, seed);
+    int rc = nc_fill(p, rowptr, col, N, E, X, ldx, PA, ldpa, QA, ldqa, F, A, act_kinds, comb_kinds, keep, p_drop, seed,
+                     seed_dev);
     if (rc != MMA_OK) return rc;
     if (!comb_kinds || !S_saved || !dOUT || !gS || !dXdir || !dPA) return MMA_ERR_INVALID;
     p.S_saved = S_saved; p.dOUT = dOUT; p.gS_w = gS; p.dXdir = dXdir; p.dPA = dPA; p.lddpa = lddpa; p.lddx = F;
@@ -433,11 +436,12 @@ extern "C" int mma_nc_aggregate_bwd_dst(const int32_t *rowptr, const int32_t *co
 extern "C" int mma_nc_aggregate_bwd_src(const int32_t *colptr, const int32_t *row, const int32_t *eid,
                                         int64_t N, int64_t E, const float *X, int64_t ldx, const float *PA,
                                         int64_t ldpa, const float *QA, int64_t ldqa, int F, int A,
-                                        const int32_t *act_kinds, const float *keep, float p_drop, uint64_t seed,
+                                        const int32_t *act_kinds, const float *keep, float p_drop, uint64_t seed, const uint64_t *seed_dev,
                                         const float *gS, float *dQA, int64_t lddqa, float *dXnbr, int64_t lddx,
                                         mma_stream_t stream) {
     NcParams p;
-    int rc = nc_fill(p, colptr, row, N, E, X, ldx, PA, ldpa, QA, ldqa, F, A, act_kinds, nullptr, keep, p_drop, seed);
+    int rc = nc_fill(p, colptr, row, N, E, X, ldx, PA, ldpa, QA, ldqa, F, A, act_kinds, nullptr, keep, p_drop, seed,
+                     seed_dev);
     if (rc != MMA_OK) return rc;
     if ((E > 0 && !eid) || !gS || !dQA || !dXnbr) return MMA_ERR_INVALID;
     p.eid = eid; p.gS_r = gS; p.dQA = dQA; p.lddqa = lddqa; p.dXnbr = dXnbr; p.lddx = lddx;

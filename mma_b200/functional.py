@@ -272,8 +272,10 @@ class _NcAggregate(torch.autograd.Function):
     """All A masked neighbour sums + combine of node_classification/layers.py:201-728 (K2)."""
 
     @staticmethod
-    def forward(ctx, X, PA, QA, nbr, acts: tuple, combs: tuple, keep, p_drop: float, seed: int):
+    def forward(ctx, X, PA, QA, nbr, acts: tuple, combs: tuple, keep, p_drop: float, seed: int, seed_dev=None):
         dev = _lib.require_cuda(X, PA, QA, nbr.rowptr)
+        if seed_dev is not None:
+            seed_dev = seed_dev.clone()      # this call's seed: the backward must see the same value
         X, PA, QA = _c(X), _c(PA), _c(QA)
         N, F = X.shape
         A = len(acts)
@@ -290,15 +292,15 @@ class _NcAggregate(torch.autograd.Function):
             _lib.check(_lib.lib().mma_nc_aggregate_fwd(
                 _lib.ptr(nbr.rowptr), _lib.ptr(nbr.col), N, nbr.E, _lib.ptr(X), X.stride(0),
                 _lib.ptr(PA), PA.stride(0), _lib.ptr(QA), QA.stride(0), F, A, ak, ck, _lib.ptr(keep),
-                float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.ptr(OUT), _lib.ptr(S),
+                float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.ptr(seed_dev), _lib.ptr(OUT), _lib.ptr(S),
                 _lib.stream_ptr(dev)), "mma_nc_aggregate_fwd")
         ctx.nbr, ctx.cfg = nbr, (acts, combs, p_drop, seed)
-        ctx.save_for_backward(X, PA, QA, keep, S)
+        ctx.save_for_backward(X, PA, QA, keep, S, seed_dev)
         return OUT
 
     @staticmethod
     def backward(ctx, dOUT):
-        X, PA, QA, keep, S = ctx.saved_tensors
+        X, PA, QA, keep, S, seed_dev = ctx.saved_tensors
         nbr = ctx.nbr
         acts, combs, p_drop, seed = ctx.cfg
         dev = dOUT.device
@@ -318,25 +320,27 @@ class _NcAggregate(torch.autograd.Function):
             _lib.check(l.mma_nc_aggregate_bwd_dst(
                 _lib.ptr(nbr.rowptr), _lib.ptr(nbr.col), N, nbr.E, _lib.ptr(X), X.stride(0),
                 _lib.ptr(PA), PA.stride(0), _lib.ptr(QA), QA.stride(0), F, A, ak, ck, _lib.ptr(keep),
-                float(p_drop), sd, _lib.ptr(S), _lib.ptr(dOUT), _lib.ptr(gS), _lib.ptr(dXdir),
+                float(p_drop), sd, _lib.ptr(seed_dev), _lib.ptr(S), _lib.ptr(dOUT), _lib.ptr(gS), _lib.ptr(dXdir),
                 _lib.ptr(dPA), A * F, _lib.stream_ptr(dev)), "mma_nc_aggregate_bwd_dst")
         with _lib.kernel_scope("mma_nc_aggregate_bwd_src", dev):
             _lib.check(l.mma_nc_aggregate_bwd_src(
                 _lib.ptr(nbr.colptr), _lib.ptr(nbr.row_t), _lib.ptr(nbr.perm_t), N, nbr.E,
                 _lib.ptr(X), X.stride(0), _lib.ptr(PA), PA.stride(0), _lib.ptr(QA), QA.stride(0), F, A, ak,
-                _lib.ptr(keep), float(p_drop), sd, _lib.ptr(gS), _lib.ptr(dQA), A * F, _lib.ptr(dXn), F,
+                _lib.ptr(keep), float(p_drop), sd, _lib.ptr(seed_dev), _lib.ptr(gS), _lib.ptr(dQA), A * F, _lib.ptr(dXn), F,
                 _lib.stream_ptr(dev)), "mma_nc_aggregate_bwd_src")
-        return dXdir + dXn, dPA, dQA, None, None, None, None, None, None
+        return dXdir + dXn, dPA, dQA, None, None, None, None, None, None, None
 
 
 def nc_aggregate(X: Tensor, PA: Tensor, QA: Tensor, nbr, acts: Sequence[int], combs: Sequence[int],
-                 keep: Optional[Tensor] = None, p_drop: float = 0.0, seed: int = 0) -> Tensor:
+                 keep: Optional[Tensor] = None, p_drop: float = 0.0, seed: int = 0,
+                 seed_dev: Optional[Tensor] = None) -> Tensor:
     """OUT[a] = combine_a(x_i, sum_j act_a(PA[i,a] + QA[j,a]) * keepscale * x_j)  -> [A, N, F].
-    `nbr` is a NeighbourLists (CSR of add_all; edge id == CSR position)."""
+    `nbr` is a NeighbourLists (CSR of add_all; edge id == CSR position).  `seed_dev` (int64 [1] on the device): the
+    dropout key is read from it at run time instead of `seed` (CUDA-graph replays then draw fresh masks)."""
     if len(acts) > _lib.MAX_AGGR:
         raise _lib.MMAError("more than 8 aggregators in one call")
     return _NcAggregate.apply(X, PA, QA, nbr, tuple(int(a) for a in acts), tuple(int(c) for c in combs),
-                              keep, float(p_drop), int(seed))
+                              keep, float(p_drop), int(seed), seed_dev)
 
 
 # ------------------------------------------------------------------------------------------

@@ -138,6 +138,9 @@ class MMA(Module):
         self._nbr = None
         self._inject_keep = None        # test hook: dict name -> keep-scale [E, F] in neighbour-list order
         self.last_seed = None
+        self.device_seed = False        # True: the dropout seed lives in a device tensor advanced ON the device at every
+                                        # call, so a train step captured in a CUDA graph draws a fresh mask per replay
+        self._seed_dev = None
 
     def reset_parameters(self):
         stdv = 1. / math.sqrt(self.weight.size(0))
@@ -161,6 +164,14 @@ class MMA(Module):
         s = (torch.initial_seed() + 0x9E3779B97F4A7C15 * (self._uid * 1000003 + self._calls)) & 0xFFFFFFFFFFFFFFFF
         self.last_seed = s
         return s
+
+    def _next_seed_dev(self, dev):
+        """Device-resident seed, advanced by a device-side add (capturable; create it before the capture)."""
+        if self._seed_dev is None or self._seed_dev.device != dev:
+            s = (torch.initial_seed() + 0x9E3779B97F4A7C15 * (self._uid * 1000003)) & 0x7FFFFFFFFFFFFFFF
+            self._seed_dev = torch.tensor([s], dtype=torch.int64, device=dev)
+        self._seed_dev.add_(0x9E3779B97F4A7C15 - (1 << 64))     # golden-ratio increment, wraps modulo 2^64
+        return self._seed_dev
 
     def aggregate_all(self, input, names):
         """[A, N, F]: every named aggregator in one K2 launch (chunks of 8)."""
@@ -188,8 +199,9 @@ class MMA(Module):
             keep = None
             if self._inject_keep is not None:
                 keep = torch.stack([self._inject_keep[nm] for nm in chunk]).to(input.device)
+            seed_dev = self._next_seed_dev(input.device) if (self.device_seed and keep is None) else None
             out = MF.nc_aggregate(input, PA, QA, nbr, acts, combs, keep=keep, p_drop=self.dropout,
-                                  seed=self._next_seed())
+                                  seed=0 if seed_dev is not None else self._next_seed(), seed_dev=seed_dev)
             parts = []
             for a, f in enumerate(fam):
                 o = out[a]
