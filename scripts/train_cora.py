@@ -3,11 +3,13 @@
 --epochs=200 --weight_decay=3e-4 --hidden=64 --dropout=0.75`) through the drop-in modules
 (`mma_b200.node_classification.models.MMAConv` = GraphConvolution -> ReLU -> dropout -> MMA -> log_softmax).
 
-    python scripts/train_cora.py [--epochs 200] [--dropout 0.75]
+    python scripts/train_cora.py [--epochs 200] [--dropout 0.75] [--graph]
 
 The dataset comes from the committed data fixture tests/golden/cora_dataset.pt (what `utils.load_data("cora")`
-returns; written by oracle/make_cora_fixture.py in the build container).  Eager launches (the K2 dropout seed is a
-host-side counter, so a captured step would replay one mask).  No CPU path: the layers raise without CUDA.
+returns; written by oracle/make_cora_fixture.py in the build container).  `--graph` replays the whole train step
+(forward, loss, backward, Adam) as ONE CUDA graph: the layers' dropout seeds then live on the device and are advanced
+inside the graph (`MMA.device_seed`), so every replay draws fresh masks like an eager epoch.  No CPU path: the layers
+raise without CUDA.
 """
 from __future__ import annotations
 
@@ -60,7 +62,9 @@ def run(args, init=None, verbose=True):
     add_all, adj, x, labels, itr, iva, ite = load_fixture(device)
     torch.manual_seed(args.seed)
     model = build_model(add_all, x.shape[1], int(labels.max()) + 1, args, device, init)
-    opt = torch.optim.Adam(model.parameters(), lr=args.lr, weight_decay=args.weight_decay)     # train.py:66-67
+    use_graph = bool(getattr(args, "graph", False))
+    opt = torch.optim.Adam(model.parameters(), lr=args.lr, weight_decay=args.weight_decay,     # train.py:66-67
+                           capturable=use_graph)
     hist = []
 
     def train_step():
@@ -75,10 +79,39 @@ def run(args, init=None, verbose=True):
         with torch.no_grad():
             return model(x, adj)
 
+    graph = None
+    if use_graph:
+        model.gc2.device_seed = True
+        snap = [p.detach().clone() for p in model.parameters()]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                          # warm-up outside the capture (handles, caches, Adam state)
+            for _ in range(3):
+                train_step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        with torch.no_grad():                                  # back to the initial parameters and a fresh optimiser state
+            for p, q in zip(model.parameters(), snap):
+                p.copy_(q)
+            for st in opt.state.values():
+                st["step"].zero_(); st["exp_avg"].zero_(); st["exp_avg_sq"].zero_()
+        opt.zero_grad(set_to_none=False)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            model.train()
+            for p in model.parameters():
+                if p.grad is not None:
+                    p.grad.zero_()
+            g_out = model(x, adj)
+            g_loss = F.nll_loss(g_out[itr], labels[itr])
+            g_loss.backward(); opt.step()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for ep in range(args.epochs):
-        out, loss = train_step()
+        if graph is not None:
+            graph.replay(); out, loss = g_out, g_loss
+        else:
+            out, loss = train_step()
         acc = accuracy(out[itr], labels[itr])
         ev = eval_step()                                       # train.py:79-83: validation in eval mode
         hist.append((loss.item(), acc, F.nll_loss(ev[iva], labels[iva]).item(), accuracy(ev[iva], labels[iva])))
@@ -91,7 +124,7 @@ def run(args, init=None, verbose=True):
     test = (F.nll_loss(ev[ite], labels[ite]).item(), accuracy(ev[ite], labels[ite]))
     if verbose:
         print(f"Test set results: loss= {test[0]:.4f} accuracy= {test[1]:.4f}   ({sec * 1e3:.2f} ms per epoch "
-              f"incl. the evaluation pass)")
+              f"incl. the evaluation pass{', train step as one CUDA graph' if graph is not None else ''})")
     return torch.tensor(hist, dtype=torch.float64), test, sec
 
 
@@ -106,6 +139,7 @@ def parser():
     p.add_argument("--aggregators", type=str, default="mean,mean2")
     p.add_argument("--activation", type=str, default="new_sigmoid")
     p.add_argument("--k", type=int, default=2)
+    p.add_argument("--graph", action="store_true", help="replay the train step as one CUDA graph (device-resident seeds)")
     return p
 
 

@@ -70,3 +70,16 @@ def test_cora_readme_run_reaches_reference_accuracy():
           f"(reference {ref['sec_per_epoch']:.1f} s/epoch on {ref['threads']} CPU threads)")
     assert hist[-1, 0] < 0.5 * hist[0, 0]
     assert test[1] >= ref_acc - 0.03, f"test accuracy {test[1]:.4f} vs the reference's {ref_acc:.4f}"
+
+
+@pytest.mark.gpu
+def test_cora_readme_run_as_cuda_graph():
+    """The same run with the train step replayed as one CUDA graph (device-resident dropout seeds)."""
+    import train_cora
+    ref = load_golden("cora_train_ref_full.pt")
+    hist, test, sec = train_cora.run(_args(graph=True), verbose=False)
+    print(f"cora README run, CUDA-graph train step: test accuracy {test[1]:.4f} (reference {ref['test'][1]:.4f}), "
+          f"{sec * 1e3:.2f} ms/epoch")
+    assert hist[-1, 0] < 0.5 * hist[0, 0] and len(set(hist[-20:, 0].tolist())) > 10      # still stochastic: fresh masks
+    assert test[1] >= ref["test"][1] - 0.03
+

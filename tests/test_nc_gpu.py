@@ -155,3 +155,52 @@ def test_model_trains_on_cora_topology():
         loss = torch.nn.functional.nll_loss(model(feats, adj)[:500], labels[:500])
         loss.backward(); opt.step(); losses.append(loss.item())
     assert all(torch.isfinite(torch.tensor(losses))) and losses[-1] < losses[0]
+
+
+def test_k2_device_seed_cuda_graph_replay_draws_fresh_masks():
+    """MMA.device_seed: the dropout key is read from a device tensor that is advanced on the device at every call, so a
+    captured layer call draws a new mask per replay; forward and backward of one call see the same key (the gradient
+    of a replay matches an eager call made with that key)."""
+    from mma_b200.node_classification.layers import MMA, _ALL
+    topo = load_golden("planetoid_topology.pt")["cora"]
+    rowptr, col = topo["rowptr"].long(), topo["col"].long()
+    n, Fd, C = rowptr.numel() - 1, 16, 7
+    add_all = [col[rowptr[i]:rowptr[i + 1]].numpy() for i in range(n)]
+    from oracle import restate
+    adj = restate.csr_to_sparse_adj(rowptr, col, n).cuda()
+    torch.manual_seed(3)
+    new = lambda *s: torch.nn.Parameter(torch.empty(*s, device="cuda"))
+    layer = MMA(add_all, "new_sigmoid", 2, Fd, C, new(Fd, C), new(C), *[new(2 * Fd, Fd) for _ in _ALL], 0.5,
+                ["mean", "max2"], "cuda")
+    layer.device_seed = True
+    x = torch.rand(n, Fd, device="cuda").requires_grad_()
+    gy = torch.randn(n, C, device="cuda")
+
+    def call():
+        y = layer(x, adj)
+        (gx,) = torch.autograd.grad(y, [x], gy)
+        return y, gx
+
+    side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            call()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        y_s, gx_s = call()
+    outs = []
+    for _ in range(3):
+        g.replay()
+        torch.cuda.synchronize()
+        seed_used = int(layer._seed_dev.item())
+        outs.append((y_s.clone(), gx_s.clone(), seed_used))
+    assert not torch.equal(outs[0][0], outs[1][0]) and not torch.equal(outs[1][0], outs[2][0]), "replays must differ"
+    assert len({o[2] for o in outs}) == 3
+    # an eager call with the key of the last replay reproduces it bit for bit (same kernels, same key)
+    layer.device_seed = False
+    layer._next_seed = lambda: outs[2][2]
+    y_e, gx_e = call()
+    assert torch.equal(y_e, outs[2][0]) and torch.equal(gx_e, outs[2][1])
+
