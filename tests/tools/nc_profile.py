@@ -7,7 +7,7 @@ from oracle import restate
 dev = torch.device("cuda", 0)
 ORDER = ["moment_3", "sum", "sum2", "sum3", "sum4", "mean", "mean2", "mean3", "mean4", "max", "max2", "max3",
          "max4", "min", "min2", "min3", "min4", "softmax", "softmin", "std", "normalized_mean"]
-topo = torch.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "planetoid_topology.pt"))
+topo = torch.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "golden", "planetoid_topology.pt"))
 which, Fd, C, names, p = (sys.argv[1] if len(sys.argv) > 1 else "pubmed"), 16, 3, ["min", "min2", "min3", "min4"], 0.5
 if which == "cora":
     Fd, C, names, p = 64, 7, ["mean", "mean2"], 0.75

@@ -118,7 +118,7 @@ def zinc_case():
           f"({E / min(t_eager, t_graph if t_graph == t_graph else t_eager):6.2f} M edges/s) | CPU port ({torch.get_num_threads()} threads) {t_cpu:11.1f} us  -> x{t_cpu / t_eager:.0f}")
 
 
-topo = torch.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
+topo = torch.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "golden",
                                "planetoid_topology.pt"))
 nc_case("c1 Cora   MMA layer (mean,mean2; hidden 64 -> 7; dropout 0.75)", topo["cora"], 64, 7, ["mean", "mean2"], 0.75)
 zinc_case()
