@@ -47,3 +47,31 @@ def test_no_oracle_import_in_product_path():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "from oracle" not in src and "import oracle" not in src, f
+
+
+def test_integration_stub_matches_the_abi():
+    """The ctypes stub a maintainer of the reference would paste must carry the argument list
+    of include/mma_b200.h as bound in mma_b200/_lib.py -- same types, same count, in the declaration and in the call."""
+    import ctypes as C
+    import os
+    import re
+    from mma_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    txt = open(os.path.join(root, "INTEGRATION.md")).read()
+    body = re.search(r"lib\.mmconv_aggregate_fwd\.argtypes = \[(.*?)\]\s*#[^\n]*\nKIND", txt, re.S).group(1)
+    toks = [t.strip() for t in re.sub(r"#[^\n]*", "", body).replace("\n", " ").split(",") if t.strip()]
+    names = {"vp": C.c_void_p, "i64": C.c_int64, "i32": C.c_int, "f32": C.c_float, "u64": C.c_uint64}
+    assert [names[t] for t in toks] == list(_lib._SIGS["mmconv_aggregate_fwd"][0])
+    call = re.search(r"rc = lib\.mmconv_aggregate_fwd\((.*?)\)\n    assert rc == 0", txt, re.S).group(1)
+    call = re.sub(r"#[^\n]*", "", call)
+    depth, n = 0, 1
+    for ch in call:
+        depth += ch in "([" 
+        depth -= ch in ")]"
+        n += (ch == "," and depth == 0)
+    assert n == len(toks)
+    # the header declares exactly the parameters that are bound
+    hdr = open(os.path.join(root, "include", "mma_b200.h")).read()
+    decl = re.search(r"\nint mmconv_aggregate_fwd\((.*?)\);", hdr, re.S).group(1)
+    assert len([a for a in decl.split(",") if a.strip()]) == len(toks)
+

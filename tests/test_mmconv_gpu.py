@@ -455,3 +455,35 @@ def test_cuda_graph_replay_draws_fresh_dropout():
         torch.cuda.synchronize()
         for a, b in zip(outs, eager[k]):
             assert torch.equal(a, b), f"replay {k} differs from eager call {k}"
+
+
+def test_integration_md_ctypes_stub_runs():
+    """The binding INTEGRATION.md section 2 shows (plain ctypes over the C ABI, pasted into the reference's
+    MMAConv.aggregate) is executed as written and reproduces the verbatim reference's output."""
+    import os
+    import re
+    import types
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    txt = open(os.path.join(root, "INTEGRATION.md")).read()
+    code = re.search(r"```python\n(import ctypes as C, torch\n.*?)```", txt, re.S).group(1)
+    ns = {}
+    cwd = os.getcwd()
+    os.chdir(root)                              # the stub loads "mma_b200/libmma_b200.so" relative to the repo root
+    try:
+        exec(compile(code, "INTEGRATION.md", "exec"), ns)
+    finally:
+        os.chdir(cwd)
+    gd = load_golden("aggregate_all.pt")
+    inputs, index, n = gd["inputs"], gd["index"], gd["n"]
+    E, T, F_in = inputs.shape
+    me = types.SimpleNamespace(avg_deg=gd["avg_deg"], aggregators=gd["aggregators"], scalers=gd["scalers"])
+    out = ns["aggregate"](me, inputs.cuda(), index.cuda(), n)
+    torch.cuda.synchronize()
+    A, S = len(gd["aggregators"]), len(gd["scalers"])
+    ov, rv = out.cpu().view(n, T, S, A, F_in), gd["out"].view(n, T, S, A, F_in)
+    for ai, a in enumerate(gd["aggregators"]):
+        if a in ("min", "max"):
+            bitexact(ov[:, :, :, ai], rv[:, :, :, ai], f"stub:{a}")
+        else:
+            close(ov[:, :, :, ai], rv[:, :, :, ai], what=f"stub:{a}")
+
