@@ -25,6 +25,39 @@ def test_every_declared_symbol_is_exported_and_bound():
     assert _lib.lib().mma_b200_version() >= 100
 
 
+def test_binding_table_matches_every_declaration():
+    """Parameter by parameter: the C type of every declared argument against the ctypes type it is bound with."""
+    text = open(os.path.join(ROOT, "include", "mma_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    checked = 0
+    for name, args in re.findall(r"\b(?:int|const char \*)\s*(mma\w+|mmconv\w+)\s*\((.*?)\)\s*;", text, flags=re.S):
+        params = [a.strip() for a in args.split(",") if a.strip() and a.strip() != "void"]
+        bound = _lib._SIGS[name][0]
+        assert len(params) == len(bound), f"{name}: {len(params)} declared, {len(bound)} bound"
+        for prm, ct in zip(params, bound):
+            prm = re.sub(r"^const\s+", "", prm)
+            if "*" in prm:
+                want = (ctypes.c_void_p, ctypes.c_char_p)
+                ok = ct in want or (hasattr(ct, "_type_"))          # POINTER(c_size_t) for out-parameters
+            elif prm.startswith("uint64_t"):
+                ok = ct is ctypes.c_uint64
+            elif prm.startswith("int64_t"):
+                ok = ct is ctypes.c_int64
+            elif prm.startswith("size_t"):
+                ok = ct is ctypes.c_size_t
+            elif prm.startswith("uint32_t"):
+                ok = ct is ctypes.c_uint32
+            elif prm.startswith("float"):
+                ok = ct is ctypes.c_float
+            elif prm.startswith("mma_stream_t"):
+                ok = ct is ctypes.c_void_p
+            else:
+                ok = ct is ctypes.c_int and re.match(r"(int|int32_t)\b", prm) is not None
+            assert ok, f"{name}: parameter '{prm}' bound as {ct}"
+            checked += 1
+    assert checked > 250
+
+
 def test_argument_validation_without_gpu():
     l = _lib.lib()
     n = ctypes.c_size_t(0)
