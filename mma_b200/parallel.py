@@ -151,6 +151,32 @@ def allreduce_grads(params, group=None) -> None:
         off += g.numel()
 
 
+def split_graph_batch(edge_index: Tensor, batch: Tensor, rank: int, world: int, *node_tensors: Tensor,
+                      edge_tensors: Sequence[Tensor] = ()):
+    """Scheme (ii) for a PyG-style batch of small graphs (ZINC, graph_regression/mma.py:52-54): the batch is block
+    diagonal, so rank r simply takes a contiguous run of whole graphs -- no halo, no exchange in the layer; only the
+    weight gradients are summed afterwards (`allreduce_grads`).  `batch` [N] is the sorted graph id of every node.
+    Returns (edge_index_local [2, E_r] renumbered from 0, batch_local [N_r] renumbered from 0, node_slice, edge_ids,
+    node tensors sliced to the rank's nodes, edge tensors sliced to its edges).  Pure index arithmetic (CPU or CUDA)."""
+    if batch.numel() and bool((batch[1:] < batch[:-1]).any()):
+        raise ValueError("split_graph_batch expects nodes numbered graph by graph (sorted `batch`)")
+    n_graphs = int(batch.max()) + 1 if batch.numel() else 0
+    per = (n_graphs + world - 1) // world
+    g_lo, g_hi = min(rank * per, n_graphs), min((rank + 1) * per, n_graphs)
+    counts = torch.bincount(batch, minlength=n_graphs)
+    ptr = torch.zeros(n_graphs + 1, dtype=torch.long, device=batch.device)
+    ptr[1:] = torch.cumsum(counts, 0)
+    n_lo, n_hi = int(ptr[g_lo]), int(ptr[g_hi])
+    dst = edge_index[1]
+    eids = torch.nonzero((dst >= n_lo) & (dst < n_hi), as_tuple=False).flatten()      # original relative order
+    ei = edge_index.index_select(1, eids) - n_lo
+    if ei.numel() and (int(ei.min()) < 0 or int(ei.max()) >= n_hi - n_lo):
+        raise ValueError("an edge connects two graphs of the batch: it is not block diagonal")
+    nodes = slice(n_lo, n_hi)
+    return (ei, batch[nodes] - g_lo, nodes, eids, tuple(t[nodes] for t in node_tensors),
+            tuple(t.index_select(0, eids) for t in edge_tensors))
+
+
 # ------------------------------------------------------------------------------------------
 # sharded fused aggregate
 # ------------------------------------------------------------------------------------------

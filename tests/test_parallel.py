@@ -73,6 +73,33 @@ def test_partition_bounds_single_process():
     assert sum(s.stop - s.start for s in _slices(100, 3)) == 100
 
 
+def test_split_graph_batch_covers_every_graph_once():
+    """Scheme (ii), config 2: a batch of small graphs is split by whole graphs -- every node and edge lands on exactly
+    one rank, renumbered from 0, in its original relative order."""
+    from mma_b200.parallel import split_graph_batch
+    from oracle import restate
+    ei, batch = restate.zinc_like_batch(13, seed=1)
+    n, E = batch.numel(), ei.shape[1]
+    x = torch.arange(n).float().unsqueeze(1)
+    ea = torch.arange(E)
+    for world in (1, 2, 3, 5):
+        seen_nodes, seen_edges = [], []
+        for r in range(world):
+            e_l, b_l, nodes, eids, (x_l,), (ea_l,) = split_graph_batch(ei, batch, r, world, x, edge_tensors=(ea,))
+            assert torch.equal(x_l, x[nodes]) and torch.equal(ea_l, eids)
+            assert torch.equal(e_l + nodes.start, ei[:, eids]) and torch.all(eids[1:] > eids[:-1])
+            if b_l.numel():
+                assert int(b_l.min()) == 0 and torch.equal(b_l + int(batch[nodes.start]), batch[nodes])
+            seen_nodes.append(torch.arange(nodes.start, nodes.stop)); seen_edges.append(eids)
+        assert torch.equal(torch.cat(seen_nodes), torch.arange(n))
+        assert torch.equal(torch.sort(torch.cat(seen_edges)).values, torch.arange(E))
+    with pytest.raises(ValueError):
+        split_graph_batch(ei, batch.flip(0), 0, 2)
+    bad = ei.clone(); bad[0, 0] = n - 1                         # an edge between the first and the last graph
+    with pytest.raises(ValueError):
+        split_graph_batch(bad, batch, 0, 2)
+
+
 def test_config5_partition_balances_edges_and_rows():
     """config 5's generator (bench.py): power-law in-degrees dealt to random node ids.  Destination ranges balanced by
     in-edge count must then also hold similar row counts -- the all-gathered Q layout is padded to the largest range."""
@@ -192,3 +219,58 @@ def test_sharded_fused_layer_matches_single_gpu():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     mp.spawn(_gpu_layer_worker, args=(2, _free_port(), 6000, 90000, 128), nprocs=2, join=True)
+
+
+def _gpu_dp_worker(rank, world, port):
+    """Scheme (ii), config 2: a ZINC-shaped batch split by whole graphs, MMAConv (towers 5, edge features) per rank on
+    its graphs, weight gradients all-reduced -- against the full batch on one GPU with the same injected masks."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import mma_b200
+        from mma_b200 import parallel as par
+        from oracle import restate
+        ei, batch = restate.zinc_like_batch(24, seed=2)
+        n, E = batch.numel(), ei.shape[1]
+        g = torch.Generator().manual_seed(4)
+        x = torch.randn(n, 75, generator=g)
+        ea = torch.randn(E, 50, generator=g)
+        gy = torch.randn(n, 75, generator=g)
+        keep = (torch.rand(E, 5, 75, generator=g) < 0.5).float() * 2
+        torch.manual_seed(6)
+        conv = mma_b200.MMAConv(75, 75, ["min", "max"], ["identity", "amplification", "linear"],
+                                restate.degree_histogram(ei, n), edge_dim=50, towers=5).to(dev)
+        params = list(conv.parameters()) + conv.mask_parameters()
+        # the whole batch on this GPU
+        xf = x.to(dev).requires_grad_()
+        conv._inject_keep = keep.to(dev)
+        yf = conv(xf, ei.to(dev), ea.to(dev))
+        gf = torch.autograd.grad(yf, [xf] + params, gy.to(dev), allow_unused=True)
+        # this rank's graphs
+        e_l, b_l, nodes, eids, (x_l, gy_l), (ea_l, keep_l) = par.split_graph_batch(ei, batch, rank, world, x, gy,
+                                                                                    edge_tensors=(ea, keep))
+        xl = x_l.to(dev).requires_grad_()
+        conv._inject_keep = keep_l.to(dev)
+        yl = conv(xl, e_l.to(dev), ea_l.to(dev))
+        gl = torch.autograd.grad(yl, [xl] + params, gy_l.to(dev), allow_unused=True)
+        tol = lambda a: 1e-5 * a.abs().max().item() + 1e-30
+        assert (yl - yf[nodes]).abs().max().item() <= tol(yf), "per-rank output rows"
+        assert (gl[0] - gf[0][nodes]).abs().max().item() <= tol(gf[0]), "per-rank dx"
+        for p_, a in zip(params, gl[1:]):
+            p_.grad = None if a is None else a.clone()
+        par.allreduce_grads(params)
+        for p_, b in zip(params, gf[1:]):
+            if b is not None:
+                assert (p_.grad - b).abs().max().item() <= tol(b), "all-reduced weight gradient"
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_graph_batch_data_parallel_matches_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    mp.spawn(_gpu_dp_worker, args=(2, _free_port()), nprocs=2, join=True)
+
