@@ -74,6 +74,33 @@ def test_scatter_semantics_edge_cases():
     assert e.shape == (2, 3) and e.abs().sum() == 0
 
 
+def test_scatter_restatement_vs_sequential_c_property():
+    """Property test (hypothesis): the torch restatement of torch_scatter's reductions against the sequential C ground
+    truth on random inputs drawn from a small value set -- many exact ties, +-0, NaN, empty and single-edge rows."""
+    from hypothesis import given, settings, strategies as st
+
+    vals = st.sampled_from([0.0, -0.0, 1.0, -1.0, 2.5, -2.5, 1e-30, float("nan"), 3.0, 3.0])
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 6), st.integers(0, 40), st.integers(1, 5), st.data())
+    def run(n, E, F, data):
+        src = torch.tensor(data.draw(st.lists(vals, min_size=E * F, max_size=E * F)), dtype=torch.float32).view(E, F)
+        index = torch.tensor(data.draw(st.lists(st.integers(0, n - 1), min_size=E, max_size=E)), dtype=torch.int64)
+        for is_max in (False, True):
+            o, a = restate._minmax_first(src, index, n, is_max)
+            o2, a2 = seq.scatter_minmax(src, index, n, is_max)
+            assert torch.equal(a, a2), (src, index, is_max)
+            assert torch.equal(torch.nan_to_num(o, nan=-7.0).view(torch.int32),
+                               torch.nan_to_num(o2, nan=-7.0).view(torch.int32)), (src, index, is_max)
+        finite = torch.nan_to_num(src, nan=0.5)
+        for mean in (False, True):
+            a = restate.scatter(finite, index, 0, None, n, "mean" if mean else "sum")
+            b = seq.scatter_sum(finite, index, n, mean=mean)
+            assert torch.allclose(a, b, rtol=1e-6, atol=1e-37), (finite, index, mean)
+
+    run()
+
+
 @pytest.mark.parametrize("name", ["nc_small_mean.pt", "nc_small_min4.pt", "nc_small_mixed.pt",
                                   "nc_small_sigmoid.pt", "nc_cora_mean_f8.pt"])
 def test_node_classification_restatement(name):
