@@ -36,6 +36,7 @@ import torch.nn.functional as F
 from torch import Tensor
 from torch.nn import ModuleList, ReLU, Sequential
 
+from .. import _lib
 from .. import functional as MF
 from .. import fused_layer
 from ..graph import Graph, cached_graph
@@ -174,6 +175,7 @@ class MMAConv(torch.nn.Module):
     # ------------------------------------------------------------------ forward
     def forward(self, x: Tensor, edge_index, edge_attr: Optional[Tensor] = None) -> Tensor:
         T, F_in = self.towers, self.F_in
+        self._check_names()                     # ValueError first, whatever the device (message(), :150-154)
         if self.divide_input:
             xt = x.view(-1, T, F_in)
         else:
@@ -370,6 +372,12 @@ class MMAConv(torch.nn.Module):
 
     def aggregate(self, inputs: Tensor, index: Tensor, dim_size: Optional[int] = None) -> Tensor:
         """mma_conv.py:159-196, callable on its own: inputs [E,T,F], index [E] -> [N,T,S*A*F]."""
+        for a in self.aggregators:              # :164-174 / :182-194: exact names, ValueError whatever the device
+            if a not in _lib.AGGR_KINDS:
+                raise ValueError(f'Unknown aggregator "{a}".')
+        for s_ in self.scalers:
+            if s_ not in _lib.SCALER_KINDS:
+                raise ValueError(f'Unknown scaler "{s_}".')
         if not inputs.is_cuda:
             raise RuntimeError("mma_b200.MMAConv.aggregate needs CUDA tensors (no CPU fallback)")
         n = int(index.max()) + 1 if dim_size is None else int(dim_size)
