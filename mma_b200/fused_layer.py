@@ -18,6 +18,7 @@ The GEMMs are 3xTF32 (fp32-accurate, see csrc/gemm_tf32x3.cu).  No CPU path.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -28,9 +29,6 @@ from . import tc_gemm as tg
 from . import functional as MF
 from .functional import cumulative_scale_factors
 from .graph import Graph
-
-
-import os
 
 # Run the backward's reduce-scatter on a side stream under the weight-gradient GEMM.  Off by default: NCCL's
 # CTAs take SMs away from the persistent one-CTA-per-SM GEMM, whose displaced CTAs then run as a second wave
