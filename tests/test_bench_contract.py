@@ -35,3 +35,19 @@ def test_algorithmic_bytes_match_design():
     assert abs((ab["fwd"] + ab["bwd"]) / 1e9 - 67.1) < 0.1
     s4 = bench.algo_bytes(N, E, F, A=5, S=4, n_mm=2, std=True)
     assert abs((s4["fwd"] + s4["bwd"]) / 1e9 - 97.8) < 0.2            # SURVEY's figure with the scaler blocks materialised
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank0():
+    """N > 1: the driver launches the reference arm exactly like ours (torch.distributed.run, one process per GPU);
+    rank 0 alone runs the CPU path and prints the line, the other ranks exit 0 without work."""
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "bench.py"),
+                          "--impl", "reference", "--gpus", "2", "--config", "c4s", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, out.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
