@@ -35,6 +35,11 @@ from .graph import Graph
 # (measured: the GEMM took 2x as long, cancelling the overlap).
 OVERLAP_EXCHANGE = os.environ.get("MMA_OVERLAP_EXCHANGE", "0") == "1"
 
+# Parity hook (bench.py --verify, tests): when set to a dict, every forward leaves references to its raw aggregates
+# and arg indices there (Z in CSR-row order, arg_min / arg_max as CSR slots), so a sharded run can be compared bit for
+# bit with the single-GPU run.  None = off (the default; nothing is retained).
+KEEP_LAST: Optional[dict] = None
+
 
 class PostPlan:
     """Row ranges of equal in-degree (graph.buckets) -> tile / slab tables of the grouped GEMMs."""
@@ -188,6 +193,8 @@ class _FusedMMAConv(torch.autograd.Function):
             ct = plan.cum[:, plan.tail_bucket].t()                                                  # [nt, S]
             Yt = (Zt.unsqueeze(1) * ct.unsqueeze(2)).reshape(Zt.shape[0], S * K)
             out.index_copy_(0, nodes, (Yt @ Wy.t()) @ Wl.t() + XW.index_select(0, nodes))
+        if KEEP_LAST is not None:
+            KEEP_LAST.update(Z=Z, arg_min=arg_min, arg_max=arg_max, graph=graph)
         ctx.graph, ctx.sg, ctx.plan, ctx.cfg = graph, sg, plan, cfg
         ctx.has_R, ctx.has_b = R is not None, (bm is not None, bp is not None, bl is not None)
         need_sq = 4 in akinds or 5 in akinds

@@ -201,24 +201,33 @@ class Graph:
         return g
 
 
-_CACHE: "OrderedDict[tuple, Graph]" = OrderedDict()
-_CACHE_SIZE = 16
+_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
+_CACHE_SIZE = 8
 
 
 def cached_graph(edge_index: Tensor, num_nodes: int, sort_rows: bool = False) -> Graph:
-    """Graph for an `edge_index` tensor, cached on (storage pointer, shape, version, N).
-    A tensor mutated in place bumps `_version` and is rebuilt; pass a `Graph`
-    explicitly to the layers to bypass the cache altogether."""
-    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes),
-           str(edge_index.device), bool(sort_rows))
-    g = _CACHE.get(key)
-    if g is None:
-        g = Graph.from_edge_index(edge_index, num_nodes, sort_rows=sort_rows)
-        _CACHE[key] = g
-        while len(_CACHE) > _CACHE_SIZE:
-            _CACHE.popitem(last=False)
-    else:
-        _CACHE.move_to_end(key)
+    """Graph for an `edge_index` tensor, cached on (storage pointer, offset-free geometry, version, N).
+
+    The entry OWNS a reference to the key tensor: while it sits in the cache the tensor's storage cannot be
+    freed, so the CUDA caching allocator cannot hand the same address to another edge list (a per-step
+    `torch.randint(...)` or a new mini-batch of the same shape would otherwise hit a stale entry -- the Graph
+    itself drops its src/dst after build_transpose()).  A hit additionally requires the same storage
+    (`untyped_storage().data_ptr()`), geometry and `_version` (bumped by any in-place write, shared by
+    views).  Pass a `Graph` explicitly to the layers to bypass the cache altogether."""
+    key = (edge_index.data_ptr(), tuple(edge_index.shape), tuple(edge_index.stride()), str(edge_index.dtype),
+           int(num_nodes), str(edge_index.device), bool(sort_rows))
+    hit = _CACHE.get(key)
+    if hit is not None:
+        owner, version, g = hit
+        if (owner.untyped_storage().data_ptr() == edge_index.untyped_storage().data_ptr()
+                and version == edge_index._version):
+            _CACHE.move_to_end(key)
+            return g
+        del _CACHE[key]                          # mutated in place since: rebuild
+    g = Graph.from_edge_index(edge_index, num_nodes, sort_rows=sort_rows)
+    _CACHE[key] = (edge_index, edge_index._version, g)
+    while len(_CACHE) > _CACHE_SIZE:
+        _CACHE.popitem(last=False)
     return g
 
 
@@ -273,16 +282,26 @@ class SparseAdj:
         self.val_t = val.index_select(0, perm_t.to(torch.int64)).contiguous()
 
 
-_ADJ_CACHE: "OrderedDict[tuple, SparseAdj]" = OrderedDict()
+_ADJ_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
 
 
 def cached_adj(adj: Tensor) -> SparseAdj:
-    a = adj if adj.is_coalesced() else adj.coalesce()
-    key = (a.indices().data_ptr(), a.values().data_ptr(), a._nnz(), tuple(a.shape), str(a.device))
-    s = _ADJ_CACHE.get(key)
-    if s is None:
-        s = SparseAdj(a)
-        _ADJ_CACHE[key] = s
-        while len(_ADJ_CACHE) > 8:
-            _ADJ_CACHE.popitem(last=False)
+    """SparseAdj of a sparse COO adjacency, cached.  As in `cached_graph` the entry keeps the caller's tensor
+    alive (so its index/value storages cannot be recycled for another adjacency) and a hit requires the same
+    storages and versions; a non-coalesced `adj` is keyed by its OWN raw indices/values, never by the
+    temporaries of `coalesce()`."""
+    idx, val = adj._indices(), adj._values()
+    key = (idx.data_ptr(), val.data_ptr(), int(adj._nnz()), tuple(adj.shape), str(adj.device), bool(adj.is_coalesced()))
+    hit = _ADJ_CACHE.get(key)
+    if hit is not None:
+        owner, versions, s = hit
+        if (owner._indices().data_ptr() == idx.data_ptr() and owner._values().data_ptr() == val.data_ptr()
+                and versions == (idx._version, val._version)):
+            _ADJ_CACHE.move_to_end(key)
+            return s
+        del _ADJ_CACHE[key]
+    s = SparseAdj(adj)
+    _ADJ_CACHE[key] = (adj, (idx._version, val._version), s)
+    while len(_ADJ_CACHE) > 8:
+        _ADJ_CACHE.popitem(last=False)
     return s

@@ -41,8 +41,9 @@ def partition_bounds(dst: Tensor, num_nodes: int, world: int, balance: str = "ed
     if world < 1:
         raise ValueError("world must be >= 1")
     if balance == "nodes" or dst.numel() == 0:
-        per = (num_nodes + world - 1) // world
-        return [min(r * per, num_nodes) for r in range(world)] + [num_nodes]
+        if 0 < num_nodes < world:
+            raise ValueError(f"cannot give {world} ranks a non-empty destination range of {num_nodes} nodes")
+        return [(num_nodes * r) // world for r in range(world)] + [num_nodes]
     if balance != "edges":
         raise ValueError(f"unknown balance mode {balance!r}")
     deg = torch.bincount(dst, minlength=num_nodes)
@@ -51,8 +52,13 @@ def partition_bounds(dst: Tensor, num_nodes: int, world: int, balance: str = "ed
     targets = torch.tensor([(total * r) // world for r in range(1, world)], device=dst.device, dtype=csum.dtype)
     cuts = torch.searchsorted(csum, targets, right=False).tolist() if world > 1 else []
     bounds = [0] + [min(int(c) + 1, num_nodes) for c in cuts] + [num_nodes]
-    for i in range(1, len(bounds)):
-        bounds[i] = max(bounds[i], bounds[i - 1])
+    # every rank gets at least one row (a hub holding >= 1/world of the edges would otherwise leave an EMPTY range,
+    # and a rank without rows cannot enter the layer's GEMMs / collectives): the cuts are pushed apart.  The same
+    # arithmetic runs on every rank, so either all ranks get bounds or all raise.
+    if num_nodes < world:
+        raise ValueError(f"cannot give {world} ranks a non-empty destination range of {num_nodes} nodes")
+    for i in range(1, world):
+        bounds[i] = min(max(bounds[i], bounds[i - 1] + 1), num_nodes - (world - i))
     return bounds
 
 
@@ -138,17 +144,26 @@ def reduce_scatter_rows(x_all: Tensor, max_rows: int, rows: int, group=None) -> 
     return out[:rows]
 
 
-def allreduce_grads(params, group=None) -> None:
-    """Data-parallel step (ii): sum weight gradients over ranks (one flat bucket)."""
-    grads = [p.grad for p in params if p.grad is not None]
-    if not grads or not dist.is_initialized() or dist.get_world_size(group) == 1:
+def allreduce_grads(params, group=None, average: bool = False) -> None:
+    """Data-parallel step (ii): SUM weight gradients over ranks in one flat bucket (`average=True` divides by the
+    world size afterwards; the layers' losses here are sums over nodes / graphs, so the sum is the full-batch
+    gradient).  The bucket layout is rank-independent: every parameter of `params` takes part, a rank whose
+    gradient is None (e.g. it received no graph of the batch) contributes zeros and receives the total."""
+    params = list(params)
+    if not params or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
-    flat = torch.cat([g.reshape(-1) for g in grads])
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
     dist.all_reduce(flat, group=group)
+    if average:
+        flat /= dist.get_world_size(group)
     off = 0
-    for g in grads:
-        g.copy_(flat[off: off + g.numel()].view_as(g))
-        off += g.numel()
+    for p in params:
+        g = flat[off: off + p.numel()].view_as(p)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
+        off += p.numel()
 
 
 def split_graph_batch(edge_index: Tensor, batch: Tensor, rank: int, world: int, *node_tensors: Tensor,

@@ -66,7 +66,17 @@ def test_partition_bounds_single_process():
     assert partition_bounds(dst, 100, 4, "nodes") == [0, 25, 50, 75, 100]
     b = partition_bounds(dst, 100, 4, "edges")
     assert b[0] == 0 and b[-1] == 100 and b[1] == 1           # the hub row alone fills the first shard
-    assert partition_bounds(torch.zeros(0, dtype=torch.long), 10, 3, "edges") == [0, 4, 8, 10]
+    assert partition_bounds(torch.zeros(0, dtype=torch.long), 10, 3, "edges") == [0, 3, 6, 10]
+    # no rank is ever left without rows: a hub holding more than 1/world of the edges, or fewer nodes per rank than
+    # the ceiling split would deal out -- and the failure for N < world is the same ValueError on every rank
+    hub = torch.cat([torch.full((1000,), 7, dtype=torch.long), torch.arange(8)])
+    for mode in ("edges", "nodes"):
+        for world in (2, 3, 4, 8):
+            bb = partition_bounds(hub, 8, world, mode)
+            assert bb[0] == 0 and bb[-1] == 8 and all(bb[i + 1] > bb[i] for i in range(world)), (mode, world, bb)
+        assert partition_bounds(hub, 5, 4, mode) [-1] == 5
+        with pytest.raises(ValueError):
+            partition_bounds(hub, 3, 4, mode)
     sl = _slices(128, 4)
     assert [(s.start, s.stop) for s in sl] == [(0, 32), (32, 64), (64, 96), (96, 128)]
     assert [(s.start, s.stop) for s in _slices(75, 4)] == [(0, 75)]
@@ -170,6 +180,14 @@ def test_sharded_aggregate_matches_single_gpu(p_drop):
     mp.spawn(_gpu_worker, args=(2, _free_port(), 4000, 60000, 128, p_drop), nprocs=2, join=True)
 
 
+@pytest.mark.gpu
+def test_sharded_aggregate_world1_runs_the_windowed_exchange_path():
+    """One GPU is enough to drive the sharded autograd node end to end (NCCL communicator of one rank): the padded
+    all-gathered layout, the column-window pipeline (4 windows: virtual Q base pointers, per-window partial dQ and
+    reduce-scatter, the std backward on a re-gathered window) against the plain single-GPU call, bit for bit."""
+    mp.spawn(_gpu_worker, args=(1, _free_port(), 3000, 45000, 128, 0.5), nprocs=1, join=True)
+
+
 def _gpu_layer_worker(rank, world, port, n, E, Fd):
     """The whole drop-in layer on a destination-range shard (fused tcgen05 path) vs the single-GPU layer:
     same seed -> same dropout stream (keyed by global node id), outputs and all gradients must agree."""
@@ -219,6 +237,13 @@ def test_sharded_fused_layer_matches_single_gpu():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     mp.spawn(_gpu_layer_worker, args=(2, _free_port(), 6000, 90000, 128), nprocs=2, join=True)
+
+
+@pytest.mark.gpu
+def test_sharded_fused_layer_world1():
+    """The sharded branch of the fused layer (exchange of Q, partial dQ over the padded source layout, reduce-scatter,
+    all-reduced weight gradients) on a one-rank communicator against the single-GPU branch."""
+    mp.spawn(_gpu_layer_worker, args=(1, _free_port(), 5000, 70000, 128), nprocs=1, join=True)
 
 
 def _gpu_dp_worker(rank, world, port):
