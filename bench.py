@@ -919,7 +919,7 @@ def main():
     ap.add_argument("--impl", default="mma_b200", choices=["mma_b200", "reference"])
     ap.add_argument("--config", default="c4", choices=sorted(CONFIGS) + sorted(SMALL))
     ap.add_argument("--dropout", type=float, default=0.5, help="0.5 = the reference's always-on dropout")
-    ap.add_argument("--slices", type=int, default=2, help="feature windows of the sharded pipeline")
+    ap.add_argument("--slices", type=int, default=1, help="feature windows of the sharded exchange pipeline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-tc", action="store_true", help="cuBLAS fp32 GEMMs instead of the tcgen05 3xTF32 layer")

@@ -308,6 +308,47 @@ int mma_reduce_slabs(const float *part, const float *coef, int64_t n_slots, int6
 int mma_reduce_slabs_segmented(const float *part, const int32_t *seg_ptr, int64_t n_segs, int64_t n,
                                float *out, mma_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * C1: the two exchanges of the destination-range sharded layer (new -- the reference
+ * is single-device) over NVLink peer memory.  The payload (forward: every rank's Q rows
+ * into every peer's gathered buffer; backward: every rank's partial dQ slice into its owner's slice
+ * buffer) is moved by the COPY ENGINES through peer-to-peer copies the host enqueues; these entry
+ * points are the device-side handshake around them and the owner's fixed-order reduction.
+ *   epoch        device uint64, advanced once per layer call (a step captured in a CUDA graph then hands
+ *                out a fresh value at every replay);
+ *   phase        0..15: which exchange of the call (forward window k, backward window k, buffers free);
+ *   a flag holds epoch * 16 + phase of the last announcement; flags only grow.
+ * ---------------------------------------------------------------------- */
+/* Host.  The exchange buffers are the one thing the library allocates itself (a CUDA IPC handle names a
+ * whole cudaMalloc allocation): mma_peer_alloc = cudaMalloc + zero fill + cudaIpcGetMemHandle (handle64:
+ * 64 bytes out, to be sent to the peer processes); mma_peer_open maps a peer process's buffer into the
+ * CURRENT device's address space (cudaIpcOpenMemHandle with lazy peer access -- the importer's kernels
+ * and copy engines then reach it over NVLink); mma_peer_close / mma_peer_free undo them. */
+int mma_peer_alloc(size_t bytes, void **ptr, void *handle64);
+int mma_peer_free(void *ptr);
+int mma_peer_open(const void *handle64, void **ptr);
+int mma_peer_close(void *ptr);
+/* Host: lets the CURRENT device address `peer_device`'s memory directly (cudaDeviceEnablePeerAccess;
+ * already-enabled is fine).  MMA_ERR_UNSUPPORTED when the two devices have no peer path. */
+int mma_peer_enable_access(int peer_device);
+/* epoch += 1; vals[p] = epoch * 16 + p for p < 16 (vals: device uint64 [16], optional). */
+int mma_peer_epoch_advance(uint64_t *epoch, uint64_t *vals, mma_stream_t stream);
+/* cudaMemcpyAsync / cudaMemcpy2DAsync between (peer-mapped) device pointers on `stream`: the copy engines
+ * move the payload, and an 8-byte copy of vals[phase] into the peer's flag, enqueued right after the
+ * payload on the same stream, announces it -- neither needs an SM, so both run under persistent kernels. */
+int mma_peer_copy(void *dst, const void *src, size_t bytes, mma_stream_t stream);
+int mma_peer_copy_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes,
+                     size_t height, mma_stream_t stream);
+/* Returns (on the stream) once flags[t] >= epoch * 16 + phase for all t < n_flags <= 32 (acquire, system
+ * scope).  After timeout_ns without progress *err = 1 + t (device int32, optional) and the wait gives up:
+ * a lost peer must never hang the GPU. */
+int mma_peer_wait(const uint64_t *epoch, const uint64_t *flags, int n_flags, int phase,
+                  uint64_t timeout_ns, int32_t *err, mma_stream_t stream);
+/* out[r, 0:w] = sum_k slices[k][r, 0:w], k ascending (deterministic, no atomics); slices: HOST array of
+ * n_slices <= 16 device pointers to contiguous [rows, w] fp32 blocks, w % 4 == 0. */
+int mma_sum_slices(const float *const *slices, int n_slices, int64_t rows, int w, float *out, int64_t ldo,
+                   mma_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,6 +56,16 @@ _SIGS = {
                          C.c_int),
     "mma_reduce_slabs": ([_vp, _vp, _i64, _i64, _vp, _vp], C.c_int),
     "mma_reduce_slabs_segmented": ([_vp, _vp, _i64, _i64, _vp, _vp], C.c_int),
+    "mma_peer_epoch_advance": ([_vp, _vp, _vp], C.c_int),
+    "mma_peer_alloc": ([C.c_size_t, C.POINTER(_vp), _vp], C.c_int),
+    "mma_peer_free": ([_vp], C.c_int),
+    "mma_peer_open": ([_vp, C.POINTER(_vp)], C.c_int),
+    "mma_peer_close": ([_vp], C.c_int),
+    "mma_peer_enable_access": ([_i32], C.c_int),
+    "mma_peer_copy": ([_vp, _vp, C.c_size_t, _vp], C.c_int),
+    "mma_peer_copy_2d": ([_vp, C.c_size_t, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp], C.c_int),
+    "mma_peer_wait": ([_vp, _vp, _i32, _i32, _u64, _vp, _vp], C.c_int),
+    "mma_sum_slices": ([C.POINTER(_vp), _i32, _i64, _i32, _vp, _i64, _vp], C.c_int),
 }
 EXPORTS = tuple(_SIGS)
 

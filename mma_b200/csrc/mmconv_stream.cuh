@@ -235,6 +235,77 @@ struct Ring {
     __device__ __forceinline__ void end() { cp_async_wait<0>(); }
 };
 
+// Forward kernel: the same ring with ROW-ALIGNED stages.  A stage holds the next (up to) 4 edges OF ONE ROW: the
+// last stage of a row is short (its unused slots are predicated off), so every full stage lies inside one row and is
+// consumed by the unrolled 4-edge body, and an edge's in-row position is a multiple of 4 at every stage start -- a
+// stage never straddles a 32-position dropout word either.  Only the deg mod 4 edges of a row's last stage go edge by
+// edge (with position-aligned stages three row boundaries in four fell INSIDE a stage at Poisson(16) in-degrees and
+// sent a quarter of all edges down the single-edge path).  The issue side walks the row boundaries itself, NST - 1
+// stages ahead of the consumer; both derive the same stage sequence from the row pointer.
+template <int NST, int VEC>
+struct RowRing {
+    uint32_t base;             // shared-memory address of this lane's bytes in ring slot 0
+    int rowb;                  // bytes of one gathered row window
+    const char *Qc;            // Q + this lane's column
+    uint32_t ldq_b;
+    int lane;
+    bool live;
+    const int32_t *colp;       // col + first CSR slot of the stream
+    const int32_t *rp;         // (virtual) row pointer
+    int s0, len;
+    int i_row, i_pos, i_end;   // issue side: row being issued, stream position of its next edge, end of that row
+    int idx_base, idx_cur, idx_nxt;   // col[] of stream positions [idx_base, +32) / [idx_base + 32, +64)
+    int ring_i;
+
+    __device__ __forceinline__ int load_chunk(int pbase) const {
+        const int i = pbase + lane;
+        return i < len ? __ldg(colp + i) : 0;
+    }
+    __device__ __forceinline__ void issue() {
+        while (i_pos == i_end && i_pos < len) { ++i_row; i_end = __ldg(rp + i_row + 1) - s0; }     // skip finished / empty rows
+        int n = i_end - i_pos;
+        n = n < 4 ? n : 4;
+        if (i_pos >= len) n = 0;
+        if (n > 0) {
+            if (i_pos >= idx_base + 32) { idx_cur = idx_nxt; idx_base += 32; idx_nxt = load_chunk(idx_base + 32); }
+            const uint32_t dst = base + (uint32_t)(ring_i * 4 * rowb);
+            const int o = i_pos - idx_base;
+            if (o + n <= 32) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = __shfl_sync(0xffffffffu, idx_cur, (o + u) & 31);
+                    cp_async_pred<VEC * 4>(dst + (uint32_t)(u * rowb), Qc + (uint64_t)(uint32_t)j * ldq_b, live && u < n);
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int a = __shfl_sync(0xffffffffu, idx_cur, (o + u) & 31);
+                    const int b = __shfl_sync(0xffffffffu, idx_nxt, (o + u) & 31);
+                    const int j = o + u < 32 ? a : b;
+                    cp_async_pred<VEC * 4>(dst + (uint32_t)(u * rowb), Qc + (uint64_t)(uint32_t)j * ldq_b, live && u < n);
+                }
+            }
+        }
+        cp_async_commit();
+        i_pos += n;
+        ring_i = ring_i + 1 == NST ? 0 : ring_i + 1;
+    }
+    __device__ __forceinline__ void begin(const int32_t *col_at_s0, const int32_t *rp_, int r0, int s0_, int len_) {
+        colp = col_at_s0; rp = rp_; s0 = s0_; len = len_;
+        i_row = r0; i_pos = 0; i_end = __ldg(rp + r0 + 1) - s0;
+        ring_i = 0;
+        idx_base = 0; idx_cur = load_chunk(0); idx_nxt = load_chunk(32);
+#pragma unroll 1
+        for (int k = 0; k < NST; ++k) issue();
+        cp_async_wait<NST - 1>();                   // stage 0 has landed
+    }
+    __device__ __forceinline__ void advance() {
+        issue();
+        cp_async_wait<NST - 1>();
+    }
+    __device__ __forceinline__ void end() { cp_async_wait<0>(); }
+};
+
 // One int per stream edge (G-row slot, original edge id), read by the CONSUMER in coalesced chunks of
 // 32 edges, one chunk ahead.  load(pbase) returns the value of stream edge pbase + lane (0 past the end).
 struct EdgeAttr {
@@ -336,7 +407,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_fwd_stream(const __grid_
     // row of Y, or -1 (fill_params); anything else goes through the generic loop
     const bool simple_out = p.simple_out != 0;
 
-    Ring<NST, true, VEC> ring;
+    RowRing<NST, VEC> ring;
     ring.rowb = p.ncols * 4;
     ring.base = smem_addr(smem_ring) + (uint32_t)warp * (uint32_t)(NST * 4 * ring.rowb) + (live ? (uint32_t)(lane * VEC * 4) : 0u);   // idle lanes stay inside the ring
     ring.Qc = reinterpret_cast<const char *>(p.Q + c);
@@ -449,9 +520,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_fwd_stream(const __grid_
         reset_acc();
 
         if (len > 0) {
-            ring.begin(p.col + s0, len);
-            run_stream<NST, true, VEC>(ring, s0, len, row_end, row_next,
-                [&](int at, const Vec<VEC> (&q)[4], int) {                    // 4 edges inside the row
+            ring.begin(p.col + s0, rp, r0, s0, len);
+            int c_pos = 0, cons_i = 0;
+#pragma unroll 1
+            while (c_pos < len) {
+                const int at = s0 + c_pos;
+                if (at == row_end) { row_next(); continue; }
+                const int n = row_end - at < 4 ? row_end - at : 4;
+                const uint32_t sb = ring.base + (uint32_t)(cons_i * 4 * ring.rowb);
+                if (n == 4) {                                                 // a full stage: 4 edges of this row
+                    Vec<VEC> q[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) q[i] = lds_vec<VEC>(sb + (uint32_t)(i * ring.rowb));
                     rng_refresh<DROP, VEC>(p, rid, pos, c, bits);
                     uint32_t w[VEC];
                     const int sh = DROP == FD_BIT ? (pos & 31) : 0;
@@ -467,19 +547,25 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_fwd_stream(const __grid_
                         }
                     }
                     pos += 4;
-                },
-                [&](int at, const Vec<VEC> &q, int) {                         // one edge
-                    rng_refresh<DROP, VEC>(p, rid, pos, c, bits);
+                } else {                                                      // the row's last, short stage
+#pragma unroll 1
+                    for (int u = 0; u < n; ++u) {
+                        const Vec<VEC> q = lds_vec<VEC>(sb + (uint32_t)(u * ring.rowb));
+                        rng_refresh<DROP, VEC>(p, rid, pos, c, bits);
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) {
-                        const float x = fast_message<MSG_PQ, DROP>(pv.v[v], q.v[v], 0.0f, scale);
-                        accumulate<false, DROP != FD_NONE, MINMAX, SQ>(x, keep_at<DROP>(bits[v], pos, thr), 1u, at,
-                                                                       sum[v], sq[v], mn[v], mx[v], amn[v], amx[v]);
+                        for (int v = 0; v < VEC; ++v) {
+                            const float x = fast_message<MSG_PQ, DROP>(pv.v[v], q.v[v], 0.0f, scale);
+                            accumulate<false, DROP != FD_NONE, MINMAX, SQ>(x, keep_at<DROP>(bits[v], pos, thr), 1u, at + u,
+                                                                           sum[v], sq[v], mn[v], mx[v], amn[v], amx[v]);
+                        }
+                        ++pos;
                     }
-                    ++pos;
-                },
-                [&]() { return DROP == FD_BIT ? (pos & 31) <= 28 : (DROP == FD_BYTE ? (pos & 3) == 0 : true); },
-                [](int) {});
+                }
+                c_pos += n;
+                ring.advance();
+                cons_i = cons_i + 1 == NST ? 0 : cons_i + 1;
+            }
+            ring.end();
         }
         // the last row with edges, then trailing empty rows
         for (;;) {

@@ -34,6 +34,9 @@ from .graph import Graph
 # CTAs take SMs away from the persistent one-CTA-per-SM GEMM, whose displaced CTAs then run as a second wave
 # (measured: the GEMM took 2x as long, cancelling the overlap).
 OVERLAP_EXCHANGE = os.environ.get("MMA_OVERLAP_EXCHANGE", "0") == "1"
+# How the sharded layer's two exchanges travel: "peer" = copy engines over NVLink peer memory, pipelined per feature
+# window (mma_b200/peer.py, the default); "nccl" = one all-gather / reduce-scatter (the round-1 path, kept for A/B runs).
+EXCHANGE = os.environ.get("MMA_EXCHANGE", "peer")
 
 # Parity hook (bench.py --verify, tests): when set to a dict, every forward leaves references to its raw aggregates
 # and arg indices there (Z in CSR-row order, arg_min / arg_max as CSR slots), so a sharded run can be compared bit for
@@ -41,14 +44,47 @@ OVERLAP_EXCHANGE = os.environ.get("MMA_OVERLAP_EXCHANGE", "0") == "1"
 KEEP_LAST: Optional[dict] = None
 
 
-class PostPlan:
-    """Row ranges of equal in-degree (graph.buckets) -> tile / slab tables of the grouped GEMMs."""
+def fold_blocks(akinds: Sequence[int]):
+    """Which aggregate blocks K1 has to MATERIALISE for the aggregator kinds `akinds` (sum 0, mean 1, min 2, max 3,
+    var 4, std 5).  `mean` is `sum / deg`, and the post weight is already one matrix per in-degree, so a mean block is
+    never written: its weight block, divided by the degree, is added onto the sum block's (W_sum + W_mean / d).
+    Returns (kinds of the materialised blocks, block of each aggregator, whether its coefficient is 1 / deg)."""
+    mat, block_of, inv = [], [], []
+    for k in akinds:
+        km = 0 if k == 1 else k
+        if km not in mat:
+            mat.append(km)
+        block_of.append(mat.index(km))
+        inv.append(k == 1)
+    return tuple(mat), tuple(block_of), tuple(inv)
 
-    def __init__(self, graph: Graph, scalers: Sequence[str], avg_deg: Dict[str, float], min_rows: int, Fo: int, K: int):
+
+def materialised_blocks(aggregators: Sequence[str]) -> int:
+    """Number of [N, F] aggregate blocks the fused layer's K1 writes for these aggregator names (bench.py's byte count)."""
+    return len(fold_blocks(tuple(_lib.AGGR_KINDS[a] for a in aggregators))[0])
+
+
+class PostPlan:
+    """Row ranges of equal in-degree (graph.buckets) -> tile / slab tables of the grouped GEMMs, and the coefficients
+    that turn the S x A blocks of the post weight into ONE effective weight per degree over the materialised blocks:
+    coef[b, s, a, m] = cum_s(d_b) * [block_of(a) == m] * (1 / max(d_b, 1) if a is a mean else 1)."""
+
+    def __init__(self, graph: Graph, scalers: Sequence[str], avg_deg: Dict[str, float], min_rows: int, Fo: int,
+                 akinds: Sequence[int], F: int):
         dev = graph.device
         degs = [d for d, _, _ in graph.buckets]
         self.S = len(scalers)
+        self.akinds = tuple(akinds)
+        self.mat, self.block_of, self.inv = fold_blocks(akinds)
+        A, Am = len(akinds), len(self.mat)
+        K = Am * F                                                                       # width of Z / dZ
+        self.K = K
         self.cum = cumulative_scale_factors(scalers, avg_deg, degs).to(dev)           # [S, n_buckets]
+        degf = torch.tensor(degs, dtype=torch.float32).clamp_(min=1)
+        fold = torch.zeros((len(degs), A, Am), dtype=torch.float32)                    # [n_buckets, A, Am]
+        for a in range(A):
+            fold[:, a, self.block_of[a]] = (1.0 / degf) if self.inv[a] else 1.0
+        self.fold = fold.to(dev)
         big, tiles, tiles_t, slabs, seg_ptr, tail_rows, tail_b = [], [], [], [], [0], [], []
         for b, (_, lo, hi) in enumerate(graph.buckets):
             if hi - lo >= min_rows:
@@ -66,20 +102,26 @@ class PostPlan:
         i32 = lambda rows: torch.tensor(rows, dtype=torch.int32, device=dev).reshape(-1, 4)
         self.big = big
         self.cum_big = self.cum[:, big].contiguous() if big else None                 # [S, B]
+        # [B, S, A, Am]
+        self.coef_big = (self.cum_big.t().reshape(len(big), self.S, 1, 1) * self.fold[big].unsqueeze(1)).contiguous() \
+            if big else None
         self.tile_tab, self.tile_tab_t, self.slabs = i32(tiles), i32(tiles_t), i32(slabs)
         self.seg_ptr = torch.tensor(seg_ptr, dtype=torch.int32, device=dev)
         self.tail_idx = torch.cat(tail_rows).to(dev) if tail_rows else None           # CSR rows of the small buckets
         self.tail_bucket = torch.cat(tail_b).to(dev) if tail_b else None
         self.tail_nodes = (graph.row_map.to(torch.int64).index_select(0, self.tail_idx)
                            if tail_rows else None)                                      # their node ids
+        # tail rows (literal formula): Y_t[n, s, a, :] = coef_t[n, s, a, m] * Z_t[n, m, :]
+        self.tail_coef = ((self.cum[:, self.tail_bucket].t().reshape(-1, self.S, 1, 1)
+                           * self.fold[self.tail_bucket].unsqueeze(1)).contiguous() if tail_rows else None)
 
 
-def post_plan(graph: Graph, scalers, avg_deg, min_rows: int, Fo: int, K: int) -> PostPlan:
-    key = ("tc", tuple(scalers), float(avg_deg["log"]), float(avg_deg["lin"]), int(min_rows), int(Fo), int(K))
+def post_plan(graph: Graph, scalers, avg_deg, min_rows: int, Fo: int, akinds, F: int) -> PostPlan:
+    key = ("tc", tuple(scalers), float(avg_deg["log"]), float(avg_deg["lin"]), int(min_rows), int(Fo), tuple(akinds), int(F))
     plans = graph.__dict__.setdefault("_post_plans", {})
     p = plans.get(key)
     if p is None:
-        p = plans[key] = PostPlan(graph, scalers, avg_deg, min_rows, Fo, K)
+        p = plans[key] = PostPlan(graph, scalers, avg_deg, min_rows, Fo, akinds, F)
     return p
 
 
@@ -122,6 +164,58 @@ def _k1_bwd(graph: Graph, P, Q, R, keep, F, akinds, p_drop, seed, dZ, arg_min, a
     return G if need_R else None
 
 
+def _k1_fwd_windows(graph: Graph, P: Tensor, ex, F: int, akinds, p_drop: float, seed: int, seed_dev):
+    """K1 over this rank's rows, one launch per feature window of the peer exchange, each as soon as that window of
+    the gathered Q has arrived from every rank (column-window ABI: col0 / ncols, virtual Q base, ldq = window width)."""
+    dev = P.device
+    n, A = graph.n_dst, len(akinds)
+    Z = torch.empty((n, A * F), dtype=torch.float32, device=dev)
+    has_min, has_max = 2 in akinds, 3 in akinds
+    need_sq = 4 in akinds or 5 in akinds
+    arg_min = torch.empty((n, F), dtype=torch.int32, device=dev) if has_min else None
+    arg_max = torch.empty((n, F), dtype=torch.int32, device=dev) if has_max else None
+    mean = torch.empty((n, F), dtype=torch.float32, device=dev) if need_sq else None
+    var = torch.empty((n, F), dtype=torch.float32, device=dev) if need_sq else None
+    for k, s_ in enumerate(ex.windows):
+        ex.wait(k)
+        q_ptr, ldq = ex.q_window(k)
+        MF.k1_forward(graph, P, None, None, None, T=1, F_in=F, akinds=akinds, skinds=(0,), tab=None, p_drop=p_drop,
+                      seed=seed, Y=Z, arg_min=arg_min, arg_max=arg_max, mean=mean, var=var, local_args=True,
+                      seed_dev=seed_dev, col0=s_.start, ncols=s_.stop - s_.start, q_ptr=q_ptr, ldq=ldq)
+    return Z, arg_min, arg_max, mean, var
+
+
+def _k1_bwd_windows(graph: Graph, P, ex, F, akinds, p_drop, seed, dZ, arg_min, arg_max, mean, var, dP: Tensor,
+                    need_sq: bool, seed_dev) -> None:
+    dev = dZ.device
+    graph.build_transpose()
+    G = torch.empty((graph.E, F), dtype=torch.float32, device=dev)       # CSC order, full width, filled window by window
+    for k, s_ in enumerate(ex.windows):
+        w = s_.stop - s_.start
+        q_ptr, ldq = ex.q_window(k) if need_sq else (None, None)
+        part = torch.empty((graph.n_src, w), dtype=torch.float32, device=dev)
+        if graph.E > 0:
+            MF.k1_backward_dst(graph, P, None, None, None, T=1, F_in=F, akinds=akinds, skinds=(0,), tab=None,
+                               p_drop=p_drop, seed=seed, dY=dZ, arg_min=arg_min, arg_max=arg_max, mean=mean, var=var,
+                               gslot=graph.csr2csc, G=G, ldg=F, dP=dP, lddp=dP.stride(0), local_args=True,
+                               seed_dev=seed_dev, col0=s_.start, ncols=w, q_ptr=q_ptr, ldq=ldq)
+            # transpose pass owner by owner (source rows are laid out rank-major): each owner's slice leaves on the copy
+            # engines while the next owner's rows are being summed
+            mr = ex.max_rows
+            for o in ex.owner_order():
+                with _lib.kernel_scope("mma_segment_sum_rows", dev):
+                    _lib.check(_lib.lib().mma_segment_sum_rows(graph.colptr.data_ptr() + 4 * o * mr, None, None, mr,
+                                                               G.data_ptr() + 4 * s_.start, F, w,
+                                                               part.data_ptr() + 4 * o * mr * w, w,
+                                                               _lib.stream_ptr(dev)), "mma_segment_sum_rows")
+                ex.push_partial_block(k, o, part)
+        else:
+            part.zero_()
+            if k == 0:
+                dP.zero_()
+            ex.push_partial(k, part)
+
+
 class _FusedMMAConv(torch.autograd.Function):
     """post_layers == 1: there is no nonlinearity between the post Linear (mma_conv.py:132-133) and `lin`
     (:136), so the two compose:  out = Z (W_lin W_eff(d))^T + x (W_lin W_x)^T + (W_lin b_post + b_lin).
@@ -136,7 +230,8 @@ class _FusedMMAConv(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, Wm, bm, Wp, bp, Wl, bl, R, keep, graph, plan: PostPlan, cfg):
-        F, akinds, p_drop, seed, seed_dev = cfg
+        F, akinds, p_drop, seed, seed_dev = cfg[:5]
+        n_win, owner = cfg[5:7]
         if seed_dev is not None:
             seed_dev = seed_dev.clone()      # this call's seed: the backward must see the same value
         dev = _lib.require_cuda(x, Wm, Wp, Wl)
@@ -145,7 +240,7 @@ class _FusedMMAConv(torch.autograd.Function):
             graph = sg.local
         n = graph.n_dst
         A, S = len(akinds), plan.S
-        K = A * F
+        Am, K = len(plan.mat), plan.K                # materialised aggregate blocks (a mean rides on the sum block)
         Fo, Co = Wp.shape[0], Wl.shape[0]
         zeros = lambda k: torch.zeros(k, dtype=torch.float32, device=dev)
         Wx, Wy = Wp[:, :F], Wp[:, F:].contiguous()
@@ -156,11 +251,20 @@ class _FusedMMAConv(torch.autograd.Function):
         W1hi, W1lo = tg.split_weight(W1)
         PQX = tg.linear(x, W1hi, W1lo, 2 * F + Co, bias=b1, name="gemm_mask_proj")                  # [n, 2F+Co], node order
         P, Q, XW = PQX[:, :F], PQX[:, F:2 * F], PQX[:, 2 * F:]
-        gathered = None
-        if sg is not None:
-            # the one exchange of the forward: every rank's Q rows (the halo of a random graph is ~all of Q),
-            # rank-major padded layout that the shard's source indices already address.  It runs on the
-            # communication stream under the weight-space algebra below (tiny kernels, no SM pressure).
+        gathered = ex = None
+        if sg is not None and EXCHANGE == "peer":
+            # the one exchange of the forward, over peer memory: every rank pushes its Q rows, feature window by
+            # feature window, into every peer's gathered buffer with the copy engines (mma_b200/peer.py).  The pushes
+            # start here and run under the weight-space algebra and under K1 of the earlier windows.
+            from .parallel import _slices
+            from .peer import exchange_for
+            ex = exchange_for(sg, F, _slices(F, n_win), dev, owner)
+            ex.begin_call()
+            ex.fwd_calls += 1
+            ex.push_q(Q, n)
+        elif sg is not None:
+            # NCCL variant (MMA_EXCHANGE=nccl): one all-gather of Q on the communication stream under the
+            # weight-space algebra below; kept for A/B measurements against the copy-engine exchange
             from .parallel import all_gather_rows, _comm_stream
             comm, cur = _comm_stream(dev), torch.cuda.current_stream(dev)
             Qc = Q.contiguous()
@@ -170,18 +274,23 @@ class _FusedMMAConv(torch.autograd.Function):
                 done = torch.cuda.Event(); done.record(comm)
             Qc.record_stream(comm)
             gathered = (Qg, done)
-        # composed weight of every degree range: W_c(d) = W_lin W_eff(d) = sum_s c_s(d) (W_lin W_s): S small products,
-        # then a weighted sum over the ranges (no [B, F_out, K] batched product)
-        WlWy = torch.matmul(Wl, Wy.view(Fo, S, K).permute(1, 0, 2))                                 # [S, Co, K]
+        # composed weight of every degree range over the materialised blocks:
+        #   W_c(d)[:, m] = sum_s sum_{a -> m} c_s(d) coef_a(d) (W_lin W_{s,a})      (coef = 1 / d for a mean, else 1)
+        # S small products, then one contraction with the per-range coefficients (no [B, F_out, K] batched product)
+        WlWy = torch.matmul(Wl, Wy.view(Fo, S, A * F).permute(1, 0, 2))                             # [S, Co, A*F]
         Wc = hi = lo = None
         if plan.big:
-            Wc = torch.einsum("sb,sck->bck", plan.cum_big, WlWy).contiguous()                       # [B, Co, K]
+            Wc = torch.einsum("bsam,scaf->bcmf", plan.coef_big, WlWy.view(S, Co, A, F)).reshape(-1, Co, K).contiguous()   # [B, Co, K]
             hi, lo = tg.split_weight(Wc.view(-1, K))
         if gathered is not None:
             Q, done = gathered
             torch.cuda.current_stream(dev).wait_event(done)
             Q.record_stream(torch.cuda.current_stream(dev))
-        Z, arg_min, arg_max, mean, var = _k1_fwd(graph, P, Q, R, keep, F, akinds, p_drop, seed, seed_dev)   # sorted rows
+        if ex is not None:
+            Z, arg_min, arg_max, mean, var = _k1_fwd_windows(graph, P, ex, F, plan.mat, p_drop, seed, seed_dev)
+            ex.join()
+        else:
+            Z, arg_min, arg_max, mean, var = _k1_fwd(graph, P, Q, R, keep, F, plan.mat, p_drop, seed, seed_dev)   # sorted rows
         out = torch.empty((n, Co), dtype=torch.float32, device=dev)
         if plan.big:
             tg.linear(Z, hi, lo, Co, tile_tab=plan.tile_tab, out=out, out_map=graph.row_map, add=XW,
@@ -190,15 +299,15 @@ class _FusedMMAConv(torch.autograd.Function):
             ti = plan.tail_idx
             nodes = plan.tail_nodes
             Zt = Z.index_select(0, ti)
-            ct = plan.cum[:, plan.tail_bucket].t()                                                  # [nt, S]
-            Yt = (Zt.unsqueeze(1) * ct.unsqueeze(2)).reshape(Zt.shape[0], S * K)
+            Yt = torch.einsum("nsam,nmf->nsaf", plan.tail_coef, Zt.view(-1, Am, F)).reshape(Zt.shape[0], S * A * F)
             out.index_copy_(0, nodes, (Yt @ Wy.t()) @ Wl.t() + XW.index_select(0, nodes))
         if KEEP_LAST is not None:
             KEEP_LAST.update(Z=Z, arg_min=arg_min, arg_max=arg_max, graph=graph)
         ctx.graph, ctx.sg, ctx.plan, ctx.cfg = graph, sg, plan, cfg
         ctx.has_R, ctx.has_b = R is not None, (bm is not None, bp is not None, bl is not None)
         need_sq = 4 in akinds or 5 in akinds
-        Qsave = Q if (sg is not None and need_sq) else None       # gathered Q, kept so the backward does not re-gather
+        Qsave = Q if (sg is not None and need_sq and ex is None) else None   # NCCL variant: gathered Q kept for the backward
+        ctx.ex, ctx.ex_call = ex, (ex.fwd_calls if ex is not None else 0)
         ctx.save_for_backward(x, PQX, Z, Wm, Wp, bp, Wl, Wc, R, keep, arg_min, arg_max, mean, var, Qsave,
                               seed_dev)
         return out
@@ -208,11 +317,12 @@ class _FusedMMAConv(torch.autograd.Function):
         (x, PQX, Z, Wm, Wp, bp, Wl, Wc, R, keep, arg_min, arg_max, mean, var, Qsave,
          seed_dev) = ctx.saved_tensors
         graph, sg, plan = ctx.graph, ctx.sg, ctx.plan
-        F, akinds, p_drop, seed, _ = ctx.cfg
+        F, akinds, p_drop, seed = ctx.cfg[:4]
+        ex = ctx.ex
         dev = d_out.device
         n = graph.n_dst
         A, S = len(akinds), plan.S
-        K = A * F
+        Am, K = len(plan.mat), plan.K
         Fo, Co = Wp.shape[0], Wl.shape[0]
         P, Q = PQX[:, :F], PQX[:, F:2 * F]
         if Qsave is not None:
@@ -229,23 +339,33 @@ class _FusedMMAConv(torch.autograd.Function):
             tg.linear(dO, hi, lo, K, tile_tab=plan.tile_tab_t, out=dZ, name="gemm_post_dgrad")
         if plan.tail_idx is not None:
             ti = plan.tail_idx
-            ct = plan.cum[:, plan.tail_bucket].t()
             dOt = dO.index_select(0, ti)
             dHt = dOt @ Wl
-            dYt = (dHt @ Wy).view(-1, S, K)
-            dZ.index_copy_(0, ti, (dYt * ct.unsqueeze(2)).sum(dim=1))
+            dYt = (dHt @ Wy).view(-1, S, A, F)
+            dZ.index_copy_(0, ti, torch.einsum("nsam,nsaf->nmf", plan.tail_coef, dYt).reshape(-1, K))
         dPQ = torch.empty((n, 2 * F), dtype=torch.float32, device=dev)
         need_R = ctx.has_R and ctx.needs_input_grad[7]
         pending = None
         if sg is None:
-            dR = _k1_bwd(graph, P, Q, R, keep, F, akinds, p_drop, seed, dZ, arg_min, arg_max, mean, var,
+            dR = _k1_bwd(graph, P, Q, R, keep, F, plan.mat, p_drop, seed, dZ, arg_min, arg_max, mean, var,
                          dPQ[:, :F], dPQ[:, F:2 * F], need_R, seed_dev)
+        elif ex is not None:
+            # per feature window: destination pass + transpose pass give this rank's PARTIAL dQ over all sources; its
+            # slices leave for their owners on the copy engines while the next window is computed; the owner sums the
+            # slices in rank order after the weight-gradient GEMM below, which does not depend on dQ
+            need_sq = 4 in akinds or 5 in akinds
+            if need_sq and ctx.ex_call != ex.fwd_calls:
+                raise RuntimeError("sharded MMAConv: the gathered Q of this forward was overwritten by a later forward of "
+                                   "the same layer; run backward before the next forward of this layer")
+            ex.begin_call()
+            dR = None
+            _k1_bwd_windows(graph, P, ex, F, plan.mat, p_drop, seed, dZ, arg_min, arg_max, mean, var, dPQ[:, :F],
+                            need_sq, seed_dev)
         else:
-            # partial dQ over ALL sources from this rank's edges, then the one exchange of the backward: a
-            # reduce-scatter that runs on the communication stream under the weight-gradient GEMM below
+            # NCCL variant: partial dQ over ALL sources, then one reduce-scatter
             from .parallel import reduce_scatter_rows, _comm_stream
             dQ_part = torch.empty((graph.n_src, F), dtype=torch.float32, device=dev)
-            dR = _k1_bwd(graph, P, Q, R, keep, F, akinds, p_drop, seed, dZ, arg_min, arg_max, mean, var,
+            dR = _k1_bwd(graph, P, Q, R, keep, F, plan.mat, p_drop, seed, dZ, arg_min, arg_max, mean, var,
                          dPQ[:, :F], dQ_part, need_R, seed_dev)
             if OVERLAP_EXCHANGE:
                 comm, cur = _comm_stream(dev), torch.cuda.current_stream(dev)
@@ -264,19 +384,25 @@ class _FusedMMAConv(torch.autograd.Function):
         if plan.big:
             part = tg.wgrad_partials(dO, Z, plan.slabs, plan.slabs.shape[0], name="gemm_post_wgrad")
             dWc = tg.reduce_slabs_segmented(part, plan.seg_ptr)                                     # [B, Co, K]
-            # W_c(d) = sum_s c_s(d) W_lin W_s  ->  D_s = sum_d c_s(d) dW_c(d);  dW_lin += sum_s D_s W_s^T,  dW_s = W_lin^T D_s
-            D = torch.einsum("sb,bck->sck", plan.cum_big, dWc)                                      # [S, Co, K]
-            Ws = Wy.view(Fo, S, K).permute(1, 0, 2)                                                 # [S, Fo, K]
+            # W_c(d)[:, m] = sum_{s, a -> m} coef(d, s, a) W_lin W_{s,a}  ->  D_{s,a} = sum_d coef(d, s, a) dW_c(d)[:, m(a)];
+            # dW_lin += sum_s D_s W_s^T,  dW_s = W_lin^T D_s
+            D = torch.einsum("bsam,bcmf->scaf", plan.coef_big, dWc.view(-1, Co, Am, F)).reshape(S, Co, A * F)
+            Ws = Wy.view(Fo, S, A * F).permute(1, 0, 2)                                             # [S, Fo, A*F]
             dWl = dWl + torch.matmul(D, Ws.transpose(1, 2)).sum(0)
-            dWy = torch.matmul(Wl.t(), D).permute(1, 0, 2).reshape(Fo, S * K)
+            dWy = torch.matmul(Wl.t(), D).permute(1, 0, 2).reshape(Fo, S * A * F)
         if plan.tail_idx is not None:
             ti = plan.tail_idx
             Zt = Z.index_select(0, ti)
-            Yt = (Zt.unsqueeze(1) * ct.unsqueeze(2)).reshape(Zt.shape[0], S * K)
+            Yt = torch.einsum("nsam,nmf->nsaf", plan.tail_coef, Zt.view(-1, Am, F)).reshape(Zt.shape[0], S * A * F)
             dWl = dWl + dOt.t() @ (Yt @ Wy.t())
             g = dHt.t() @ Yt
             dWy = g if dWy is None else dWy + g
         del dO
+        if ex is not None:
+            dQv = dPQ[:, F:2 * F]
+            for k in range(len(ex.windows)):
+                ex.sum_window(k, dQv, n)
+            ex.join()
         if pending is not None:
             dQ_loc, done = pending
             torch.cuda.current_stream(dev).wait_event(done)
@@ -315,7 +441,7 @@ def fused_mmaconv(x: Tensor, graph, *, W_mask: Tensor, b_mask: Optional[Tensor],
                   b_post: Optional[Tensor], W_lin: Tensor, b_lin: Optional[Tensor], R: Optional[Tensor],
                   keep: Optional[Tensor], aggregators: Sequence[str], scalers: Sequence[str],
                   avg_deg: Dict[str, float], p_drop: float, seed: int, min_rows: int,
-                  seed_dev: Optional[Tensor] = None) -> Tensor:
+                  seed_dev: Optional[Tensor] = None, n_windows: int = 2, owner: int = 0) -> Tensor:
     """x [N, F] (node order) -> MMAConv output [N, out] for towers == 1, pre_layers == post_layers == 1.
     W_mask [F, 2F or 3F] (the live mask Linear, Q2; only the first 2F columns are used here, the edge
     part arrives as R), W_post [Fo, (S*A+1)*F], W_lin [out, Fo]."""
@@ -331,6 +457,6 @@ def fused_mmaconv(x: Tensor, graph, *, W_mask: Tensor, b_mask: Optional[Tensor],
     if len(aggregators) > _lib.MAX_AGGR or len(scalers) > _lib.MAX_SCALER:
         raise _lib.MMAError("more than 8 aggregators or scalers in one call")
     akinds = tuple(_lib.AGGR_KINDS[a] for a in aggregators)
-    plan = post_plan(local, scalers, avg_deg, min_rows, W_lin.shape[0], len(akinds) * F)
+    plan = post_plan(local, scalers, avg_deg, min_rows, W_lin.shape[0], akinds, F)
     return _FusedMMAConv.apply(x, W_mask, b_mask, W_post, b_post, W_lin, b_lin, R, keep, graph, plan,
-                               (F, akinds, float(p_drop), int(seed), seed_dev))
+                               (F, akinds, float(p_drop), int(seed), seed_dev, int(n_windows), int(owner)))

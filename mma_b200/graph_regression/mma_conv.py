@@ -110,7 +110,7 @@ class MMAConv(torch.nn.Module):
         self.use_tensor_cores = True         # towers == 1: whole layer as one autograd node over tcgen05 GEMMs + K1
         self.fold_scalers = True             # towers == 1: fold the scalers into the post weight (see _forward_folded)
         self.fold_min_rows = 512             # degree ranges smaller than this use the literal formula
-        self.comm_slices = 2                 # feature windows of the sharded comm/compute pipeline
+        self.comm_slices = 1                 # feature windows of the sharded exchange (1: full-width K1; narrow windows cost more in K1 than they hide)
         self.global_max_deg = None           # sharded runs: global max in-degree (else all-reduced per call)
         self.device_seed = False             # True: the dropout seed lives in a device tensor that is advanced ON the
                                              # device at every call, so a step captured in a CUDA graph draws a fresh
@@ -269,7 +269,8 @@ class MMAConv(torch.nn.Module):
             x.contiguous(), graph, W_mask=live.weight, b_mask=live.bias, W_post=first.weight, b_post=first.bias,
             W_lin=self.lin.weight, b_lin=self.lin.bias, R=R, keep=keep, aggregators=self.aggregators,
             scalers=self.scalers, avg_deg=self.avg_deg, p_drop=self.dropout,
-            seed=0 if seed_dev is not None else self._next_seed(), min_rows=self.fold_min_rows, seed_dev=seed_dev)
+            seed=0 if seed_dev is not None else self._next_seed(), min_rows=self.fold_min_rows, seed_dev=seed_dev,
+            n_windows=self.comm_slices, owner=self._uid)
 
     def _forward_folded(self, x: Tensor, graph: Graph, edge_attr: Optional[Tensor]) -> Tensor:
         """towers == 1 fast path: K1 emits the RAW aggregates Z [N, A*F_in] in degree-sorted row

@@ -1,0 +1,271 @@
+"""Peer-memory exchange of the destination-range sharded layer: one process per GPU on ONE node, every rank's
+exchange buffers mapped into every other rank's address space (CUDA IPC over NVLink 5 / NVSwitch), payload moved by
+the COPY ENGINES, arrival announced by an 8-byte copy into the receiver's flag array (csrc/peer_exchange.cu).
+
+Why not NCCL for these two exchanges (north_star: "halo all-gather ... overlapped with interior aggregation"): an NCCL
+collective is a kernel that needs SMs; the aggregation kernels and the tcgen05 GEMMs are persistent one-CTA-per-SM
+kernels that own the whole register file, so a concurrent NCCL kernel either waits or displaces a CTA into a second
+wave (measured in round 1: the overlap cancelled itself).  Copy-engine transfers need no SM at all, so the transfer of
+feature window k+1 really runs under the aggregation of window k.  torch.distributed (NCCL) stays the plumbing: group
+set-up, handle exchange, weight-gradient all-reduce.
+
+The reference has no distributed code; this is new and follows BASELINE.json's north_star.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+from . import _lib
+
+N_PHASES = 16
+PHASE_ENTER = 15                # "this rank has entered the call": every earlier reader of its receive buffers is done
+WAIT_TIMEOUT_NS = 20_000_000_000
+
+
+class _RawCuda:
+    """A raw device pointer presented through __cuda_array_interface__ so torch can alias it as a tensor."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False),
+                                         "version": 2, "strides": None}
+
+
+class SharedRegion:
+    """One cudaMalloc allocation of this rank (zero-filled, made by the library: a CUDA IPC handle names a whole
+    allocation) mapped into every rank of the group ON THAT RANK'S OWN DEVICE, i.e. as peer memory its kernels and
+    copy engines reach over NVLink.  `base[r]` is the address of rank r's region in THIS process; `local` aliases this
+    rank's region as a uint8 tensor.  Collective: all ranks must construct it together with the same size."""
+
+    def __init__(self, nbytes: int, device, group=None):
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.nbytes = int(nbytes)
+        self.device = torch.device(device)
+        lib = _lib.lib()
+        handle = (C.c_ubyte * 64)()
+        p = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.mma_peer_alloc(self.nbytes, C.byref(p), handle), "mma_peer_alloc")
+        self._own = int(p.value)
+        handles: List = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self.base: List[int] = []
+        self._opened: List[int] = []
+        for r in range(self.world):
+            if r == self.rank:
+                self.base.append(self._own)
+                continue
+            q = C.c_void_p()
+            hb = (C.c_ubyte * 64).from_buffer_copy(handles[r])
+            with torch.cuda.device(self.device):
+                _lib.check(lib.mma_peer_open(hb, C.byref(q)), "mma_peer_open")
+            self.base.append(int(q.value))
+            self._opened.append(int(q.value))
+        self.local = torch.as_tensor(_RawCuda(self._own, self.nbytes), device=self.device)
+        dist.barrier(group)             # nobody proceeds before everyone has opened the handles
+
+    def view(self, offset: int, shape, dtype) -> Tensor:
+        """Tensor view of this rank's region at a byte offset."""
+        n = 1
+        for d in shape:
+            n *= int(d)
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        return self.local[offset: offset + nbytes].view(dtype).view(*shape)
+
+    def close(self) -> None:
+        """Unmaps the peers' regions and frees this rank's (call on all ranks, after a barrier, when nothing is in flight)."""
+        lib = _lib.lib()
+        with torch.cuda.device(self.device):
+            for q in self._opened:
+                lib.mma_peer_close(q)
+            self._opened = []
+            if self._own:
+                self.local = None
+                lib.mma_peer_free(self._own)
+                self._own = 0
+
+
+class PeerExchange:
+    """Buffers, flags and streams of the two exchanges for ONE (rows, width, windows) geometry.
+
+    recv_q   [W][world * max_rows, Fw]   gathered Q, one contiguous block per feature window (what K1's col0 / ncols /
+                                         ldq ABI reads); every rank pushes its rows of window k into every peer's block
+    slices   [W][world][max_rows, Fw]    partial-dQ slices as they arrive at their owner, summed in rank order
+    flags    [N_PHASES][world] uint64    flags[phase][sender] = epoch * 16 + phase of the sender's last announcement
+    """
+
+    def __init__(self, world: int, rank: int, max_rows: int, F: int, windows: Sequence[slice], device, group=None,
+                 n_copy_streams: int = 4):
+        self.world, self.rank, self.max_rows, self.F, self.group = world, rank, int(max_rows), int(F), group
+        self.windows = list(windows)
+        self.dev = device
+        W = len(self.windows)
+        if 2 * W + 1 > PHASE_ENTER:
+            raise ValueError("too many feature windows for the phase space of the flags")
+        widths = [s.stop - s.start for s in self.windows]
+        self.widths = widths
+        tot = world * self.max_rows
+        # ONE shared allocation per rank: [ recv_q blocks | slice blocks | flags ], window blocks laid out back to back
+        q_elems = sum(tot * w for w in widths)
+        self._off_recv, self._off_slice = 0, 4 * q_elems
+        self._off_flags = 8 * q_elems
+        self.region = SharedRegion(8 * q_elems + 8 * N_PHASES * world, device, group)
+        self._recv_flat = self.region.view(self._off_recv, (q_elems,), torch.float32)
+        self._slice_flat = self.region.view(self._off_slice, (q_elems,), torch.float32)
+        self._flags = self.region.view(self._off_flags, (N_PHASES, world), torch.int64)
+        self.epoch = torch.zeros(1, dtype=torch.int64, device=device)
+        self.vals = torch.zeros(N_PHASES, dtype=torch.int64, device=device)
+        self.err = torch.zeros(1, dtype=torch.int32, device=device)
+        self.q_off, off = [], 0
+        for w in widths:
+            self.q_off.append(off)
+            off += tot * w
+        self.recv_q = [self._recv_flat[o: o + tot * w].view(tot, w) for o, w in zip(self.q_off, widths)]
+        self.slices = [self._slice_flat[o: o + tot * w].view(world, self.max_rows, w) for o, w in zip(self.q_off, widths)]
+        self.streams = [torch.cuda.Stream(device=device, priority=-1) for _ in range(max(1, min(n_copy_streams, world)))]
+        self.fwd_calls = 0          # host-side count of forward calls (guards the gathered Q a backward re-reads)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)
+
+    # ---------------------------------------------------------------- low level
+    def _copy(self, dst_ptr: int, src_ptr: int, nbytes: int, stream: torch.cuda.Stream) -> None:
+        _lib.check(_lib.lib().mma_peer_copy(dst_ptr, src_ptr, nbytes, stream.cuda_stream), "mma_peer_copy")
+
+    def _stream_for(self, peer: int) -> torch.cuda.Stream:
+        return self.streams[((peer - self.rank) % self.world) % len(self.streams)]
+
+    def begin_call(self) -> None:
+        """On the current stream: epoch += 1, announcement values for all phases, and the entry barrier's own
+        announcement (every earlier reader of this rank's receive buffers ran before this point in stream order)."""
+        cur = torch.cuda.current_stream(self.dev)
+        with torch.cuda.device(self.dev):
+            _lib.check(_lib.lib().mma_peer_epoch_advance(self.epoch.data_ptr(), self.vals.data_ptr(), cur.cuda_stream),
+                       "mma_peer_epoch_advance")
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        for st in self.streams:
+            st.wait_event(ev)
+        self._announce(PHASE_ENTER, range(self.world))
+
+    def _announce(self, phase: int, peers) -> None:
+        """8-byte copy of vals[phase] into flags[phase][my rank] of each peer, on that peer's copy stream."""
+        src = self.vals.data_ptr() + 8 * phase
+        for o in peers:
+            dst = self.region.base[o] + self._off_flags + 8 * (phase * self.world + self.rank)
+            with torch.cuda.device(self.dev):
+                self._copy(dst, src, 8, self._stream_for(o))
+
+    def wait(self, phase: int, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """`stream` (default: current) continues once every rank's announcement of `phase` for this epoch is here."""
+        st = stream or torch.cuda.current_stream(self.dev)
+        with torch.cuda.device(self.dev):
+            _lib.check(_lib.lib().mma_peer_wait(self.epoch.data_ptr(), self._flags.data_ptr() + 8 * phase * self.world,
+                                                self.world, phase, WAIT_TIMEOUT_NS, self.err.data_ptr(), st.cuda_stream),
+                       "mma_peer_wait")
+
+    def _peer_order(self):
+        return [(self.rank + k) % self.world for k in range(self.world)]      # self first, then staggered
+
+    # ---------------------------------------------------------------- forward: all-gather of Q, window by window
+    def push_q(self, Q: Tensor, rows: int) -> None:
+        """Q [rows, F] (unit column stride; may be a column view of a wider matrix): window k goes, as a strided 2-D copy
+        straight out of Q (measured 670-750 GB/s even for 32-column windows of a 1536-byte pitch: no pack pass needed),
+        into rows [rank * max_rows, +rows) of every rank's recv_q[k]; phase k announces it.  The copy streams first
+        wait for all ranks' entry announcement (their receive buffers are free)."""
+        if Q.stride(1) != 1 or Q.dtype != torch.float32:
+            raise RuntimeError("push_q: Q must be fp32 with unit column stride")
+        cur = torch.cuda.current_stream(self.dev)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        for st in self.streams:
+            st.wait_event(ev)
+            self.wait(PHASE_ENTER, st)
+        lib = _lib.lib()
+        spitch = Q.stride(0) * 4
+        for k, (s_, w) in enumerate(zip(self.windows, self.widths)):
+            src = Q.data_ptr() + 4 * s_.start
+            for o in self._peer_order():
+                dst = self.region.base[o] + self._off_recv + 4 * (self.q_off[k] + self.rank * self.max_rows * w)
+                with torch.cuda.device(self.dev):
+                    _lib.check(lib.mma_peer_copy_2d(dst, w * 4, src, spitch, w * 4, rows, self._stream_for(o).cuda_stream),
+                               "mma_peer_copy_2d")
+            self._announce(k, self._peer_order())
+        for st in self.streams:
+            Q.record_stream(st)
+
+    def q_window(self, k: int):
+        """(base pointer shifted back by col0 columns, ldq) of the gathered window k for K1's q_ptr / ldq."""
+        return self.recv_q[k].data_ptr() - 4 * self.windows[k].start, self.widths[k]
+
+    # ---------------------------------------------------------------- backward: reduce-scatter of the partial dQ
+    def push_partial_block(self, k: int, o: int, part: Tensor) -> None:
+        """part [world * max_rows, Fw] (contiguous) holds this rank's partial dQ of window k; its rows of OWNER o
+        (rows [o * max_rows, +max_rows)) are final once the kernels enqueued so far on the current stream have run:
+        they go into slices[k][my rank] of rank o, and phase W + k announces them to o.  Calling it block by block,
+        right after the transpose pass of each owner's source rows, lets the slices leave while the next block is
+        still being summed."""
+        W, w = len(self.windows), self.widths[k]
+        cur = torch.cuda.current_stream(self.dev)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        st = self._stream_for(o)
+        st.wait_event(ev)
+        nbytes = self.max_rows * w * 4
+        dst = self.region.base[o] + self._off_slice + 4 * (self.q_off[k] + self.rank * self.max_rows * w)
+        src = part.data_ptr() + 4 * o * self.max_rows * w
+        with torch.cuda.device(self.dev):
+            self._copy(dst, src, nbytes, st)
+        self._announce(W + k, [o])
+        part.record_stream(st)
+
+    def push_partial(self, k: int, part: Tensor) -> None:
+        """All owners' blocks of window k at once (the whole `part` is final)."""
+        for o in self._peer_order():
+            self.push_partial_block(k, o, part)
+
+    def owner_order(self):
+        """Owners in the order their blocks should be produced and sent: the next rank first, this rank last."""
+        return [(self.rank + 1 + j) % self.world for j in range(self.world)]
+
+    def sum_window(self, k: int, out: Tensor, rows: int) -> None:
+        """out[:, window k] (a [rows, >= F] view with unit column stride) = sum over ranks, ascending, of the arrived
+        slices -- after waiting for phase W + k on the current stream."""
+        W, w = len(self.windows), self.widths[k]
+        self.wait(W + k)
+        ptrs = (C.c_void_p * self.world)(*[self.slices[k][r].data_ptr() for r in range(self.world)])
+        dst = out.data_ptr() + 4 * self.windows[k].start
+        with torch.cuda.device(self.dev):
+            _lib.check(_lib.lib().mma_sum_slices(ptrs, self.world, rows, w, dst, out.stride(0),
+                                                 _lib.stream_ptr(self.dev)), "mma_sum_slices")
+
+    def join(self) -> None:
+        """The current stream waits for everything enqueued on the copy streams (end of a call / of a capture)."""
+        cur = torch.cuda.current_stream(self.dev)
+        for st in self.streams:
+            cur.wait_stream(st)
+
+    def check(self) -> None:
+        """Host-side: raises if a wait gave up (a peer never announced).  Synchronises."""
+        torch.cuda.synchronize(self.dev)
+        e = int(self.err.item())
+        if e:
+            raise _lib.MMAError(f"peer exchange: rank {self.rank} timed out waiting for rank {e - 1}")
+
+
+_EXCHANGES: Dict[tuple, PeerExchange] = {}
+
+
+def exchange_for(sg, F: int, windows: Sequence[slice], device, owner: int = 0) -> PeerExchange:
+    """The PeerExchange of (ShardedGraph, layer `owner`, F, windows); built collectively on first use (every rank must
+    reach this call), cached on the graph.  Every layer owns its buffers: the gathered Q of its forward has to survive
+    until its own backward, whatever other layers run in between."""
+    key = (int(owner), int(F), tuple((s.start, s.stop) for s in windows))
+    cache = sg.__dict__.setdefault("_peer_exchanges", {})
+    ex = cache.get(key)
+    if ex is None:
+        ex = cache[key] = PeerExchange(sg.world, sg.rank, sg.max_rows, F, windows, device, sg.group)
+    return ex

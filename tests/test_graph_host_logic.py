@@ -109,8 +109,13 @@ def test_post_plan_tiles_cover_every_row_once_and_scalers_compound():
                               row_map=torch.randperm(deg.numel(), generator=torch.Generator().manual_seed(4)).int())
     scalers = ["identity", "amplification", "attenuation", "linear"]
     avg = {"lin": float(deg.float().mean()), "log": float((deg.float() + 1).log().mean())}
-    Fo, K, min_rows = 128, 640, 64
-    plan = PostPlan(g, scalers, avg, min_rows, Fo, K)
+    Fo, F, min_rows = 128, 128, 64
+    akinds = (1, 0, 2, 3, 5)                                   # mean, sum, min, max, std
+    plan = PostPlan(g, scalers, avg, min_rows, Fo, akinds, F)
+    K = plan.K
+    # the mean is not materialised: it rides on the sum block with coefficient 1 / deg
+    assert plan.mat == (0, 2, 3, 5) and plan.block_of == (0, 0, 1, 2, 3) and plan.inv == (True, False, False, False, False)
+    assert K == 4 * F
     n = deg.numel()
     seen = torch.zeros(n, dtype=torch.int64)
     big = {b: i for i, b in enumerate(plan.big)}
@@ -140,3 +145,16 @@ def test_post_plan_tiles_cover_every_row_once_and_scalers_compound():
     want = torch.stack([torch.ones_like(d), amp, amp * (avg["log"] / torch.log(d + 1)),
                         amp * (avg["log"] / torch.log(d + 1)) * (d / avg["lin"])])
     assert torch.equal(plan.cum, want)
+    # coef[b, s, a, m] = cum_s(d_b) * [a -> m] * (1 / d_b for the mean): contracting it with the reference's S x A blocks
+    # Y[s, a] = cum_s * agg_a reproduces the literal formula from the materialised blocks (sum, min, max, std)
+    B = len(plan.big)
+    assert plan.coef_big.shape == (B, 4, 5, 4)
+    gen = torch.Generator().manual_seed(0)
+    zsum, zmin, zmax, zstd = (torch.randn(B, generator=gen) for _ in range(4))
+    dbig = d[plan.big]
+    lit = torch.stack([zsum / dbig, zsum, zmin, zmax, zstd], 1).unsqueeze(1) * plan.cum[:, plan.big].t().unsqueeze(2)   # [B,S,A]
+    got = torch.einsum("bsam,bm->bsa", plan.coef_big, torch.stack([zsum, zmin, zmax, zstd], 1))
+    assert torch.allclose(got, lit, rtol=1e-6, atol=0)
+    from mma_b200.fused_layer import fold_blocks, materialised_blocks
+    assert fold_blocks((1, 2)) == ((0, 2), (0, 1), (True, False))          # a mean without a sum: a sum block is written
+    assert materialised_blocks(["mean", "sum", "min", "max", "std"]) == 4 and materialised_blocks(["min", "max"]) == 2
