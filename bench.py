@@ -659,6 +659,11 @@ def run_large(args, cfg, rank, world, local_rank):
                             "max_rows": graph.max_rows}
         rows = graph.rows
         graph.local.build_transpose()
+        from mma_b200 import fused_layer as _fl
+        cfg["exchange"] = {"kind": ("copy engines over NVLink peer memory (mma_b200/peer.py)" if _fl.EXCHANGE == "peer"
+                                    else "NCCL all-gather / reduce-scatter"),
+                           "feature_windows": args.slices,
+                           "bytes_on_the_wire_per_rank_per_step": 2 * (world - 1) * graph.max_rows * F * 4}
     else:
         graph = mma_b200.Graph(src, dst, N, sort_rows=True)      # degree-sorted CSR rows: scalers folded into the post GEMM
         rows = N

@@ -69,7 +69,9 @@ class PostPlan:
     that turn the S x A blocks of the post weight into ONE effective weight per degree over the materialised blocks:
     coef[b, s, a, m] = cum_s(d_b) * [block_of(a) == m] * (1 / max(d_b, 1) if a is a mean else 1)."""
 
-    def __init__(self, graph: Graph, scalers: Sequence[str], avg_deg: Dict[str, float], min_rows: int, Fo: int,
+    MAX_BIG = 256
+
+    def __init__(self, graph: Graph, scalers: Sequence[str], avg_deg: Dict[str, float], min_rows: Optional[int], Fo: int,
                  akinds: Sequence[int], F: int):
         dev = graph.device
         degs = [d for d, _, _ in graph.buckets]
@@ -86,6 +88,17 @@ class PostPlan:
             fold[:, a, self.block_of[a]] = (1.0 / degf) if self.inv[a] else 1.0
         self.fold = fold.to(dev)
         big, tiles, tiles_t, slabs, seg_ptr, tail_rows, tail_b = [], [], [], [], [0], [], []
+        if min_rows is None or min_rows <= 0:
+            # auto: every degree range gets its own effective weight (no tail path at all) as long as there are at most
+            # MAX_BIG of them -- a graph with few distinct degrees, e.g. config 4; on a skewed degree distribution the
+            # MAX_BIG largest ranges do, and the many tiny hub ranges beyond them take the literal formula
+            sizes = sorted((hi - lo for _, lo, hi in graph.buckets), reverse=True)
+            min_rows = 1
+            if len(sizes) > self.MAX_BIG:
+                min_rows = sizes[self.MAX_BIG - 1]
+                if sizes[self.MAX_BIG] == min_rows:          # ties at the cut: keep the count bounded
+                    min_rows += 1
+        self.min_rows = int(min_rows)
         for b, (_, lo, hi) in enumerate(graph.buckets):
             if hi - lo >= min_rows:
                 i = len(big)
@@ -116,8 +129,8 @@ class PostPlan:
                            * self.fold[self.tail_bucket].unsqueeze(1)).contiguous() if tail_rows else None)
 
 
-def post_plan(graph: Graph, scalers, avg_deg, min_rows: int, Fo: int, akinds, F: int) -> PostPlan:
-    key = ("tc", tuple(scalers), float(avg_deg["log"]), float(avg_deg["lin"]), int(min_rows), int(Fo), tuple(akinds), int(F))
+def post_plan(graph: Graph, scalers, avg_deg, min_rows: Optional[int], Fo: int, akinds, F: int) -> PostPlan:
+    key = ("tc", tuple(scalers), float(avg_deg["log"]), float(avg_deg["lin"]), int(min_rows or 0), int(Fo), tuple(akinds), int(F))
     plans = graph.__dict__.setdefault("_post_plans", {})
     p = plans.get(key)
     if p is None:
@@ -440,7 +453,7 @@ def supported(F_in: int, F_out: int, out_channels: int) -> bool:
 def fused_mmaconv(x: Tensor, graph, *, W_mask: Tensor, b_mask: Optional[Tensor], W_post: Tensor,
                   b_post: Optional[Tensor], W_lin: Tensor, b_lin: Optional[Tensor], R: Optional[Tensor],
                   keep: Optional[Tensor], aggregators: Sequence[str], scalers: Sequence[str],
-                  avg_deg: Dict[str, float], p_drop: float, seed: int, min_rows: int,
+                  avg_deg: Dict[str, float], p_drop: float, seed: int, min_rows: Optional[int],
                   seed_dev: Optional[Tensor] = None, n_windows: int = 2, owner: int = 0) -> Tensor:
     """x [N, F] (node order) -> MMAConv output [N, out] for towers == 1, pre_layers == post_layers == 1.
     W_mask [F, 2F or 3F] (the live mask Linear, Q2; only the first 2F columns are used here, the edge

@@ -109,7 +109,8 @@ class MMAConv(torch.nn.Module):
 
         self.use_tensor_cores = True         # towers == 1: whole layer as one autograd node over tcgen05 GEMMs + K1
         self.fold_scalers = True             # towers == 1: fold the scalers into the post weight (see _forward_folded)
-        self.fold_min_rows = 512             # degree ranges smaller than this use the literal formula
+        self.fold_min_rows = None            # degree ranges smaller than this use the literal formula (None: auto --
+                                             # no tail at all when the graph has at most 256 distinct in-degrees)
         self.comm_slices = 1                 # feature windows of the sharded exchange (1: full-width K1; narrow windows cost more in K1 than they hide)
         self.global_max_deg = None           # sharded runs: global max in-degree (else all-reduced per call)
         self.device_seed = False             # True: the dropout seed lives in a device tensor that is advanced ON the
@@ -300,7 +301,7 @@ class MMAConv(torch.nn.Module):
         first = self.post_nns[0][0]
         W = first.weight                                                             # [F_out, (S*A+1)*F_in]
         Hs = MF.scaled_post(Z.view(n, -1), W[:, F_in:], graph, self.scalers, self.avg_deg,
-                            min_rows=self.fold_min_rows)
+                            min_rows=self.fold_min_rows or 512)
         h = Hs.index_select(0, graph.row_rank) + F.linear(x, W[:, :F_in], first.bias)
         for m in list(self.post_nns[0])[1:]:
             h = m(h)

@@ -155,6 +155,16 @@ def test_post_plan_tiles_cover_every_row_once_and_scalers_compound():
     lit = torch.stack([zsum / dbig, zsum, zmin, zmax, zstd], 1).unsqueeze(1) * plan.cum[:, plan.big].t().unsqueeze(2)   # [B,S,A]
     got = torch.einsum("bsam,bm->bsa", plan.coef_big, torch.stack([zsum, zmin, zmax, zstd], 1))
     assert torch.allclose(got, lit, rtol=1e-6, atol=0)
+    # min_rows = None (the layer's default): at most MAX_BIG degree ranges get their own weight -- all of them on a graph
+    # with few distinct degrees (no tail path at all), the largest ones on a skewed one
+    auto = PostPlan(g, scalers, avg, None, Fo, akinds, F)
+    assert len(auto.big) <= PostPlan.MAX_BIG and auto.min_rows >= 1
+    if len(g.buckets) <= PostPlan.MAX_BIG:
+        assert auto.tail_idx is None and len(auto.big) == len(g.buckets)
+    few = types.SimpleNamespace(device=torch.device("cpu"), buckets=[(5, 0, 3), (4, 3, 1000), (0, 1000, 1001)],
+                                row_map=torch.arange(1001).int())
+    pf = PostPlan(few, scalers, avg, None, Fo, akinds, F)
+    assert pf.tail_idx is None and pf.big == [0, 1, 2] and pf.min_rows == 1
     from mma_b200.fused_layer import fold_blocks, materialised_blocks
     assert fold_blocks((1, 2)) == ((0, 2), (0, 1), (True, False))          # a mean without a sum: a sum block is written
     assert materialised_blocks(["mean", "sum", "min", "max", "std"]) == 4 and materialised_blocks(["min", "max"]) == 2
