@@ -179,7 +179,7 @@ def _k1_bwd(graph: Graph, P, Q, R, keep, F, akinds, p_drop, seed, dZ, arg_min, a
 
 def _k1_fwd_windows(graph: Graph, P: Tensor, ex, F: int, akinds, p_drop: float, seed: int, seed_dev):
     """K1 over this rank's rows, one launch per feature window of the peer exchange, each as soon as that window of
-    the gathered Q has arrived from every rank (column-window ABI: col0 / ncols, virtual Q base, ldq = window width)."""
+    the gathered Q has arrived from every rank (column-window ABI: col0 / ncols on the full-width gathered buffer)."""
     dev = P.device
     n, A = graph.n_dst, len(akinds)
     Z = torch.empty((n, A * F), dtype=torch.float32, device=dev)
@@ -191,42 +191,34 @@ def _k1_fwd_windows(graph: Graph, P: Tensor, ex, F: int, akinds, p_drop: float, 
     var = torch.empty((n, F), dtype=torch.float32, device=dev) if need_sq else None
     for k, s_ in enumerate(ex.windows):
         ex.wait(k)
-        q_ptr, ldq = ex.q_window(k)
-        MF.k1_forward(graph, P, None, None, None, T=1, F_in=F, akinds=akinds, skinds=(0,), tab=None, p_drop=p_drop,
+        MF.k1_forward(graph, P, ex.recv_q, None, None, T=1, F_in=F, akinds=akinds, skinds=(0,), tab=None, p_drop=p_drop,
                       seed=seed, Y=Z, arg_min=arg_min, arg_max=arg_max, mean=mean, var=var, local_args=True,
-                      seed_dev=seed_dev, col0=s_.start, ncols=s_.stop - s_.start, q_ptr=q_ptr, ldq=ldq)
+                      seed_dev=seed_dev, col0=s_.start, ncols=s_.stop - s_.start)
     return Z, arg_min, arg_max, mean, var
 
 
-def _k1_bwd_windows(graph: Graph, P, ex, F, akinds, p_drop, seed, dZ, arg_min, arg_max, mean, var, dP: Tensor,
+def _k1_bwd_sharded(graph: Graph, P, ex, F, akinds, p_drop, seed, dZ, arg_min, arg_max, mean, var, dP: Tensor,
                     need_sq: bool, seed_dev) -> None:
+    """Destination pass at full width, then the transpose pass OWNER BY OWNER (the partial dQ is laid out rank-major
+    over all sources): each owner's slice leaves on the copy engine while the next owner's rows are being summed."""
     dev = dZ.device
     graph.build_transpose()
-    G = torch.empty((graph.E, F), dtype=torch.float32, device=dev)       # CSC order, full width, filled window by window
-    for k, s_ in enumerate(ex.windows):
-        w = s_.stop - s_.start
-        q_ptr, ldq = ex.q_window(k) if need_sq else (None, None)
-        part = torch.empty((graph.n_src, w), dtype=torch.float32, device=dev)
-        if graph.E > 0:
-            MF.k1_backward_dst(graph, P, None, None, None, T=1, F_in=F, akinds=akinds, skinds=(0,), tab=None,
-                               p_drop=p_drop, seed=seed, dY=dZ, arg_min=arg_min, arg_max=arg_max, mean=mean, var=var,
-                               gslot=graph.csr2csc, G=G, ldg=F, dP=dP, lddp=dP.stride(0), local_args=True,
-                               seed_dev=seed_dev, col0=s_.start, ncols=w, q_ptr=q_ptr, ldq=ldq)
-            # transpose pass owner by owner (source rows are laid out rank-major): each owner's slice leaves on the copy
-            # engines while the next owner's rows are being summed
-            mr = ex.max_rows
-            for o in ex.owner_order():
-                with _lib.kernel_scope("mma_segment_sum_rows", dev):
-                    _lib.check(_lib.lib().mma_segment_sum_rows(graph.colptr.data_ptr() + 4 * o * mr, None, None, mr,
-                                                               G.data_ptr() + 4 * s_.start, F, w,
-                                                               part.data_ptr() + 4 * o * mr * w, w,
-                                                               _lib.stream_ptr(dev)), "mma_segment_sum_rows")
-                ex.push_partial_block(k, o, part)
-        else:
-            part.zero_()
-            if k == 0:
-                dP.zero_()
-            ex.push_partial(k, part)
+    part = torch.empty((graph.n_src, F), dtype=torch.float32, device=dev)
+    if graph.E == 0:
+        part.zero_(); dP.zero_()
+        ex.push_partial(part)
+        return
+    G = torch.empty((graph.E, F), dtype=torch.float32, device=dev)       # CSC order
+    MF.k1_backward_dst(graph, P, ex.recv_q if need_sq else None, None, None, T=1, F_in=F, akinds=akinds, skinds=(0,),
+                       tab=None, p_drop=p_drop, seed=seed, dY=dZ, arg_min=arg_min, arg_max=arg_max, mean=mean, var=var,
+                       gslot=graph.csr2csc, G=G, ldg=F, dP=dP, lddp=dP.stride(0), local_args=True, seed_dev=seed_dev)
+    mr = ex.max_rows
+    for o in ex.owner_order():
+        with _lib.kernel_scope("mma_segment_sum_rows", dev):
+            _lib.check(_lib.lib().mma_segment_sum_rows(graph.colptr.data_ptr() + 4 * o * mr, None, None, mr,
+                                                       _lib.ptr(G), F, F, part.data_ptr() + 4 * o * mr * F, F,
+                                                       _lib.stream_ptr(dev)), "mma_segment_sum_rows")
+        ex.push_partial_block(o, part)
 
 
 class _FusedMMAConv(torch.autograd.Function):
@@ -363,8 +355,8 @@ class _FusedMMAConv(torch.autograd.Function):
             dR = _k1_bwd(graph, P, Q, R, keep, F, plan.mat, p_drop, seed, dZ, arg_min, arg_max, mean, var,
                          dPQ[:, :F], dPQ[:, F:2 * F], need_R, seed_dev)
         elif ex is not None:
-            # per feature window: destination pass + transpose pass give this rank's PARTIAL dQ over all sources; its
-            # slices leave for their owners on the copy engines while the next window is computed; the owner sums the
+            # destination pass + transpose pass give this rank's PARTIAL dQ over all sources; its slices leave for their
+            # owners on the copy engine, owner by owner, while the next owner's rows are summed; the owner adds the
             # slices in rank order after the weight-gradient GEMM below, which does not depend on dQ
             need_sq = 4 in akinds or 5 in akinds
             if need_sq and ctx.ex_call != ex.fwd_calls:
@@ -372,7 +364,7 @@ class _FusedMMAConv(torch.autograd.Function):
                                    "the same layer; run backward before the next forward of this layer")
             ex.begin_call()
             dR = None
-            _k1_bwd_windows(graph, P, ex, F, plan.mat, p_drop, seed, dZ, arg_min, arg_max, mean, var, dPQ[:, :F],
+            _k1_bwd_sharded(graph, P, ex, F, plan.mat, p_drop, seed, dZ, arg_min, arg_max, mean, var, dPQ[:, :F],
                             need_sq, seed_dev)
         else:
             # NCCL variant: partial dQ over ALL sources, then one reduce-scatter
@@ -412,9 +404,7 @@ class _FusedMMAConv(torch.autograd.Function):
             dWy = g if dWy is None else dWy + g
         del dO
         if ex is not None:
-            dQv = dPQ[:, F:2 * F]
-            for k in range(len(ex.windows)):
-                ex.sum_window(k, dQv, n)
+            ex.sum_slices(dPQ[:, F:2 * F], n)
             ex.join()
         if pending is not None:
             dQ_loc, done = pending

@@ -41,7 +41,7 @@ from .. import functional as MF
 from .. import fused_layer
 from ..graph import Graph, cached_graph
 from ..parallel import ShardedGraph, sharded_mmconv_aggregate
-from ..linear import Linear, reset
+from ..linear import Linear, dense_linear, reset
 from .mask_aggr import MaskAggregateLinear
 
 _UID = itertools.count(1)
@@ -206,16 +206,21 @@ class MMAConv(torch.nn.Module):
                                f"{first[0].weight.size(1)}x{first[0].weight.size(0)})")
         if T == 1:
             w = first[0].weight
-            h = F.linear(out[:, 0], w[:, F_in:], first[0].bias) + F.linear(xt[:, 0], w[:, :F_in])
+            h = dense_linear(out[:, 0], w[:, F_in:], first[0].bias) + dense_linear(xt[:, 0], w[:, :F_in])
             hs = [h]
         else:
+            # T per-tower Linears as ONE GEMM with a block-diagonal weight [T*F_out, T*K] (tcgen05 3xTF32): the
+            # towers are tiny (ZINC: 450 -> 15), one launch beats T launches and the zero blocks cost nothing that
+            # matters at this size; gradients of the zero blocks are simply never read back
             W = torch.stack([m.weight for m in first])                  # [T, F_out, F_in + K]
             b = torch.stack([m.bias for m in first])                    # [T, F_out]
-            h = torch.einsum("ntk,tok->nto", out, W[:, :, F_in:]) + b
+            Fo = W.shape[1]
+            h = dense_linear(out.reshape(n, T * K), torch.block_diag(*W[:, :, F_in:].unbind(0)), b.reshape(-1))
             if self.divide_input:
-                h = h + torch.einsum("ntk,tok->nto", xt, W[:, :, :F_in])
+                h = h + dense_linear(xt.reshape(n, T * F_in), torch.block_diag(*W[:, :, :F_in].unbind(0)))
             else:
-                h = h + torch.einsum("nk,tok->nto", xt[:, 0], W[:, :, :F_in])
+                h = h + dense_linear(xt[:, 0], W[:, :, :F_in].reshape(T * Fo, F_in))
+            h = h.view(n, T, Fo)
             hs = [h[:, t] for t in range(T)]
         outs = []
         for t, seq in enumerate(self.post_nns):
@@ -236,16 +241,17 @@ class MMAConv(torch.nn.Module):
         b = torch.stack([m.bias for m in live]).reshape(1, T * F_in)
         if xt.size(1) == 1:                     # towers share x: one GEMM gives P and Q of all towers
             Wpq = torch.cat([W[:, :, :F_in].reshape(T * F_in, F_in), W[:, :, F_in:2 * F_in].reshape(T * F_in, F_in)])
-            PQ = F.linear(xt[:, 0], Wpq)                                            # [N, 2*T*F_in]
+            PQ = dense_linear(xt[:, 0], Wpq)                                        # [N, 2*T*F_in]
             P = PQ[:, :T * F_in] + b
             Q = PQ[:, T * F_in:]
-        else:
-            P = torch.einsum("ntk,tok->nto", xt, W[:, :, :F_in]).reshape(n, T * F_in) + b
-            Q = torch.einsum("ntk,tok->nto", xt, W[:, :, F_in:2 * F_in]).reshape(n, T * F_in)
+        else:                                   # divide_input: tower t sees its own slice -> block-diagonal weights
+            xf = xt.reshape(n, T * F_in)
+            P = dense_linear(xf, torch.block_diag(*W[:, :, :F_in].unbind(0))) + b
+            Q = dense_linear(xf, torch.block_diag(*W[:, :, F_in:2 * F_in].unbind(0)))
         R = None
         if edge_attr is not None:
             e = self.edge_encoder(edge_attr)                                        # [E, F_in], :143
-            R = F.linear(e, W[:, :, 2 * F_in:].reshape(T * F_in, F_in))             # [E, T*F_in]
+            R = dense_linear(e, W[:, :, 2 * F_in:].reshape(T * F_in, F_in))         # [E, T*F_in]
         return P, Q, R
 
     def _forward_fused(self, x: Tensor, graph: Graph, edge_attr: Optional[Tensor]) -> Tensor:
@@ -260,7 +266,7 @@ class MMAConv(torch.nn.Module):
         R = None
         if edge_attr is not None:
             e = self.edge_encoder(edge_attr)                                        # [E, F_in], :143
-            R = F.linear(e, live.weight[:, 2 * F_in:])
+            R = dense_linear(e, live.weight[:, 2 * F_in:])
         keep = self._inject_keep
         if keep is not None:
             keep = keep.reshape(graph.E, F_in)
@@ -302,7 +308,7 @@ class MMAConv(torch.nn.Module):
         W = first.weight                                                             # [F_out, (S*A+1)*F_in]
         Hs = MF.scaled_post(Z.view(n, -1), W[:, F_in:], graph, self.scalers, self.avg_deg,
                             min_rows=self.fold_min_rows or 512)
-        h = Hs.index_select(0, graph.row_rank) + F.linear(x, W[:, :F_in], first.bias)
+        h = Hs.index_select(0, graph.row_rank) + dense_linear(x, W[:, :F_in], first.bias)
         for m in list(self.post_nns[0])[1:]:
             h = m(h)
         return self.lin(h)

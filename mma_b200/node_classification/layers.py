@@ -26,6 +26,7 @@ from torch.nn.modules.module import Module
 from .. import _lib
 from .. import functional as MF
 from ..graph import NeighbourLists, cached_adj
+from ..linear import dense_mm
 from .scalers import SCALERS
 
 _UID = itertools.count(1)
@@ -70,7 +71,7 @@ class GraphConvolution(Module):
             self.bias.data.uniform_(-stdv, stdv)
 
     def forward(self, input, adj):
-        support = torch.mm(input, self.weight)
+        support = dense_mm(input, self.weight)             # x @ W on the tensor cores (3xTF32), layers.py:40
         output = spmm(adj, support)
         if self.bias is not None:
             return output + self.bias
@@ -190,7 +191,7 @@ class MMA(Module):
             masks = [getattr(self, "mask_" + nm) for nm in chunk]
             Wc = torch.cat([m[:F] for m in masks], dim=1)              # [F, A*F]   centre half  (:215 cen_nei)
             Wn = torch.cat([m[F:] for m in masks], dim=1)              # [F, A*F]   neighbour half
-            PQ = torch.mm(input, torch.cat([Wc, Wn], dim=1))           # one GEMM: [N, 2*A*F]
+            PQ = dense_mm(input, torch.cat([Wc, Wn], dim=1))           # one GEMM: [N, 2*A*F]
             PA, QA = PQ[:, :A * F], PQ[:, A * F:]
             acts = [_lib.ACT_RAW if (self.activation == "new_sigmoid" and nm in _RAW_UNDER_NEW_SIGMOID)
                     else _lib.ACT_SIGMOID for nm in chunk]
@@ -228,7 +229,7 @@ class MMA(Module):
                                "at non-singleton dimension 0")
         amp, att = _nc_scale_constants(N)
         # cat_s(scale_s(m)) @ cat([W,W,W])  (:856-860)  ==  (m + amp*m + att*m) @ W
-        support = torch.mm(m + amp * m + att * m, self.weight)                   # [A*N, C]
+        support = dense_mm(m + amp * m + att * m, self.weight)                   # [A*N, C]
         # spmm(cat((adj,)*A, 1), support) (:861-862) == adj @ sum_a support_a
         output = spmm(adj, support.view(A, N, -1).sum(dim=0))
         if self.bias is not None:

@@ -90,42 +90,40 @@ class SharedRegion:
 
 
 class PeerExchange:
-    """Buffers, flags and streams of the two exchanges for ONE (rows, width, windows) geometry.
+    """Buffers, flags and the copy stream of the two exchanges for ONE (rows, width) geometry.
 
-    recv_q   [W][world * max_rows, Fw]   gathered Q, one contiguous block per feature window (what K1's col0 / ncols /
-                                         ldq ABI reads); every rank pushes its rows of window k into every peer's block
-    slices   [W][world][max_rows, Fw]    partial-dQ slices as they arrive at their owner, summed in rank order
-    flags    [N_PHASES][world] uint64    flags[phase][sender] = epoch * 16 + phase of the sender's last announcement
+    recv_q   [world * max_rows, F]     gathered Q (rank-major, padded): every rank pushes its rows, feature window by
+                                       feature window (strided 2-D copies), into every peer's copy; K1 reads it with
+                                       its col0 / ncols ABI as soon as a window is complete
+    slices   [world][max_rows, F]      partial-dQ slices as they arrive at their owner, summed in rank order
+    flags    [N_PHASES][world] uint64  flags[phase][sender] = epoch * 16 + phase of the sender's last announcement
+
+    ONE copy stream: on an 8-GPU NVSwitch box concurrent copies to different peers from several streams were SLOWER
+    (434 GB/s with 4 streams, 414 with 7) than the same copies back to back on one stream in the staggered order
+    rank+1, rank+2, ... (590 GB/s per GPU per direction; 766 GB/s between 2 GPUs) -- profiles/r2i_peer_probe_8gpu.log.
     """
 
+    PHASE_BWD = 8
+
     def __init__(self, world: int, rank: int, max_rows: int, F: int, windows: Sequence[slice], device, group=None,
-                 n_copy_streams: int = 4):
+                 n_copy_streams: int = 1):
         self.world, self.rank, self.max_rows, self.F, self.group = world, rank, int(max_rows), int(F), group
         self.windows = list(windows)
         self.dev = device
-        W = len(self.windows)
-        if 2 * W + 1 > PHASE_ENTER:
+        if len(self.windows) > self.PHASE_BWD:
             raise ValueError("too many feature windows for the phase space of the flags")
-        widths = [s.stop - s.start for s in self.windows]
-        self.widths = widths
+        self.widths = [s.stop - s.start for s in self.windows]
         tot = world * self.max_rows
-        # ONE shared allocation per rank: [ recv_q blocks | slice blocks | flags ], window blocks laid out back to back
-        q_elems = sum(tot * w for w in widths)
-        self._off_recv, self._off_slice = 0, 4 * q_elems
-        self._off_flags = 8 * q_elems
+        # ONE shared allocation per rank: [ recv_q | slices | flags ]
+        q_elems = tot * self.F
+        self._off_recv, self._off_slice, self._off_flags = 0, 4 * q_elems, 8 * q_elems
         self.region = SharedRegion(8 * q_elems + 8 * N_PHASES * world, device, group)
-        self._recv_flat = self.region.view(self._off_recv, (q_elems,), torch.float32)
-        self._slice_flat = self.region.view(self._off_slice, (q_elems,), torch.float32)
+        self.recv_q = self.region.view(self._off_recv, (tot, self.F), torch.float32)
+        self.slices = self.region.view(self._off_slice, (world, self.max_rows, self.F), torch.float32)
         self._flags = self.region.view(self._off_flags, (N_PHASES, world), torch.int64)
         self.epoch = torch.zeros(1, dtype=torch.int64, device=device)
         self.vals = torch.zeros(N_PHASES, dtype=torch.int64, device=device)
         self.err = torch.zeros(1, dtype=torch.int32, device=device)
-        self.q_off, off = [], 0
-        for w in widths:
-            self.q_off.append(off)
-            off += tot * w
-        self.recv_q = [self._recv_flat[o: o + tot * w].view(tot, w) for o, w in zip(self.q_off, widths)]
-        self.slices = [self._slice_flat[o: o + tot * w].view(world, self.max_rows, w) for o, w in zip(self.q_off, widths)]
         self.streams = [torch.cuda.Stream(device=device, priority=-1) for _ in range(max(1, min(n_copy_streams, world)))]
         self.fwd_calls = 0          # host-side count of forward calls (guards the gathered Q a backward re-reads)
         torch.cuda.synchronize(device)
@@ -168,16 +166,20 @@ class PeerExchange:
                        "mma_peer_wait")
 
     def _peer_order(self):
-        return [(self.rank + k) % self.world for k in range(self.world)]      # self first, then staggered
+        """Peers in sending order: rank+1, rank+2, ... (at any moment the ranks address distinct destinations), this
+        rank's own copy last."""
+        return [(self.rank + 1 + k) % self.world for k in range(self.world)]
+
+    owner_order = _peer_order
 
     # ---------------------------------------------------------------- forward: all-gather of Q, window by window
     def push_q(self, Q: Tensor, rows: int) -> None:
-        """Q [rows, F] (unit column stride; may be a column view of a wider matrix): window k goes, as a strided 2-D copy
-        straight out of Q (measured 670-750 GB/s even for 32-column windows of a 1536-byte pitch: no pack pass needed),
-        into rows [rank * max_rows, +rows) of every rank's recv_q[k]; phase k announces it.  The copy streams first
-        wait for all ranks' entry announcement (their receive buffers are free)."""
-        if Q.stride(1) != 1 or Q.dtype != torch.float32:
-            raise RuntimeError("push_q: Q must be fp32 with unit column stride")
+        """Q [rows, F] (unit column stride; may be a column view of a wider matrix): columns of window k go, as strided
+        2-D copies straight out of Q (no pack pass), into rows [rank * max_rows, +rows) of every rank's recv_q; phase k
+        announces the window.  The copy stream first waits for all ranks' entry announcement (their receive buffers
+        are free)."""
+        if Q.stride(1) != 1 or Q.dtype != torch.float32 or Q.shape[1] != self.F:
+            raise RuntimeError("push_q: Q must be fp32 [rows, F] with unit column stride")
         cur = torch.cuda.current_stream(self.dev)
         ev = torch.cuda.Event()
         ev.record(cur)
@@ -185,61 +187,54 @@ class PeerExchange:
             st.wait_event(ev)
             self.wait(PHASE_ENTER, st)
         lib = _lib.lib()
-        spitch = Q.stride(0) * 4
+        spitch, dpitch = Q.stride(0) * 4, self.F * 4
+        full = len(self.windows) == 1 and Q.stride(0) == self.F
         for k, (s_, w) in enumerate(zip(self.windows, self.widths)):
             src = Q.data_ptr() + 4 * s_.start
             for o in self._peer_order():
-                dst = self.region.base[o] + self._off_recv + 4 * (self.q_off[k] + self.rank * self.max_rows * w)
+                dst = self.region.base[o] + self._off_recv + 4 * (self.rank * self.max_rows * self.F + s_.start)
                 with torch.cuda.device(self.dev):
-                    _lib.check(lib.mma_peer_copy_2d(dst, w * 4, src, spitch, w * 4, rows, self._stream_for(o).cuda_stream),
-                               "mma_peer_copy_2d")
+                    if full:
+                        self._copy(dst, src, rows * self.F * 4, self._stream_for(o))
+                    else:
+                        _lib.check(lib.mma_peer_copy_2d(dst, dpitch, src, spitch, w * 4, rows,
+                                                        self._stream_for(o).cuda_stream), "mma_peer_copy_2d")
             self._announce(k, self._peer_order())
         for st in self.streams:
             Q.record_stream(st)
 
-    def q_window(self, k: int):
-        """(base pointer shifted back by col0 columns, ldq) of the gathered window k for K1's q_ptr / ldq."""
-        return self.recv_q[k].data_ptr() - 4 * self.windows[k].start, self.widths[k]
-
     # ---------------------------------------------------------------- backward: reduce-scatter of the partial dQ
-    def push_partial_block(self, k: int, o: int, part: Tensor) -> None:
-        """part [world * max_rows, Fw] (contiguous) holds this rank's partial dQ of window k; its rows of OWNER o
+    def push_partial_block(self, o: int, part: Tensor) -> None:
+        """part [world * max_rows, F] (contiguous) holds this rank's partial dQ; its rows of OWNER o
         (rows [o * max_rows, +max_rows)) are final once the kernels enqueued so far on the current stream have run:
-        they go into slices[k][my rank] of rank o, and phase W + k announces them to o.  Calling it block by block,
-        right after the transpose pass of each owner's source rows, lets the slices leave while the next block is
-        still being summed."""
-        W, w = len(self.windows), self.widths[k]
+        they go into slices[my rank] of rank o, and PHASE_BWD announces them to o.  Calling it block by block, right
+        after the transpose pass of each owner's source rows, lets the slices leave while the next block is still
+        being summed."""
         cur = torch.cuda.current_stream(self.dev)
         ev = torch.cuda.Event()
         ev.record(cur)
         st = self._stream_for(o)
         st.wait_event(ev)
-        nbytes = self.max_rows * w * 4
-        dst = self.region.base[o] + self._off_slice + 4 * (self.q_off[k] + self.rank * self.max_rows * w)
-        src = part.data_ptr() + 4 * o * self.max_rows * w
+        nbytes = self.max_rows * self.F * 4
+        dst = self.region.base[o] + self._off_slice + 4 * self.rank * self.max_rows * self.F
+        src = part.data_ptr() + 4 * o * self.max_rows * self.F
         with torch.cuda.device(self.dev):
             self._copy(dst, src, nbytes, st)
-        self._announce(W + k, [o])
+        self._announce(self.PHASE_BWD, [o])
         part.record_stream(st)
 
-    def push_partial(self, k: int, part: Tensor) -> None:
-        """All owners' blocks of window k at once (the whole `part` is final)."""
+    def push_partial(self, part: Tensor) -> None:
+        """All owners' blocks at once (the whole `part` is final)."""
         for o in self._peer_order():
-            self.push_partial_block(k, o, part)
+            self.push_partial_block(o, part)
 
-    def owner_order(self):
-        """Owners in the order their blocks should be produced and sent: the next rank first, this rank last."""
-        return [(self.rank + 1 + j) % self.world for j in range(self.world)]
-
-    def sum_window(self, k: int, out: Tensor, rows: int) -> None:
-        """out[:, window k] (a [rows, >= F] view with unit column stride) = sum over ranks, ascending, of the arrived
-        slices -- after waiting for phase W + k on the current stream."""
-        W, w = len(self.windows), self.widths[k]
-        self.wait(W + k)
-        ptrs = (C.c_void_p * self.world)(*[self.slices[k][r].data_ptr() for r in range(self.world)])
-        dst = out.data_ptr() + 4 * self.windows[k].start
+    def sum_slices(self, out: Tensor, rows: int) -> None:
+        """out (a [rows, F] view with unit column stride) = sum over ranks, ascending, of the arrived slices -- after
+        waiting for PHASE_BWD on the current stream."""
+        self.wait(self.PHASE_BWD)
+        ptrs = (C.c_void_p * self.world)(*[self.slices[r].data_ptr() for r in range(self.world)])
         with torch.cuda.device(self.dev):
-            _lib.check(_lib.lib().mma_sum_slices(ptrs, self.world, rows, w, dst, out.stride(0),
+            _lib.check(_lib.lib().mma_sum_slices(ptrs, self.world, rows, self.F, out.data_ptr(), out.stride(0),
                                                  _lib.stream_ptr(self.dev)), "mma_sum_slices")
 
     def join(self) -> None:

@@ -90,13 +90,13 @@ del out, big
 torch.cuda.synchronize(); dist.barrier(); region.close()
 torch.cuda.empty_cache()
 
-# ---- the protocol: push_q / wait / push_partial / sum_window against NCCL, eager and graph replay
+# ---- the protocol: push_q / wait / push_partial / sum_slices against NCCL, eager and graph replay
 for n_win in (1, 2, 4):
     wins = _slices(F, n_win)
     ex = PeerExchange(world, rank, rows, F, wins, dev)
     Q = torch.randn(rows, 3 * F, device=dev)[:, F:2 * F]            # strided view like PQX[:, F:2F]
     ref = torch.empty(world * rows, F, device=dev)
-    part = [torch.randn(world * rows, s.stop - s.start, device=dev) for s in wins]
+    part = torch.randn(world * rows, F, device=dev)
     dq = torch.zeros(rows, 2 * F, device=dev)
     sink = torch.zeros(world * rows, F, device=dev)
 
@@ -105,21 +105,19 @@ for n_win in (1, 2, 4):
         ex.push_q(Q, rows)
         for k, s in enumerate(wins):
             ex.wait(k)
-            sink[:, s] = ex.recv_q[k]                                 # a consumer of window k on the compute stream
+            sink[:, s] = ex.recv_q[:, s]                              # a consumer of window k on the compute stream
         ex.join()
         ex.begin_call()
-        for k in range(len(wins)):
-            ex.push_partial(k, part[k])
-        for k in range(len(wins)):
-            ex.sum_window(k, dq[:, F:], rows)
+        for o in ex.owner_order():
+            ex.push_partial_block(o, part)
+        ex.sum_slices(dq[:, F:], rows)
         ex.join()
 
     def check(tag):
         dist.all_gather_into_tensor(ref, Q.contiguous())
         ok_q = torch.equal(sink, ref)
-        full = torch.cat(part, 1)
         want = torch.empty(rows, F, device=dev)
-        dist.reduce_scatter_tensor(want, full.contiguous())
+        dist.reduce_scatter_tensor(want, part)
         err = float((dq[:, F:] - want).abs().max() / want.abs().max())
         ex.check()
         t = torch.tensor([float(ok_q), -err], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MIN)
@@ -135,8 +133,8 @@ for n_win in (1, 2, 4):
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
         call()
-    for it in range(3):
-        Q.normal_(); [p.normal_() for p in part]; sink.zero_(); dq.zero_()
+    for it in range(2):
+        Q.normal_(); part.normal_(); sink.zero_(); dq.zero_()
         torch.cuda.synchronize(); dist.barrier()
         g.replay()
         check(f"CUDA graph replay {it}")
