@@ -285,6 +285,8 @@ int mma_tf32_split(const float *w, float *hi, float *lo, int64_t n, mma_stream_t
  *   row-major output leave through TMA tile stores); everything else the streaming kernel.  Environment
  *   switches for A/B runs, read once per process: MMA_GEMM_ARES=0 (always stream), MMA_GEMM_TMA_STORE=0. */
 #define MMA_GEMM_ADD_BY_INPUT_ROW 4
+#define MMA_GEMM_RELU 8           /* or-ed into `mode`: C = max(C, 0) after bias / addend (BatchNorm-in-eval + ReLU
+                                     folded into the layer's `lin`, graph_regression/mma.py:120-121) */
 
 int mma_linear_tf32x3(const float *A0, int64_t lda0, int K0, const float *A1, int64_t lda1, int K1,
                       const float *Bhi, const float *Blo, int64_t ldb, int64_t b_rows,
@@ -307,6 +309,24 @@ int mma_reduce_slabs(const float *part, const float *coef, int64_t n_slots, int6
 /* out[g][i] = sum of part[s][i] for s in [seg_ptr[g], seg_ptr[g+1]), ascending s; out [n_segs][n]. */
 int mma_reduce_slabs_segmented(const float *part, const int32_t *seg_ptr, int64_t n_segs, int64_t n,
                                float *out, mma_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * BatchNorm + ReLU over the rows of x [n, F] in ONE kernel per direction: the step that follows the layer in
+ * the reference's Net (graph_regression/mma.py:120-121, `F.relu(batch_norm(conv(...)))`).
+ *   mean_in / var_in NULL : batch statistics (training) -- two-pass mean / centred second moment, biased variance
+ *                           for the normalisation; running_mean / running_var (optional) are updated with
+ *                           `momentum` and the unbiased variance, as torch.nn.BatchNorm1d does;
+ *   mean_in / var_in given: those statistics (eval mode).
+ *   save_mean / save_rstd [F] (optional out): what the backward needs.  gamma / beta NULL = 1 / 0.
+ * Backward: dz = dy * (y > 0); dx (optional), dgamma, dbeta (optional) -- batch_stats != 0: the statistics
+ * depended on x.  Fixed-order reductions, no atomics.  One CTA per 32 columns: sized for batches of small graphs.
+ * ---------------------------------------------------------------------- */
+int mma_bn_relu_fwd(const float *x, int64_t ldx, int64_t n, int F, const float *gamma, const float *beta, float eps,
+                    const float *mean_in, const float *var_in, float *y, int64_t ldy, float *save_mean,
+                    float *save_rstd, float *running_mean, float *running_var, float momentum, mma_stream_t stream);
+int mma_bn_relu_bwd(const float *x, int64_t ldx, const float *y, int64_t ldy, const float *dy, int64_t lddy,
+                    int64_t n, int F, const float *gamma, const float *save_mean, const float *save_rstd,
+                    int batch_stats, float *dx, int64_t lddx, float *dgamma, float *dbeta, mma_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * C1: the two exchanges of the destination-range sharded layer (new -- the reference

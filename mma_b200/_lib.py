@@ -57,6 +57,8 @@ _SIGS = {
     "mma_reduce_slabs": ([_vp, _vp, _i64, _i64, _vp, _vp], C.c_int),
     "mma_reduce_slabs_segmented": ([_vp, _vp, _i64, _i64, _vp, _vp], C.c_int),
     "mma_peer_epoch_advance": ([_vp, _vp, _vp], C.c_int),
+    "mma_bn_relu_fwd": ([_vp, _i64, _i64, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _f32, _vp], C.c_int),
+    "mma_bn_relu_bwd": ([_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _vp], C.c_int),
     "mma_peer_alloc": ([C.c_size_t, C.POINTER(_vp), _vp], C.c_int),
     "mma_peer_free": ([_vp], C.c_int),
     "mma_peer_open": ([_vp, C.POINTER(_vp)], C.c_int),

@@ -67,6 +67,7 @@ struct alignas(64) NtParams {
     const float *add;           // indexed like C (output rows) or, add_in != 0, by the input row
     int64_t ldadd;
     int add_in;
+    int relu;                   // epilogue: C = max(C, 0) after bias / addend (MMA_GEMM_RELU)
 };
 
 struct Tile { int64_t row0, row_end; int b_off, n0; };
@@ -107,6 +108,8 @@ __device__ __forceinline__ void store_chunk(float *stg, const uint32_t (&r)[32],
                                             int col0, int n_cols, float *C, int64_t ldc, const int32_t *out_map,
                                             const float *bias, const float *add, int64_t ldadd, int add_in) {
     (void)stg;
+    const bool relu = (add_in & 2) != 0;            // bit 1 of the flag word: ReLU after bias / addend
+    add_in &= 1;
     const int64_t grow = row0 + lane;
     if (grow >= row_end || col0 >= n_cols) return;
     const int64_t orow = out_map ? (int64_t)__ldg(out_map + grow) : grow;
@@ -138,6 +141,10 @@ __device__ __forceinline__ void store_chunk(float *stg, const uint32_t (&r)[32],
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] += av[8 * j + i];
             }
+            if (relu) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.0f);
+            }
             asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(crow + 8 * j), "f"(v[0]), "f"(v[1]),
                          "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
                          : "memory");
@@ -160,6 +167,7 @@ __device__ __forceinline__ void store_chunk(float *stg, const uint32_t (&r)[32],
                 v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
             }
             if (arow) { v.x += av[j].x; v.y += av[j].y; v.z += av[j].z; v.w += av[j].w; }
+            if (relu) { v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f); }
             __stcs(reinterpret_cast<float4 *>(crow) + j, v);
         }
     }
@@ -337,7 +345,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_kernel(const __grid_con
                     if (lane == 0) mbar_arrive(tempty_bar(buf));
                 }
                 store_chunk(stg, r, lane, tl.row0 + wq * 32, tl.row_end, tl.n0 + c * 32, p.N, p.C, p.ldc, p.out_map,
-                            p.bias, p.add, p.ldadd, p.add_in);
+                            p.bias, p.add, p.ldadd, p.add_in | (p.relu << 1));
                 __syncwarp();
             }
         }
@@ -574,7 +582,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) gemm_nt_ares_kernel(const __gri
                     const int col0 = j * AR_BN + c * 32;
                     if (!via_tma) {
                         store_chunk(nullptr, r, lane, tl.row0 + wq * 32, tl.row_end, col0, p.N, p.C, p.ldc,
-                                    p.out_map, p.bias, p.add, p.ldadd, p.add_in);
+                                    p.out_map, p.bias, p.add, p.ldadd, p.add_in | (p.relu << 1));
                         __syncwarp();
                         continue;
                     }
@@ -941,7 +949,7 @@ extern "C" int mma_linear_tf32x3(const float *A0, int64_t lda0, int K0, const fl
                                  const float *add, int64_t ldadd, int mode_flags, int max_ctas, mma_stream_t stream) {
     if (!A0 || !Bhi || !Blo || !C || M < 0 || N < 1 || K0 < 1 || K1 < 0 || b_rows < 1) return MMA_ERR_INVALID;
     const int mode = mode_flags & 3;
-    if (mode_flags < 0 || mode > 2 || (mode_flags & ~(3 | MMA_GEMM_ADD_BY_INPUT_ROW))) return MMA_ERR_INVALID;
+    if (mode_flags < 0 || mode > 2 || (mode_flags & ~(3 | MMA_GEMM_ADD_BY_INPUT_ROW | MMA_GEMM_RELU))) return MMA_ERR_INVALID;
     if ((N % 4) != 0 || (ldc % 4) != 0 || !aligned16(C) || !aligned16(bias) || !aligned16(add) || (ldadd % 4) != 0)
         return MMA_ERR_UNSUPPORTED;
     if (K1 > 0 && (!A1 || (K0 % BK) != 0)) return MMA_ERR_INVALID;
@@ -965,6 +973,7 @@ extern "C" int mma_linear_tf32x3(const float *A0, int64_t lda0, int K0, const fl
     if (p.n_tiles_m < 1) return tile_tab ? MMA_OK : MMA_ERR_INVALID;
     p.C = C; p.ldc = ldc; p.out_map = out_map; p.bias = bias; p.add = add; p.ldadd = ldadd;
     p.add_in = (mode_flags & MMA_GEMM_ADD_BY_INPUT_ROW) ? 1 : 0;
+    p.relu = (mode_flags & MMA_GEMM_RELU) ? 1 : 0;
     int sms = 0, dev = 0;
     MMA_CUDA_CHECK(cudaGetDevice(&dev));
     MMA_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -975,7 +984,7 @@ extern "C" int mma_linear_tf32x3(const float *A0, int64_t lda0, int K0, const fl
         if ((rc = make_map_2d(&p.map_bhi, Bhi, b_rows, K0, ldb, AR_BN, BK)) != MMA_OK) return rc;
         if ((rc = make_map_2d(&p.map_blo, Blo, b_rows, K0, ldb, AR_BN, BK)) != MMA_OK) return rc;
         static const bool tma_st = [] { const char *e = getenv("MMA_GEMM_TMA_STORE"); return !(e && e[0] == '0'); }();
-        p.tma_store = (tma_st && !out_map && !add && make_map_2d(&p.map_c, C, M, N, ldc, 32, 32) == MMA_OK) ? 1 : 0;
+        p.tma_store = (tma_st && !out_map && !add && !p.relu && make_map_2d(&p.map_c, C, M, N, ldc, 32, 32) == MMA_OK) ? 1 : 0;
         MMA_CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_ares_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AR_SMEM_BYTES));
         const unsigned grid = (unsigned)(p.n_tiles_m < sms ? p.n_tiles_m : sms);
         gemm_nt_ares_kernel<<<grid, AR_THREADS, AR_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(p);

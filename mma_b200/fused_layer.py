@@ -37,6 +37,7 @@ OVERLAP_EXCHANGE = os.environ.get("MMA_OVERLAP_EXCHANGE", "0") == "1"
 # How the sharded layer's two exchanges travel: "peer" = copy engines over NVLink peer memory, pipelined per feature
 # window (mma_b200/peer.py, the default); "nccl" = one all-gather / reduce-scatter (the round-1 path, kept for A/B runs).
 EXCHANGE = os.environ.get("MMA_EXCHANGE", "peer")
+G_ORDER = os.environ.get("MMA_G_ORDER", "csc")       # order of the per-edge gradient rows G (see _k1_bwd)
 
 # Parity hook (bench.py --verify, tests): when set to a dict, every forward leaves references to its raw aggregates
 # and arg indices there (Z in CSR-row order, arg_min / arg_max as CSR slots), so a sharded run can be compared bit for
@@ -166,10 +167,18 @@ def _k1_bwd(graph: Graph, P, Q, R, keep, F, akinds, p_drop, seed, dZ, arg_min, a
     graph.build_transpose()
     G = torch.empty((E, F), dtype=torch.float32, device=dev)
     gslot = graph.perm if need_R else graph.csr2csc
+    idx = graph.perm_t if need_R else None
+    if G_ORDER == "csr" and not need_R:
+        # A/B variant (MMA_G_ORDER=csr): G in CSR order -- sequential row stores in the destination pass, random row
+        # gathers in the transpose pass; same bytes as the default (scattered stores, sequential reads).  Measured
+        # slower on config 4 (profiles/README.md, round 2), kept for re-measurement only.
+        if "_csc2csr" not in graph.__dict__:
+            from .graph import invert_perm
+            graph.__dict__["_csc2csr"] = invert_perm(graph.csr2csc)
+        gslot, idx = None, graph.__dict__["_csc2csr"]
     MF.k1_backward_dst(graph, P, Q, R, keep, T=1, F_in=F, akinds=akinds, skinds=(0,), tab=None, p_drop=p_drop,
                        seed=seed, dY=dZ, arg_min=arg_min, arg_max=arg_max, mean=mean, var=var, gslot=gslot, G=G,
                        ldg=F, dP=dP, lddp=dP.stride(0), local_args=True, seed_dev=seed_dev)
-    idx = graph.perm_t if need_R else None
     with _lib.kernel_scope("mma_segment_sum_rows", dev):
         _lib.check(_lib.lib().mma_segment_sum_rows(_lib.ptr(graph.colptr), _lib.ptr(idx), None, graph.n_src, _lib.ptr(G),
                                                    F, F, _lib.ptr(dQ), dQ.stride(0), _lib.stream_ptr(dev)),

@@ -175,7 +175,18 @@ class MMAConv(torch.nn.Module):
 
     # ------------------------------------------------------------------ forward
     def forward(self, x: Tensor, edge_index, edge_attr: Optional[Tensor] = None) -> Tensor:
+        return self._forward_impl(x, edge_index, edge_attr, None)
+
+    def forward_affine_relu(self, x: Tensor, edge_index, edge_attr: Optional[Tensor], scale: Tensor,
+                            shift: Tensor) -> Tensor:
+        """relu(forward(x, ...) * scale + shift) for per-channel scale / shift [out_channels]: BatchNorm in eval mode
+        followed by ReLU (graph_regression/mma.py:120-121) folded into the layer's `lin` -- scaled weight rows, shifted
+        bias, ReLU in the GEMM epilogue -- on the general (towers > 1) path; the other paths apply it after the layer."""
+        return self._forward_impl(x, edge_index, edge_attr, (scale, shift))
+
+    def _forward_impl(self, x: Tensor, edge_index, edge_attr: Optional[Tensor], epilogue) -> Tensor:
         T, F_in = self.towers, self.F_in
+        post = (lambda y: y) if epilogue is None else (lambda y: F.relu(y * epilogue[0] + epilogue[1]))
         self._check_names()                     # ValueError first, whatever the device (message(), :150-154)
         if self.divide_input:
             xt = x.view(-1, T, F_in)
@@ -187,13 +198,13 @@ class MMAConv(torch.nn.Module):
                         fused_layer.supported(F_in, self.F_out, self.out_channels))
             graph = self._graph(edge_index, n, sort_rows=True)
             if fused_ok and isinstance(graph, Graph) and graph.row_map is not None:
-                return self._forward_fused(x.view(n, F_in), graph, edge_attr)
+                return post(self._forward_fused(x.view(n, F_in), graph, edge_attr))
             if (fused_ok and isinstance(graph, ShardedGraph) and edge_attr is None and self._inject_keep is None
                     and graph.local is not None):
-                return self._forward_fused(x.view(n, F_in), graph, None)
+                return post(self._forward_fused(x.view(n, F_in), graph, None))
             local = graph.local if isinstance(graph, ShardedGraph) else graph
             if local.buckets is not None and not (isinstance(graph, ShardedGraph) and edge_attr is not None):
-                return self._forward_folded(xt[:, 0], graph, edge_attr)
+                return post(self._forward_folded(xt[:, 0], graph, edge_attr))
             edge_index = graph
         out = self.propagate(edge_index, x=xt, edge_attr=edge_attr, size=None)      # [N,T,S*A*F_in]
 
@@ -229,7 +240,11 @@ class MMAConv(torch.nn.Module):
                 v = m(v)
             outs.append(v)
         out = outs[0] if T == 1 else torch.cat(outs, dim=1)
-        return self.lin(out)
+        if epilogue is None:
+            return self.lin(out)
+        scale, shift = epilogue
+        b = self.lin.bias if self.lin.bias is not None else torch.zeros_like(shift)
+        return dense_linear(out, self.lin.weight * scale.unsqueeze(1), b * scale + shift, relu=True)
 
     def _mask_projections(self, xt: Tensor, edge_attr: Optional[Tensor]):
         """P = X W_i^T + b, Q = X W_j^T (node-level) and R = enc(e) W_e^T (edge-level): the mask

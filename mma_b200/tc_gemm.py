@@ -16,6 +16,7 @@ from . import _lib
 BM = BN = 128
 BK = 32
 ADD_BY_INPUT_ROW = 4    # MMA_GEMM_ADD_BY_INPUT_ROW
+RELU = 8                # MMA_GEMM_RELU
 MODE = 1            # 0: 3xTF32, hi rounded to nearest and written back; 1: raw operand as (truncated) hi -- same
                     # measured accuracy, a 5x cheaper split; 2: plain TF32 (not fp32-accurate)
 
@@ -45,7 +46,8 @@ def split_weight(W: Tensor) -> Tuple[Tensor, Tensor]:
 def linear(A0: Tensor, Whi: Tensor, Wlo: Tensor, n_out: int, *, A1: Optional[Tensor] = None,
            tile_tab: Optional[Tensor] = None, out: Optional[Tensor] = None, out_map: Optional[Tensor] = None,
            bias: Optional[Tensor] = None, add: Optional[Tensor] = None, add_by_input_row: bool = False,
-           mode: Optional[int] = None, max_ctas: int = 0, name: str = "mma_linear_tf32x3") -> Tensor:
+           mode: Optional[int] = None, max_ctas: int = 0, relu: bool = False,
+           name: str = "mma_linear_tf32x3") -> Tensor:
     """out[out_map[r]] = [A0|A1][r] @ W[b_off : b_off + n_out].T (+ bias) (+ add[out_map[r]], or add[r]
     with add_by_input_row).
 
@@ -70,7 +72,8 @@ def linear(A0: Tensor, Whi: Tensor, Wlo: Tensor, n_out: int, *, A1: Optional[Ten
             _lib.ptr(tile_tab), 0 if tile_tab is None else tile_tab.shape[0],
             _lib.ptr(out), out.stride(0), _lib.ptr(out_map), _lib.ptr(bias), _lib.ptr(add),
             0 if add is None else add.stride(0),
-            (MODE if mode is None else mode) | (ADD_BY_INPUT_ROW if add_by_input_row else 0), max_ctas,
+            (MODE if mode is None else mode) | (ADD_BY_INPUT_ROW if add_by_input_row else 0) | (RELU if relu else 0),
+            max_ctas,
             _lib.stream_ptr(dev)), name)
     return out
 

@@ -206,3 +206,75 @@ def test_graph_cache_survives_address_reuse():
         dense = adj.to_dense()
         assert torch.equal((s.rowptr[1:] - s.rowptr[:-1]).long(), (dense != 0).sum(1))
         del idx, adj, s, dense
+
+
+def test_kernels_stay_inside_their_output_buffers():
+    """compute-sanitizer is closed on this GPU pool (profiles/r2l_compute_sanitizer_closed.log), so the out-of-bounds
+    check is done by hand: every output of the hot kernels is a window inside a larger allocation whose guard bands
+    (before, after, and the padding columns of every row) hold a bit pattern that must survive the launch.  Odd sizes on
+    purpose: rows not a multiple of the tile / chunk sizes, a ragged last tile, empty rows, a hub row."""
+    import mma_b200
+    from mma_b200 import functional as MF, tc_gemm as tg, _lib
+    dev = torch.device("cuda")
+    GUARD = 0x7FC0DEAD                      # a NaN payload no kernel produces
+
+    def guarded(rows, cols, dtype, pad_cols=4, pad_rows=3):
+        full = torch.full((rows + 2 * pad_rows, cols + pad_cols), GUARD, dtype=torch.int32, device=dev)
+        view = full[pad_rows:pad_rows + rows, :cols].view(dtype)
+        return full, view, (pad_rows, rows, cols)
+
+    def intact(full, geom, what):
+        pad_rows, rows, cols = geom
+        assert bool((full[:pad_rows] == GUARD).all()) and bool((full[pad_rows + rows:] == GUARD).all()), f"{what}: rows outside"
+        assert bool((full[:, cols:] == GUARD).all()), f"{what}: padding columns"
+
+    n, E, F = 1237, 20011, 128
+    g = torch.Generator().manual_seed(9)
+    src = torch.randint(0, n, (E,), generator=g)
+    dst = torch.randint(0, n - 7, (E,), generator=g)
+    dst[:3000] = 5                                                  # a hub row
+    graph = mma_b200.Graph(src.to(dev), dst.to(dev), n, sort_rows=True)
+    graph.build_transpose()
+    P, Q = torch.randn(n, F, generator=g).to(dev), torch.randn(n, F, generator=g).to(dev)
+    akinds = (0, 2, 3, 5)
+    A = len(akinds)
+    Zf, Z, gz = guarded(n, A * F, torch.float32)
+    amf, amin, ga = guarded(n, F, torch.int32, pad_cols=0)          # [n, F] contiguous by contract: row guards only
+    axf, amax, gx = guarded(n, F, torch.int32, pad_cols=0)
+    mf, mean, gm = guarded(n, F, torch.float32, pad_cols=0)
+    vf, var, gv = guarded(n, F, torch.float32, pad_cols=0)
+    MF.k1_forward(graph, P, Q, None, None, T=1, F_in=F, akinds=akinds, skinds=(0,), tab=None, p_drop=0.5, seed=3, Y=Z,
+                  arg_min=amin, arg_max=amax, mean=mean, var=var, local_args=True)
+    torch.cuda.synchronize()
+    for full, geom, what in ((Zf, gz, "Z"), (amf, ga, "argmin"), (axf, gx, "argmax"), (mf, gm, "mean"), (vf, gv, "var")):
+        intact(full, geom, "K1 forward " + what)
+    assert bool(torch.isfinite(Z).all())
+    dZ = torch.randn(n, A * F, generator=g).to(dev)
+    Gf, G, gg = guarded(E, F, torch.float32)
+    dPf, dP, gp = guarded(n, F, torch.float32)
+    MF.k1_backward_dst(graph, P, Q, None, None, T=1, F_in=F, akinds=akinds, skinds=(0,), tab=None, p_drop=0.5, seed=3,
+                       dY=dZ, arg_min=amin, arg_max=amax, mean=mean, var=var, gslot=graph.csr2csc, G=G, ldg=G.stride(0), dP=dP,
+                       lddp=dP.stride(0), local_args=True)
+    dQf, dQ, gq = guarded(n, F, torch.float32)
+    _lib.check(_lib.lib().mma_segment_sum_rows(_lib.ptr(graph.colptr), None, None, n, _lib.ptr(G), G.stride(0), F,
+                                               _lib.ptr(dQ), dQ.stride(0), _lib.stream_ptr(dev)), "segment_sum_rows")
+    torch.cuda.synchronize()
+    intact(Gf, gg, "K1 backward G"); intact(dPf, gp, "K1 backward dP"); intact(dQf, gq, "transpose pass dQ")
+    assert bool(torch.isfinite(G).all()) and bool(torch.isfinite(dQ).all())
+    # GEMMs: ragged last tile (M % 128 != 0), N not a multiple of 128, row scatter into a guarded output
+    for M, N, K in ((1237, 132, 100), (300, 384, 128), (77, 20, 36)):
+        Am = torch.randn(M, K, generator=g).to(dev)
+        W = torch.randn(N, K, generator=g).to(dev)
+        hi, lo = tg.split_weight(W)
+        Cf, C, gc = guarded(M, N, torch.float32)
+        perm = torch.randperm(M, generator=g).to(dev).int()
+        tg.linear(Am, hi, lo, N, out=C, out_map=perm)
+        torch.cuda.synchronize()
+        intact(Cf, gc, f"linear {M}x{N}x{K}")
+        ref = (Am.double() @ W.double().t())
+        got = torch.empty_like(ref); got[perm.long()] = ref
+        assert float((C.double() - got).abs().max() / got.abs().max()) < 1e-5
+        Cf2, C2, gc2 = guarded(M, N, torch.float32)
+        tg.linear(Am, hi, lo, N, out=C2)                              # plain output: the TMA tile-store path where it applies
+        torch.cuda.synchronize()
+        intact(Cf2, gc2, f"linear (plain) {M}x{N}x{K}")

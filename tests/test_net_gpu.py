@@ -80,3 +80,74 @@ def test_net_forward_backward_vs_oracle():
     want = torch.autograd.grad(ref_loss, [emb, eemb, ws[0].pre[0][0][0], ws[3].lin[0]])
     for a, b, what in zip(got, want, ("d node_emb", "d edge_emb", "d mask Linear (layer 1)", "d lin (layer 4)")):
         close(a, b, rel=2e-4, what=what)
+
+
+@pytest.mark.parametrize("n,Fd", [(2973, 75), (40, 128), (1, 8), (5000, 33)])
+def test_fused_batch_norm_relu_vs_torch(n, Fd):
+    """mma_bn_relu_fwd / _bwd (one kernel per direction) against F.relu(F.batch_norm(...)) in float64: training mode
+    (batch statistics, running statistics updated with the unbiased variance) and eval mode (given statistics).
+    reference: graph_regression/mma.py:120-121."""
+    from mma_b200.graph_regression.net import batch_norm_relu
+    g = torch.Generator().manual_seed(n + Fd)
+    x = torch.randn(n, Fd, generator=g) * 2 + 0.5
+    gy = torch.randn(n, Fd, generator=g)
+    for training in (True, False):
+        if training and n == 1:
+            continue                                                    # torch refuses batch statistics of one row
+        bn = torch.nn.BatchNorm1d(Fd).cuda()
+        ref = torch.nn.BatchNorm1d(Fd).double()
+        with torch.no_grad():
+            for m in (bn, ref):
+                m.weight.copy_(torch.linspace(0.5, 1.5, Fd)); m.bias.copy_(torch.linspace(-0.3, 0.3, Fd))
+                m.running_mean.copy_(torch.linspace(-1, 1, Fd)); m.running_var.copy_(torch.linspace(0.5, 2, Fd))
+        bn.train(training); ref.train(training)
+        xg = x.cuda().requires_grad_()
+        y = batch_norm_relu(xg, bn)
+        xr = x.double().requires_grad_()
+        yr = F.relu(ref(xr))
+        close(y, yr, what=f"bn+relu y (training={training})")
+        got = torch.autograd.grad(y, [xg, bn.weight, bn.bias], gy.cuda())
+        want = torch.autograd.grad(yr, [xr, ref.weight, ref.bias], gy.double())
+        for a, b, what in zip(got, want, ("dx", "dgamma", "dbeta")):
+            close(a, b, rel=2e-5, what=f"bn+relu {what} (training={training})")
+        close(bn.running_mean, ref.running_mean, what="running_mean")
+        close(bn.running_var, ref.running_var, what="running_var")
+        assert int(bn.num_batches_tracked) == int(ref.num_batches_tracked)
+        assert torch.equal(y, batch_norm_relu(xg, bn)) or training         # eval: deterministic, no state change
+
+
+def test_net_eval_folds_batch_norm_and_relu_into_lin():
+    """Net.eval(): BatchNorm is a per-channel affine map and is folded, with the ReLU, into the layer's `lin` GEMM
+    (MMA_GEMM_RELU epilogue) -- same result and same gradients as the unfused sequence conv -> bn -> relu."""
+    from mma_b200.graph_regression.net import Net
+    from mma_b200.synthetic import zinc_like_batch, degree_histogram
+    torch.manual_seed(1)
+    ei, batch = zinc_like_batch(8, seed=4)
+    n, E = batch.numel(), ei.shape[1]
+    net = Net(types.SimpleNamespace(mask=True), ["min", "max"], ["identity", "amplification", "linear"],
+              degree_histogram(ei, n)).cuda()
+    g = torch.Generator().manual_seed(2)
+    with torch.no_grad():
+        for bn in net.batch_norms:
+            bn.running_mean.copy_(torch.randn(75, generator=g) * 0.1); bn.running_var.copy_(torch.rand(75, generator=g) + 0.5)
+            bn.weight.copy_(torch.rand(75, generator=g) + 0.5); bn.bias.copy_(torch.randn(75, generator=g) * 0.1)
+    net.eval()
+    conv, bn = net.convs[0], net.batch_norms[0]
+    conv._inject_keep = ((torch.rand(E, 5, 75, generator=g) < 0.5).float() * 2).cuda()
+    x = torch.randn(n, 75, generator=g).cuda().requires_grad_()
+    ea = torch.randn(E, 50, generator=g).cuda()
+    scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+    shift = bn.bias - bn.running_mean * scale
+    y = conv.forward_affine_relu(x, ei.cuda(), ea, scale, shift)
+    yr = F.relu(bn(conv(x, ei.cuda(), ea)))
+    close(y, yr, what="folded eval BatchNorm + ReLU")
+    gy = torch.randn(n, 75, generator=g).cuda()
+    ga = torch.autograd.grad(y, [x, conv.lin.weight, bn.weight, bn.bias], gy)
+    gb = torch.autograd.grad(yr, [x, conv.lin.weight, bn.weight, bn.bias], gy)
+    for a, b, what in zip(ga, gb, ("dx", "d lin.weight", "d bn.weight", "d bn.bias")):
+        close(a, b, rel=2e-5, what=what)
+    # the whole net in eval mode runs (always-on dropout makes its output stochastic, Q3: shapes and finiteness only)
+    xi = torch.randint(0, 21, (n, 1), generator=g).cuda()
+    eai = torch.randint(0, 4, (E,), generator=g).cuda()
+    out = net(xi, ei.cuda(), eai, batch.cuda())
+    assert out.shape == (8, 1) and bool(torch.isfinite(out).all())
