@@ -1007,7 +1007,7 @@ extern "C" int mmconv_aggregate_fwd(const int32_t *rowptr, const int32_t *col, c
         const int vw = stream_vec(p, fd);
         if (vw == 4) {
             if (fd == FD_BIT && minmax && sq && sc.nst == 8) e = launch_fwd_stream<8, 12, 4, FD_BIT>(p, minmax, sq, st);
-            else if (fd == FD_BIT && minmax && sq && sc.nst == 4) e = launch_fwd_stream<4, 16, 4, FD_BIT>(p, minmax, sq, st);
+            else if (fd == FD_BIT && minmax && sq && sc.nst == 4 && sc.warps == 16) e = launch_fwd_stream<4, 16, 4, FD_BIT>(p, minmax, sq, st);
             else if (fd == FD_NONE) e = launch_fwd_stream<6, 16, 4, FD_NONE>(p, minmax, sq, st);
             else if (fd == FD_BIT) e = launch_fwd_stream<6, 16, 4, FD_BIT>(p, minmax, sq, st);
             else e = launch_fwd_stream<6, 16, 4, FD_BYTE>(p, minmax, sq, st);
@@ -1106,7 +1106,7 @@ extern "C" int mmconv_aggregate_bwd_dst(const int32_t *rowptr, const int32_t *co
         const int vw = stream_vec(p, fd);
         if (vw == 4) {
             if (fd == FD_BIT && needm && sc.nst == 8) e = launch_bwd_stream<8, 12, 4, FD_BIT>(p, needm, st);
-            else if (fd == FD_BIT && needm && sc.nst == 4) e = launch_bwd_stream<4, 16, 4, FD_BIT>(p, needm, st);
+            else if (fd == FD_BIT && needm && sc.nst == 4 && sc.warps == 16) e = launch_bwd_stream<4, 16, 4, FD_BIT>(p, needm, st);
             else if (fd == FD_NONE) e = launch_bwd_stream<6, 16, 4, FD_NONE>(p, needm, st);
             else if (fd == FD_BIT) e = launch_bwd_stream<6, 16, 4, FD_BIT>(p, needm, st);
             else e = launch_bwd_stream<6, 16, 4, FD_BYTE>(p, needm, st);

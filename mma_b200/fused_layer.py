@@ -170,8 +170,9 @@ def _k1_bwd(graph: Graph, P, Q, R, keep, F, akinds, p_drop, seed, dZ, arg_min, a
     idx = graph.perm_t if need_R else None
     if G_ORDER == "csr" and not need_R:
         # A/B variant (MMA_G_ORDER=csr): G in CSR order -- sequential row stores in the destination pass, random row
-        # gathers in the transpose pass; same bytes as the default (scattered stores, sequential reads).  Measured
-        # slower on config 4 (profiles/README.md, round 2), kept for re-measurement only.
+        # gathers in the transpose pass; same bytes as the default (scattered stores, sequential reads).  Measured on
+        # config 4: destination pass 7.10 vs 7.14 ms, transpose pass 2.57 vs 2.47 ms -- no gain (profiles/README.md,
+        # round 2); kept for re-measurement only.
         if "_csc2csr" not in graph.__dict__:
             from .graph import invert_perm
             graph.__dict__["_csc2csr"] = invert_perm(graph.csr2csc)
