@@ -158,12 +158,20 @@ class PeerExchange:
                 self._copy(dst, src, 8, self._stream_for(o))
 
     def wait(self, phase: int, stream: Optional[torch.cuda.Stream] = None) -> None:
-        """`stream` (default: current) continues once every rank's announcement of `phase` for this epoch is here."""
-        st = stream or torch.cuda.current_stream(self.dev)
-        with torch.cuda.device(self.dev):
+        """`stream` (default: current) continues once every rank's announcement of `phase` for this epoch is here.
+        On the compute stream the wait kernel's duration IS the exposed (un-hidden) part of that exchange: it is
+        counted and timed like every other launch (bench.py lists it as peer_wait_q / peer_wait_dq)."""
+        def launch(st):
             _lib.check(_lib.lib().mma_peer_wait(self.epoch.data_ptr(), self._flags.data_ptr() + 8 * phase * self.world,
                                                 self.world, phase, WAIT_TIMEOUT_NS, self.err.data_ptr(), st.cuda_stream),
                        "mma_peer_wait")
+        if stream is not None:
+            with torch.cuda.device(self.dev):
+                launch(stream)
+            return
+        name = "peer_wait_dq" if phase == self.PHASE_BWD else ("peer_wait_enter" if phase == PHASE_ENTER else "peer_wait_q")
+        with _lib.kernel_scope(name, self.dev):
+            launch(torch.cuda.current_stream(self.dev))
 
     def _peer_order(self):
         """Peers in sending order: rank+1, rank+2, ... (at any moment the ranks address distinct destinations), this
@@ -233,7 +241,7 @@ class PeerExchange:
         waiting for PHASE_BWD on the current stream."""
         self.wait(self.PHASE_BWD)
         ptrs = (C.c_void_p * self.world)(*[self.slices[r].data_ptr() for r in range(self.world)])
-        with torch.cuda.device(self.dev):
+        with _lib.kernel_scope("mma_sum_slices", self.dev):
             _lib.check(_lib.lib().mma_sum_slices(ptrs, self.world, rows, self.F, out.data_ptr(), out.stride(0),
                                                  _lib.stream_ptr(self.dev)), "mma_sum_slices")
 
