@@ -311,6 +311,31 @@ int mma_reduce_slabs_segmented(const float *part, const int32_t *seg_ptr, int64_
                                float *out, mma_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * Weight-space algebra of the fused layer (mma_b200/fused_layer.py): the post Linear (reference
+ * graph_regression/mma_conv.py:132-133), `lin` (:136) and the cumulative scalers (:181-196) are composed into one
+ * effective weight per in-degree range; these three calls replace ~60 small torch launches per step.
+ *
+ * mma_small_gemm: C[z] [M, N] (ldc; slab z at C + z * M * ldc) = op(A) * op(B) over the K-range of split z, plain fp32
+ *   FFMA in ascending k.  A is [M, K] (lda), or [K, M] with trans_a; B is [K, N] (ldb), or [N, K] with trans_b.
+ *   k_splits must equal mma_small_gemm_splits(K, wanted) (K-ranges are multiples of 16); add the slabs in order with
+ *   mma_reduce_slabs.
+ * mma_compose_post_weight: W_c[b][c][m*F+f] = sum_{s,a} coef[b][s][a][m] * WlW[c][col0 + (s*A+a)*F + f], written split
+ *   for the 3xTF32 GEMMs (hi = tf32(x), lo = tf32(x - hi)): hi / lo [n_ranges][Co][Am*F] and, optionally, the
+ *   transposes hiT / loT [n_ranges][Am*F][Co].  coef [n_ranges][S][A][Am], WlW [Co][>= col0 + S*A*F] (ldw).
+ * mma_compose_post_wgrad: D[c][col0 + (s*A+a)*F + f] = sum_b coef[b][s][a][block_of[a]] * dWc[b][c][block_of[a]*F + f]
+ *   (b ascending); D[c][0 .. col0) = dX[c][.] (dX may be NULL: zeros).  dWc [n_ranges][Co][Am*F], D [Co][ldd].
+ * ---------------------------------------------------------------------- */
+int mma_small_gemm(const float *A, int64_t lda, int trans_a, const float *B, int64_t ldb, int trans_b, float *C,
+                   int64_t ldc, int M, int N, int K, int k_splits, mma_stream_t stream);
+int mma_small_gemm_splits(int K, int wanted);
+int mma_compose_post_weight(const float *coef, int n_ranges, int S, int A, int Am, const float *WlW, int64_t ldw,
+                            int col0, int Co, int F, float *hi, float *lo, float *hiT, float *loT,
+                            mma_stream_t stream);
+int mma_compose_post_wgrad(const float *coef, int n_ranges, int S, int A, int Am, const int32_t *block_of,
+                           const float *dWc, int Co, int F, const float *dX, int64_t lddx, int col0, float *D,
+                           int64_t ldd, mma_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * BatchNorm + ReLU over the rows of x [n, F] in ONE kernel per direction: the step that follows the layer in
  * the reference's Net (graph_regression/mma.py:120-121, `F.relu(batch_norm(conv(...)))`).
  *   mean_in / var_in NULL : batch statistics (training) -- two-pass mean / centred second moment, biased variance

@@ -56,6 +56,10 @@ _SIGS = {
                          C.c_int),
     "mma_reduce_slabs": ([_vp, _vp, _i64, _i64, _vp, _vp], C.c_int),
     "mma_reduce_slabs_segmented": ([_vp, _vp, _i64, _i64, _vp, _vp], C.c_int),
+    "mma_small_gemm": ([_vp, _i64, _i32, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _i32, _i32, _vp], C.c_int),
+    "mma_small_gemm_splits": ([_i32, _i32], C.c_int),
+    "mma_compose_post_weight": ([_vp, _i32, _i32, _i32, _i32, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp], C.c_int),
+    "mma_compose_post_wgrad": ([_vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _i64, _i32, _vp, _i64, _vp], C.c_int),
     "mma_peer_epoch_advance": ([_vp, _vp, _vp], C.c_int),
     "mma_bn_relu_fwd": ([_vp, _i64, _i64, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _f32, _vp], C.c_int),
     "mma_bn_relu_bwd": ([_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _vp], C.c_int),

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmma_b200.so")
 SOURCES = ["lib.cu", "mmconv_aggregate.cu", "segment_rows.cu", "nc_aggregate.cu", "dropout.cu",
-           "graph_build.cu", "gemm_tf32x3.cu", "peer_exchange.cu", "bn_relu.cu"]
+           "graph_build.cu", "gemm_tf32x3.cu", "peer_exchange.cu", "bn_relu.cu", "weight_prep.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

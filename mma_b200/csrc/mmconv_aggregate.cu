@@ -907,7 +907,7 @@ static int sm_count() {
 }
 template <typename K>
 static cudaError_t launch_stream(K kernel, const MMConvParams &p, int nst, int warps, cudaStream_t st) {
-    const int smem = warps * nst * 4 * p.ncols * 4;
+    const int smem = warps * nst * 4 * p.ncols * 4 + warps * 512;     // rings + the forward kernel's index windows (128 ints per warp)
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     kernel<<<sm_count(), warps * 32, smem, st>>>(p);

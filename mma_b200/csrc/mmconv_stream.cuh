@@ -44,6 +44,14 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
+// dst = *ptr if pred, else unchanged -- a predicated load IN PLACE.  The merge with the old value pins the destination
+// to the register that holds it, so ptxas can neither turn `if (c) x = load` into a load into a temporary + select
+// (which consumes the loaded value on the spot) nor hoist the load above the last read of the old value.
+__device__ __forceinline__ void ldg_i32_if(int &dst, const int32_t *ptr, bool pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p ld.global.nc.b32 %0, [%1];\n\t}"
+                 : "+r"(dst) : "l"(ptr), "r"((int)pred) : "memory");
+}
+
 template <int VEC>
 __device__ __forceinline__ Vec<VEC> lds_vec(uint32_t addr) {
     Vec<VEC> r;
@@ -253,48 +261,65 @@ struct RowRing {
     const int32_t *colp;       // col + first CSR slot of the stream
     const int32_t *rp;         // (virtual) row pointer
     int s0, len;
+    int64_t n_rp;              // rows of the (virtual) row pointer: rp[0 .. n_rp] are readable
     int i_row, i_pos, i_end;   // issue side: row being issued, stream position of its next edge, end of that row
-    int idx_base, idx_cur, idx_nxt;   // col[] of stream positions [idx_base, +32) / [idx_base + 32, +64)
+    int i_end_nxt;             // rp[i_row + 2], fetched one row ahead and left RAW until it is consumed (an add on a
+                               // freshly loaded value would stall the issue side for a full memory round trip per row)
+    // col[] of the stream travels through a 128-entry shared-memory window of this warp (slot = position & 127), filled
+    // 32 positions at a time with 4-byte cp.async copies that ride in the ring's own commit groups: the chunk
+    // [idx_base + 64, +32) is requested when the issue position enters [idx_base, +32), i.e. >= 15 stages before its first
+    // entry is read, and wait_group<NST - 1> after every stage has retired it long before (NST <= 8).  Registers would
+    // not do: `cur = nxt; nxt = load` makes ptxas load into a temporary and copy (or select) it into the loop-carried
+    // register in the same basic block -- a full memory round trip per chunk spent waiting (ncu: 6-7 % of all stall
+    // samples, whichever way the source was arranged).
+    uint32_t idx_smem;         // shared-memory address of the window
+    int idx_base;
     int ring_i;
 
-    __device__ __forceinline__ int load_chunk(int pbase) const {
+    __device__ __forceinline__ void request_chunk(int pbase) {          // positions [pbase, pbase + 32) -> their slots
         const int i = pbase + lane;
-        return i < len ? __ldg(colp + i) : 0;
+        cp_async_pred<4>(idx_smem + (uint32_t)((i & 127) * 4), colp + i, i < len);
+    }
+    __device__ __forceinline__ int col_at(int pos) const {             // broadcast read
+        int j;
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(j) : "r"(idx_smem + (uint32_t)((pos & 127) * 4)));
+        return j;
     }
     __device__ __forceinline__ void issue() {
-        while (i_pos == i_end && i_pos < len) { ++i_row; i_end = __ldg(rp + i_row + 1) - s0; }     // skip finished / empty rows
+        __syncwarp();                                       // the other lanes' retired index copies become visible
+        while (i_pos == i_end && i_pos < len) {                                                    // skip finished / empty rows
+            ++i_row;
+            i_end = i_end_nxt - s0;
+            const bool in_range = (int64_t)i_row + 2 <= n_rp;
+            if (!in_range) i_end_nxt = 0x7fffffff;
+            ldg_i32_if(i_end_nxt, rp + i_row + 2, in_range);
+        }
         int n = i_end - i_pos;
         n = n < 4 ? n : 4;
         if (i_pos >= len) n = 0;
         if (n > 0) {
-            if (i_pos >= idx_base + 32) { idx_cur = idx_nxt; idx_base += 32; idx_nxt = load_chunk(idx_base + 32); }
+            if (i_pos >= idx_base + 32) { idx_base += 32; request_chunk(idx_base + 64); }
             const uint32_t dst = base + (uint32_t)(ring_i * 4 * rowb);
-            const int o = i_pos - idx_base;
-            if (o + n <= 32) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int j = __shfl_sync(0xffffffffu, idx_cur, (o + u) & 31);
-                    cp_async_pred<VEC * 4>(dst + (uint32_t)(u * rowb), Qc + (uint64_t)(uint32_t)j * ldq_b, live && u < n);
-                }
-            } else {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int a = __shfl_sync(0xffffffffu, idx_cur, (o + u) & 31);
-                    const int b = __shfl_sync(0xffffffffu, idx_nxt, (o + u) & 31);
-                    const int j = o + u < 32 ? a : b;
-                    cp_async_pred<VEC * 4>(dst + (uint32_t)(u * rowb), Qc + (uint64_t)(uint32_t)j * ldq_b, live && u < n);
-                }
+            for (int u = 0; u < 4; ++u) {
+                const int j = col_at(i_pos + u);            // u >= n: a stale slot, the copy is predicated off
+                cp_async_pred<VEC * 4>(dst + (uint32_t)(u * rowb), Qc + (uint64_t)(uint32_t)j * ldq_b, live && u < n);
             }
         }
         cp_async_commit();
         i_pos += n;
         ring_i = ring_i + 1 == NST ? 0 : ring_i + 1;
     }
-    __device__ __forceinline__ void begin(const int32_t *col_at_s0, const int32_t *rp_, int r0, int s0_, int len_) {
-        colp = col_at_s0; rp = rp_; s0 = s0_; len = len_;
+    __device__ __forceinline__ void begin(const int32_t *col_at_s0, const int32_t *rp_, int64_t n_rp_, int r0, int s0_, int len_) {
+        colp = col_at_s0; rp = rp_; n_rp = n_rp_; s0 = s0_; len = len_;
         i_row = r0; i_pos = 0; i_end = __ldg(rp + r0 + 1) - s0;
+        i_end_nxt = (int64_t)r0 + 2 <= n_rp ? __ldg(rp + r0 + 2) : 0x7fffffff;
         ring_i = 0;
-        idx_base = 0; idx_cur = load_chunk(0); idx_nxt = load_chunk(32);
+        idx_base = 0;
+        __syncwarp();                                       // every lane is done reading the previous stream's window
+        request_chunk(0); request_chunk(32); request_chunk(64);
+        cp_async_commit();
+        cp_async_wait<0>();
 #pragma unroll 1
         for (int k = 0; k < NST; ++k) issue();
         cp_async_wait<NST - 1>();                   // stage 0 has landed
@@ -373,13 +398,23 @@ __device__ __forceinline__ void pick_words(const uint4 &t, int c, uint32_t (&bit
         bits[0] = k == 0 ? t.x : (k == 1 ? t.y : (k == 2 ? t.z : t.w));
     }
 }
+// The dropout key of this launch, resolved ONCE: with a device-resident seed (CUDA-graph replays) dropout_key() is a
+// global load, and repeated inside every Philox call it shared a scoreboard with the row prefetches issued just before
+// it -- the first Philox of every row then waited for THEIR memory round trip (ncu: 9 % of all stall samples).
+__device__ __forceinline__ Dropout resolve_key(const Dropout &d) {
+    Dropout r = d;
+    const uint2 k = dropout_key(d);
+    r.k0 = k.x; r.k1 = k.y; r.seed_dev = nullptr;
+    return r;
+}
+
 // dropout words for in-row position pos: refreshes `bits` at the word boundaries of the row's stream
 template <int DROP, int VEC>
-__device__ __forceinline__ void rng_refresh(const MMConvParams &p, uint32_t rid, int pos, int c, uint32_t (&bits)[VEC]) {
+__device__ __forceinline__ void rng_refresh(const Dropout &drop, uint32_t rid, int pos, int c, uint32_t (&bits)[VEC]) {
     if constexpr (DROP == FD_BIT) {
-        if ((pos & 31) == 0) pick_words<VEC>(row_rng_bits1(p.drop, rid, (uint32_t)pos, (uint32_t)c), c, bits);
+        if ((pos & 31) == 0) pick_words<VEC>(row_rng_bits1(drop, rid, (uint32_t)pos, (uint32_t)c), c, bits);
     } else if constexpr (DROP == FD_BYTE) {
-        if ((pos & 3) == 0) pick_words<VEC>(row_rng_bits8(p.drop, rid, (uint32_t)pos, (uint32_t)c), c, bits);
+        if ((pos & 3) == 0) pick_words<VEC>(row_rng_bits8(drop, rid, (uint32_t)pos, (uint32_t)c), c, bits);
     }
 }
 // non-zero iff column v of the edge at in-row position pos is kept
@@ -401,6 +436,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_fwd_stream(const __grid_
     const int64_t n_chunks = p.row_chunks ? p.n_chunks : tw;
     const bool live = lane * VEC < p.ncols;
     const int c = p.col0 + lane * VEC;
+    const Dropout drop = resolve_key(p.drop);
     const float scale = p.drop.scale;
     const uint32_t thr = p.drop.thr;
     // outputs of the common case (S == 1, every aggregator kind at most once): column offset of each kind in a
@@ -413,6 +449,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_fwd_stream(const __grid_
     ring.Qc = reinterpret_cast<const char *>(p.Q + c);
     ring.ldq_b = (uint32_t)p.ldq * 4u;
     ring.lane = lane; ring.live = live;
+    ring.idx_smem = smem_addr(smem_ring) + (uint32_t)WARPS * (uint32_t)(NST * 4 * ring.rowb) + (uint32_t)warp * 512u;   // after the rings
     const int32_t *rp = p.vrowptr ? p.vrowptr : p.rowptr;      // the (virtual) row boundaries walked by the stream
     const int64_t n_rows = p.vrowptr ? p.n_vrows : p.n_rows;
     const int ycol = p.T == 1 ? c : (c / p.F_in) * (p.S * p.A * p.F_in) + c % p.F_in;
@@ -429,9 +466,21 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_fwd_stream(const __grid_
         int row = r0;
         int row_beg = s0, row_end = __ldg(rp + r0 + 1);
         int next_end = r0 + 2 <= n_rows ? __ldg(rp + r0 + 2) : 0x7fffffff;
+        // Per-row inputs arrive through a two-level software pipeline so that no load address and no arithmetic ever
+        // waits on a load issued in the same step: the INDICES of row r + 2 (segment descriptor, P row = row_map[.],
+        // dropout row id = rng_row[.]) are fetched while row r is walked and kept raw; the P row of r + 1 is fetched
+        // with the index that arrived one row earlier; the doubling of P (1-bit dropout mode) and the rng id's offset
+        // are applied when the row becomes current.  (ncu, round 2: with a single level the row_map -> P and
+        // rng_row -> id chains stalled every warp for a memory round trip per row -- 13 % of all stall samples.)
+        // The loads are issued from the FIRST STAGE of a row (`pending`), not from row_next(): in one basic block with
+        // the moves that consume the previous values ptxas hoists the loads to the top, lands them in temporaries and
+        // copies the temporaries into the loop-carried registers at the end of the block -- the stall all over again.
+        struct RowIn { RowDesc d; int map_raw, rng_raw; };
         Vec<VEC> pv{}, pv_next{};
-        uint32_t rid = 0, rid_next = 0;
-        RowDesc rd{}, rd_next{};
+        uint32_t rid = 0;
+        RowDesc rd{};
+        RowIn in1{}, in2{};                                 // indices of row + 1 / row + 2
+        bool pending = false;                               // the loads for the rows after `row` are still to be issued
         float sum[VEC], sq[VEC], mn[VEC], mx[VEC];
         int amn[VEC], amx[VEC];
         uint32_t bits[VEC] = {};
@@ -440,18 +489,23 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_fwd_stream(const __grid_
         int32_t *amn_p = nullptr, *amx_p = nullptr;
         float *mean_p = nullptr, *var_p = nullptr;
 
-        auto fetch_row_inputs = [&](int r, Vec<VEC> &pvv, uint32_t &rdid, RowDesc &d) {   // P row (pre-scaled), rng id
-            pvv = Vec<VEC>{}; rdid = 0; d = RowDesc{r, 0, -1};
+        auto fetch_idx = [&](int r, RowIn &x) {
+            x.d = RowDesc{r, 0, -1}; x.map_raw = 0; x.rng_raw = 0;
             if (r < r1) {
-                d = row_desc(p, r);
-                const int64_t prow = p.row_map ? (int64_t)__ldg(p.row_map + d.real) : (int64_t)d.real;
-                if (live) pvv = ld_vec_stream<VEC>(p.P + prow * p.ldp + c);
-                if (p.use_rng) rdid = (uint32_t)(p.rng_row0 + (p.rng_row ? (int64_t)__ldg(p.rng_row + d.real) : (int64_t)d.real));
+                x.d = row_desc(p, r);
+                x.map_raw = p.row_map ? __ldg(p.row_map + x.d.real) : x.d.real;
+                x.rng_raw = (p.use_rng && p.rng_row) ? __ldg(p.rng_row + x.d.real) : x.d.real;
             }
-            if constexpr (DROP == FD_BIT) {
+        };
+        auto fetch_P = [&](int r, const RowIn &x, Vec<VEC> &pvv) {             // raw P row (this lane's columns)
+            pvv = Vec<VEC>{};
+            if (r < r1 && live) pvv = ld_vec_stream<VEC>(p.P + (int64_t)x.map_raw * p.ldp + c);
+        };
+        auto make_current = [&](const RowIn &x, const Vec<VEC> &raw) {        // the fetched inputs become the current row's
+            rd = x.d;
+            rid = p.use_rng ? (uint32_t)(p.rng_row0 + (int64_t)x.rng_raw) : 0u;
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) pvv.v[v] *= 2.0f;
-            }
+            for (int v = 0; v < VEC; ++v) pv.v[v] = DROP == FD_BIT ? raw.v[v] * 2.0f : raw.v[v];
         };
         auto reset_acc = [&]() {
 #pragma unroll
@@ -496,10 +550,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_fwd_stream(const __grid_
             emit_row<VEC, MINMAX, SQ>(p, simple_out, row_end - row_beg, sum, sq, mn, mx, amn, amx, yp, amn_p, amx_p,
                                       mean_p, var_p);
         };
+        auto issue_row_loads = [&]() {                      // next_end = rp[row + 2], P of row + 1, indices of row + 2
+            next_end = row + 2 <= n_rows ? __ldg(rp + row + 2) : 0x7fffffff;
+            fetch_P(row + 1, in1, pv_next);
+            fetch_idx(row + 2, in2);
+            pending = false;
+        };
         auto row_next = [&]() {
             finish_row();
+            if (pending) issue_row_loads();                 // the row had no stage (an empty row): fetch now, and wait
             ++row;
-            if (rd_next.real != rd.real) {                  // segments of one row share the output row
+            if (in1.d.real != rd.real) {                    // segments of one row share the output row
                 yp += p.ldy;
                 if (amn_p) amn_p += p.F;
                 if (amx_p) amx_p += p.F;
@@ -508,31 +569,40 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_fwd_stream(const __grid_
             }
             row_beg = row_end;
             row_end = next_end;
-            next_end = row + 2 <= n_rows ? __ldg(rp + row + 2) : 0x7fffffff;
-            pv = pv_next; rid = rid_next; rd = rd_next;
-            fetch_row_inputs(row + 1, pv_next, rid_next, rd_next);
+            make_current(in1, pv_next);
+            in1 = in2;
+            pending = true;
             reset_acc();
         };
 
-        fetch_row_inputs(row, pv, rid, rd);
-        fetch_row_inputs(row + 1, pv_next, rid_next, rd_next);
+        {
+            RowIn in0;
+            fetch_idx(row, in0);
+            fetch_idx(row + 1, in1);
+            fetch_idx(row + 2, in2);
+            Vec<VEC> raw;
+            fetch_P(row, in0, raw);
+            fetch_P(row + 1, in1, pv_next);
+            make_current(in0, raw);
+        }
         point_at(rd.real);
         reset_acc();
 
         if (len > 0) {
-            ring.begin(p.col + s0, rp, r0, s0, len);
+            ring.begin(p.col + s0, rp, n_rows, r0, s0, len);
             int c_pos = 0, cons_i = 0;
 #pragma unroll 1
             while (c_pos < len) {
                 const int at = s0 + c_pos;
                 if (at == row_end) { row_next(); continue; }
+                if (pending) issue_row_loads();
                 const int n = row_end - at < 4 ? row_end - at : 4;
                 const uint32_t sb = ring.base + (uint32_t)(cons_i * 4 * ring.rowb);
                 if (n == 4) {                                                 // a full stage: 4 edges of this row
                     Vec<VEC> q[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) q[i] = lds_vec<VEC>(sb + (uint32_t)(i * ring.rowb));
-                    rng_refresh<DROP, VEC>(p, rid, pos, c, bits);
+                    rng_refresh<DROP, VEC>(drop, rid, pos, c, bits);
                     uint32_t w[VEC];
                     const int sh = DROP == FD_BIT ? (pos & 31) : 0;
 #pragma unroll
@@ -551,7 +621,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_fwd_stream(const __grid_
 #pragma unroll 1
                     for (int u = 0; u < n; ++u) {
                         const Vec<VEC> q = lds_vec<VEC>(sb + (uint32_t)(u * ring.rowb));
-                        rng_refresh<DROP, VEC>(p, rid, pos, c, bits);
+                        rng_refresh<DROP, VEC>(drop, rid, pos, c, bits);
 #pragma unroll
                         for (int v = 0; v < VEC; ++v) {
                             const float x = fast_message<MSG_PQ, DROP>(pv.v[v], q.v[v], 0.0f, scale);
@@ -586,6 +656,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_bwd_stream(const __grid_
     const int64_t n_chunks = p.row_chunks ? p.n_chunks : tw;
     const bool live = lane * VEC < p.ncols;
     const int c = p.col0 + lane * VEC;
+    const Dropout drop = resolve_key(p.drop);
     const float scale = DROP == FD_BIT ? 2.0f : (DROP == FD_BYTE ? p.drop.scale : 1.0f);
     const uint32_t thr = p.drop.thr;
     const bool simple_out = p.simple_out != 0;
@@ -774,7 +845,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_bwd_stream(const __grid_
             ring.begin(p.col + s0, len);
             run_stream<NST, NEEDM, VEC>(ring, s0, len, row_end, row_next,
                 [&](int at, const Vec<VEC> (&q)[4], int s) {
-                    rng_refresh<DROP, VEC>(p, rid, pos, c, bits);
+                    rng_refresh<DROP, VEC>(drop, rid, pos, c, bits);
                     uint32_t w[VEC];
                     const int sh = DROP == FD_BIT ? (pos & 31) : 0;
 #pragma unroll
@@ -789,7 +860,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mmconv_bwd_stream(const __grid_
                     pos += 4;
                 },
                 [&](int at, const Vec<VEC> &q, int s) {
-                    rng_refresh<DROP, VEC>(p, rid, pos, c, bits);
+                    rng_refresh<DROP, VEC>(drop, rid, pos, c, bits);
                     uint32_t kw[VEC];
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) kw[v] = keep_at<DROP>(bits[v], pos, thr);

@@ -38,6 +38,10 @@ OVERLAP_EXCHANGE = os.environ.get("MMA_OVERLAP_EXCHANGE", "0") == "1"
 # window (mma_b200/peer.py, the default); "nccl" = one all-gather / reduce-scatter (the round-1 path, kept for A/B runs).
 EXCHANGE = os.environ.get("MMA_EXCHANGE", "peer")
 G_ORDER = os.environ.get("MMA_G_ORDER", "csc")       # order of the per-edge gradient rows G (see _k1_bwd)
+# Weight-space algebra (composition of W_lin, W_post and the scaler coefficients, and its gradient): "1" = the library's
+# small GEMM + composition kernels (csrc/weight_prep.cu, ~15 launches per step); "0" = the torch formulation (~60 launches,
+# kept as the readable statement of the algebra and for A/B runs).
+WPREP = os.environ.get("MMA_WPREP", "1") == "1"
 
 # Parity hook (bench.py --verify, tests): when set to a dict, every forward leaves references to its raw aggregates
 # and arg indices there (Z in CSR-row order, arg_min / arg_max as CSR slots), so a sharded run can be compared bit for
@@ -88,6 +92,7 @@ class PostPlan:
         for a in range(A):
             fold[:, a, self.block_of[a]] = (1.0 / degf) if self.inv[a] else 1.0
         self.fold = fold.to(dev)
+        self.block_of_t = torch.tensor(self.block_of, dtype=torch.int32, device=dev)
         big, tiles, tiles_t, slabs, seg_ptr, tail_rows, tail_b = [], [], [], [], [0], [], []
         if min_rows is None or min_rows <= 0:
             # auto: every degree range gets its own effective weight (no tail path at all) as long as there are at most
@@ -258,8 +263,14 @@ class _FusedMMAConv(torch.autograd.Function):
         Am, K = len(plan.mat), plan.K                # materialised aggregate blocks (a mean rides on the sum block)
         Fo, Co = Wp.shape[0], Wl.shape[0]
         zeros = lambda k: torch.zeros(k, dtype=torch.float32, device=dev)
-        Wx, Wy = Wp[:, :F], Wp[:, F:].contiguous()
-        Wcx = Wl @ Wx                                                                               # [Co, F]
+        Wx, Wy = Wp[:, :F], Wp[:, F:]
+        wprep = WPREP and Wp.stride(1) == 1 and Wl.stride(1) == 1
+        if wprep:
+            WlW = tg.small_gemm(Wl, Wp)                              # [Co, (S*A+1)*F] = W_lin [W_x | W_{s,a} ...]: one launch
+            Wcx = WlW[:, :F]
+        else:
+            Wy = Wy.contiguous()
+            Wcx = Wl @ Wx                                                                           # [Co, F]
         bc = (Wl @ bp if bp is not None else zeros(Co)) + (bl if bl is not None else zeros(Co))
         W1 = torch.cat([Wm[:, :F], Wm[:, F:2 * F], Wcx], dim=0)                                     # [2F+Co, F]
         b1 = torch.cat([bm if bm is not None else zeros(F), zeros(F), bc])
@@ -292,11 +303,25 @@ class _FusedMMAConv(torch.autograd.Function):
         # composed weight of every degree range over the materialised blocks:
         #   W_c(d)[:, m] = sum_s sum_{a -> m} c_s(d) coef_a(d) (W_lin W_{s,a})      (coef = 1 / d for a mean, else 1)
         # S small products, then one contraction with the per-range coefficients (no [B, F_out, K] batched product)
-        WlWy = torch.matmul(Wl, Wy.view(Fo, S, A * F).permute(1, 0, 2))                             # [S, Co, A*F]
         Wc = hi = lo = None
-        if plan.big:
-            Wc = torch.einsum("bsam,scaf->bcmf", plan.coef_big, WlWy.view(S, Co, A, F)).reshape(-1, Co, K).contiguous()   # [B, Co, K]
-            hi, lo = tg.split_weight(Wc.view(-1, K))
+        bw = None
+        if wprep:
+            # one composition kernel writes W_c already split for the 3xTF32 GEMMs, and its transpose (the dgrad GEMM's
+            # weight) with it; the backward's split W1^T is made here too -- a sharded rank is waiting for the exchange at
+            # this point, and the backward's critical path (dgrad -> K1 -> push; slices -> dgrad / wgrad) gets shorter
+            wct = None
+            if plan.big:
+                hi3, lo3, hiT, loT = tg.compose_post_weight(plan.coef_big, WlW, F, F, True)
+                hi, lo, wct = hi3.view(-1, K), lo3.view(-1, K), (hiT.view(-1, Co), loT.view(-1, Co))
+            bw = (wct, tg.split_weight(W1.t()))
+        else:
+            WlWy = torch.matmul(Wl, Wy.view(Fo, S, A * F).permute(1, 0, 2))                         # [S, Co, A*F]
+            if plan.big:
+                Wc = torch.einsum("bsam,scaf->bcmf", plan.coef_big, WlWy.view(S, Co, A, F)).reshape(-1, Co, K).contiguous()   # [B, Co, K]
+                hi, lo = tg.split_weight(Wc.view(-1, K))
+            if sg is not None:
+                wct = tg.split_weight(Wc.transpose(1, 2).contiguous().view(-1, Co)) if plan.big else None
+                bw = (wct, tg.split_weight(W1.t()))
         if gathered is not None:
             Q, done = gathered
             torch.cuda.current_stream(dev).wait_event(done)
@@ -315,7 +340,7 @@ class _FusedMMAConv(torch.autograd.Function):
             nodes = plan.tail_nodes
             Zt = Z.index_select(0, ti)
             Yt = torch.einsum("nsam,nmf->nsaf", plan.tail_coef, Zt.view(-1, Am, F)).reshape(Zt.shape[0], S * A * F)
-            out.index_copy_(0, nodes, (Yt @ Wy.t()) @ Wl.t() + XW.index_select(0, nodes))
+            out.index_copy_(0, nodes, (Yt @ Wp[:, F:].t()) @ Wl.t() + XW.index_select(0, nodes))
         if KEEP_LAST is not None:
             KEEP_LAST.update(Z=Z, arg_min=arg_min, arg_max=arg_max, graph=graph)
         ctx.graph, ctx.sg, ctx.plan, ctx.cfg = graph, sg, plan, cfg
@@ -323,6 +348,7 @@ class _FusedMMAConv(torch.autograd.Function):
         need_sq = 4 in akinds or 5 in akinds
         Qsave = Q if (sg is not None and need_sq and ex is None) else None   # NCCL variant: gathered Q kept for the backward
         ctx.ex, ctx.ex_call = ex, (ex.fwd_calls if ex is not None else 0)
+        ctx.bw, ctx.wprep = bw, wprep
         ctx.save_for_backward(x, PQX, Z, Wm, Wp, bp, Wl, Wc, R, keep, arg_min, arg_max, mean, var, Qsave,
                               seed_dev)
         return out
@@ -342,15 +368,18 @@ class _FusedMMAConv(torch.autograd.Function):
         P, Q = PQX[:, :F], PQX[:, F:2 * F]
         if Qsave is not None:
             Q = Qsave
-        Wx, Wy = Wp[:, :F], Wp[:, F:].contiguous()
+        wprep = ctx.wprep
+        Wx, Wy = Wp[:, :F], (Wp[:, F:] if wprep else Wp[:, F:].contiguous())
         d_out = d_out.contiguous()
         dO, dbc = tg.gather_rows_colsum(d_out, graph.row_map)                                       # sorted rows; [Co]
         # ---- dgrad of the grouped post transform (composed with lin), then K1's backward
         dZ = torch.empty((n, K), dtype=torch.float32, device=dev)
-        WcT = None
+        bw = ctx.bw
         if plan.big:
-            WcT = Wc.transpose(1, 2).contiguous()                                                   # [B, K, Co]
-            hi, lo = tg.split_weight(WcT.view(-1, Co))
+            if bw is not None:
+                hi, lo = bw[0]
+            else:
+                hi, lo = tg.split_weight(Wc.transpose(1, 2).contiguous().view(-1, Co))              # [B * K, Co]
             tg.linear(dO, hi, lo, K, tile_tab=plan.tile_tab_t, out=dZ, name="gemm_post_dgrad")
         if plan.tail_idx is not None:
             ti = plan.tail_idx
@@ -395,8 +424,16 @@ class _FusedMMAConv(torch.autograd.Function):
         del dZ
         # ---- wgrad of the grouped post transform
         dWl = torch.outer(dbc, bp) if bp is not None else torch.zeros_like(Wl)
-        dWy = None
-        if plan.big:
+        dWy = dWp = None
+        if plan.big and wprep:
+            part = tg.wgrad_partials(dO, Z, plan.slabs, plan.slabs.shape[0], name="gemm_post_wgrad")
+            dWc = tg.reduce_slabs_segmented(part, plan.seg_ptr)                                     # [B, Co, K]
+            # D = d(W_lin W_post) in W_post's column layout (its x-part, which needs the mask GEMM's weight gradient, is
+            # added at the end); dW_lin += D W_post^T (long K: split-K slabs added in order), dW_post = W_lin^T D
+            D = tg.compose_post_wgrad(plan.coef_big, plan.block_of_t, dWc, None, F, F)               # [Co, (S*A+1)*F]
+            dWl = dWl + tg.small_gemm(D, Wp, trans_b=True, k_splits=max(1, D.shape[1] // 128))
+            dWp = tg.small_gemm(Wl, D, trans_a=True)                                                # [Fo, (S*A+1)*F]
+        elif plan.big:
             part = tg.wgrad_partials(dO, Z, plan.slabs, plan.slabs.shape[0], name="gemm_post_wgrad")
             dWc = tg.reduce_slabs_segmented(part, plan.seg_ptr)                                     # [B, Co, K]
             # W_c(d)[:, m] = sum_{s, a -> m} coef(d, s, a) W_lin W_{s,a}  ->  D_{s,a} = sum_d coef(d, s, a) dW_c(d)[:, m(a)];
@@ -411,7 +448,10 @@ class _FusedMMAConv(torch.autograd.Function):
             Yt = torch.einsum("nsam,nmf->nsaf", plan.tail_coef, Zt.view(-1, Am, F)).reshape(Zt.shape[0], S * A * F)
             dWl = dWl + dOt.t() @ (Yt @ Wy.t())
             g = dHt.t() @ Yt
-            dWy = g if dWy is None else dWy + g
+            if dWp is not None:
+                dWp[:, F:] += g
+            else:
+                dWy = g if dWy is None else dWy + g
         del dO
         if ex is not None:
             ex.sum_slices(dPQ[:, F:2 * F], n)
@@ -422,9 +462,12 @@ class _FusedMMAConv(torch.autograd.Function):
             dPQ[:, F:2 * F] = dQ_loc
             dQ_loc.record_stream(torch.cuda.current_stream(dev))
         # ---- mask projection + composed x-part, all in node order: dx, dW1
-        Wcx = Wl @ Wx
-        W1 = torch.cat([Wm[:, :F], Wm[:, F:2 * F], Wcx], dim=0)
-        w1hi, w1lo = tg.split_weight(W1.t())
+        if bw is not None:
+            w1hi, w1lo = bw[1]
+        else:
+            Wcx = Wl @ Wx
+            W1 = torch.cat([Wm[:, :F], Wm[:, F:2 * F], Wcx], dim=0)
+            w1hi, w1lo = tg.split_weight(W1.t())
         dx = torch.empty((n, F), dtype=torch.float32, device=dev)
         if (2 * F) % 128 == 0:
             tg.linear(dPQ, w1hi, w1lo, F, A1=d_out, out=dx, name="gemm_mask_dgrad")
@@ -437,8 +480,16 @@ class _FusedMMAConv(torch.autograd.Function):
         dWm[:, :F] = dW1[:F]
         dWm[:, F:2 * F] = dW1[F:2 * F]
         dWcx = dW1[2 * F:]                                                                          # [Co, F]
-        dWl = dWl + dWcx @ Wx.t()
-        dWp = torch.cat([Wl.t() @ dWcx, dWy if dWy is not None else torch.zeros_like(Wy)], dim=1)
+        if wprep:
+            dWl = dWl + tg.small_gemm(dWcx, Wx, trans_b=True)
+            dWpx = tg.small_gemm(Wl, dWcx, trans_a=True)                                            # [Fo, F]
+            if dWp is not None:
+                dWp[:, :F] = dWpx
+            else:
+                dWp = torch.cat([dWpx, dWy if dWy is not None else torch.zeros_like(Wy)], dim=1)
+        else:
+            dWl = dWl + dWcx @ Wx.t()
+            dWp = torch.cat([Wl.t() @ dWcx, dWy if dWy is not None else torch.zeros_like(Wy)], dim=1)
         has_bm, has_bp, has_bl = ctx.has_b
         dbm = (tg.colsum(dPQ[:, :F]) if F % 4 == 0 else dPQ[:, :F].sum(0)) if has_bm else None
         dbp = dbc @ Wl if has_bp else None

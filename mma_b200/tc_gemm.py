@@ -189,3 +189,64 @@ def colsum(src: Tensor) -> Tensor:
         _lib.check(_lib.lib().mma_gather_rows(_lib.ptr(src), src.stride(0), None, n, F, None, 0,
                                               _lib.ptr(part), parts, _lib.stream_ptr(dev)), "mma_gather_rows")
     return reduce_slabs(part)
+
+
+# ---------------------------------------------------------------------------------------------
+# weight-space algebra of the fused layer (csrc/weight_prep.cu)
+# ---------------------------------------------------------------------------------------------
+def small_gemm(A: Tensor, B: Tensor, *, trans_a: bool = False, trans_b: bool = False, k_splits: int = 1,
+               name: str = "mma_small_gemm") -> Tensor:
+    """op(A) @ op(B) for the small weight-space products (plain fp32 FFMA, fixed summation order).  A / B: fp32 with
+    unit column stride.  k_splits > 1: split-K into slabs added in order by mma_reduce_slabs (long-K, few outputs)."""
+    dev = _lib.require_cuda(A, B)
+    if A.dtype != torch.float32 or B.dtype != torch.float32 or A.dim() != 2 or B.dim() != 2 or A.stride(1) != 1 or B.stride(1) != 1:
+        raise RuntimeError("small_gemm: fp32 matrices with unit column stride")
+    M, K = (A.shape[1], A.shape[0]) if trans_a else A.shape
+    Kb, N = (B.shape[1], B.shape[0]) if trans_b else B.shape
+    if K != Kb:
+        raise RuntimeError(f"small_gemm: inner dimensions {K} and {Kb} differ")
+    splits = _lib.lib().mma_small_gemm_splits(K, k_splits)
+    C = torch.empty((splits, M, N) if splits > 1 else (M, N), dtype=torch.float32, device=dev)
+    with _lib.kernel_scope(name, dev):
+        _lib.check(_lib.lib().mma_small_gemm(_lib.ptr(A), A.stride(0), int(trans_a), _lib.ptr(B), B.stride(0), int(trans_b),
+                                             _lib.ptr(C), N, M, N, K, splits, _lib.stream_ptr(dev)), name)
+    if splits == 1:
+        return C
+    return reduce_slabs(C) if (M * N) % 4 == 0 else C.sum(0)        # slabs added in ascending order either way
+
+
+def compose_post_weight(coef: Tensor, WlW: Tensor, col0: int, F: int, transposed: bool):
+    """coef [B, S, A, Am], WlW [Co, col0 + S*A*F] -> (hi, lo) [B, Co, Am*F] of the composed per-range weight, split for
+    the 3xTF32 GEMMs, and (hiT, loT) [B, Am*F, Co] when `transposed` (else None)."""
+    dev = _lib.require_cuda(coef, WlW)
+    B, S, A, Am = coef.shape
+    Co = WlW.shape[0]
+    if not coef.is_contiguous() or WlW.stride(1) != 1 or WlW.shape[1] < col0 + S * A * F:
+        raise RuntimeError("compose_post_weight: coef contiguous [B,S,A,Am]; WlW [Co, >= col0 + S*A*F]")
+    hi = torch.empty((B, Co, Am * F), dtype=torch.float32, device=dev)
+    lo = torch.empty_like(hi)
+    hiT = torch.empty((B, Am * F, Co), dtype=torch.float32, device=dev) if transposed else None
+    loT = torch.empty_like(hiT) if transposed else None
+    with _lib.kernel_scope("mma_compose_post_weight", dev):
+        _lib.check(_lib.lib().mma_compose_post_weight(_lib.ptr(coef), B, S, A, Am, _lib.ptr(WlW), WlW.stride(0), col0, Co, F,
+                                                      _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(hiT), _lib.ptr(loT),
+                                                      _lib.stream_ptr(dev)), "mma_compose_post_weight")
+    return hi, lo, hiT, loT
+
+
+def compose_post_wgrad(coef: Tensor, block_of: Tensor, dWc: Tensor, dX: Optional[Tensor], col0: int, F: int) -> Tensor:
+    """coef [B, S, A, Am], dWc [B, Co, Am*F], dX [Co, col0] -> D [Co, col0 + S*A*F]: the gradient of W_lin W_post in
+    W_post's column layout ([x-part | (s, a) blocks])."""
+    dev = _lib.require_cuda(coef, dWc, block_of)
+    B, S, A, Am = coef.shape
+    Co = dWc.shape[1]
+    if not coef.is_contiguous() or not dWc.is_contiguous() or block_of.dtype != torch.int32 or block_of.numel() != A:
+        raise RuntimeError("compose_post_wgrad: coef / dWc contiguous, block_of int32 [A]")
+    if dX is not None and (dX.shape != (Co, col0) or dX.stride(1) != 1):
+        raise RuntimeError("compose_post_wgrad: dX must be [Co, col0] with unit column stride")
+    D = torch.empty((Co, col0 + S * A * F), dtype=torch.float32, device=dev)
+    with _lib.kernel_scope("mma_compose_post_wgrad", dev):
+        _lib.check(_lib.lib().mma_compose_post_wgrad(_lib.ptr(coef), B, S, A, Am, _lib.ptr(block_of), _lib.ptr(dWc), Co, F,
+                                                     _lib.ptr(dX), 0 if dX is None else dX.stride(0), col0, _lib.ptr(D),
+                                                     D.stride(0), _lib.stream_ptr(dev)), "mma_compose_post_wgrad")
+    return D

@@ -116,3 +116,85 @@ def test_no_cpu_path():
     from mma_b200 import tc_gemm as tg
     with pytest.raises(RuntimeError):
         tg.split_weight(torch.randn(4, 4))
+
+
+# ---------------------------------------------------------------------------------------------
+# weight-space algebra of the fused layer (csrc/weight_prep.cu)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K,ta,tb,splits", [(128, 2688, 128, False, False, 1), (128, 128, 2688, False, True, 21),
+                                                (128, 2688, 128, True, False, 1), (75, 33, 50, False, False, 1),
+                                                (5, 7, 300, True, True, 4), (64, 64, 16, False, False, 1)])
+def test_small_gemm_vs_fp64(M, N, K, ta, tb, splits):
+    from mma_b200 import tc_gemm as tg
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn((K, M) if ta else (M, K), generator=g).cuda()
+    B = torch.randn((N, K) if tb else (K, N), generator=g).cuda()
+    C = tg.small_gemm(A, B, trans_a=ta, trans_b=tb, k_splits=splits)
+    ref = (A.double().t() if ta else A.double()) @ (B.double().t() if tb else B.double())
+    assert C.shape == (M, N)
+    assert relerr(C, ref) < 2e-6
+    # operands that are column slices of wider matrices (W_x = W_post[:, :F])
+    Aw = torch.randn((K, M + 8) if ta else (M, K + 8), generator=g).cuda()
+    Av = Aw[:, :M] if ta else Aw[:, :K]
+    C2 = tg.small_gemm(Av, B, trans_a=ta, trans_b=tb, k_splits=splits)
+    ref2 = (Av.double().t() if ta else Av.double()) @ (B.double().t() if tb else B.double())
+    assert relerr(C2, ref2) < 2e-6
+
+
+@pytest.mark.parametrize("nb,S,names,F,Co", [(37, 4, ("mean", "sum", "min", "max", "std"), 128, 128),
+                                             (3, 3, ("min", "max"), 20, 12), (1, 1, ("mean",), 4, 4)])
+def test_compose_post_weight_and_its_gradient_vs_einsum(nb, S, names, F, Co):
+    """W_c = sum_{s, a -> m} coef W_lin W_{s,a} (split for the 3xTF32 GEMMs, plus the transpose) and the gradient
+    D = sum_b coef dW_c against the torch statement of the same algebra (fused_layer.py, MMA_WPREP=0 path)."""
+    from mma_b200 import _lib, tc_gemm as tg
+    from mma_b200.fused_layer import fold_blocks
+    akinds = tuple(_lib.AGGR_KINDS[a] for a in names)
+    mat, block_of, inv = fold_blocks(akinds)
+    A, Am = len(akinds), len(mat)
+    g = torch.Generator().manual_seed(nb + S + F)
+    coef = torch.zeros(nb, S, A, Am)
+    for a in range(A):
+        coef[:, :, a, block_of[a]] = torch.rand(nb, S, generator=g) + 0.1
+    coef = coef.cuda()
+    WlW = torch.randn(Co, (S * A + 1) * F, generator=g).cuda()
+    hi, lo, hiT, loT = tg.compose_post_weight(coef, WlW, F, F, True)
+    ref = torch.einsum("bsam,scaf->bcmf", coef.double(), WlW[:, F:].double().view(Co, S, A, F).permute(1, 0, 2, 3)).reshape(nb, Co, Am * F)
+    assert relerr(hi + lo, ref) < 1e-6
+    assert torch.equal(hiT, hi.transpose(1, 2)) and torch.equal(loT, lo.transpose(1, 2))
+    # hi is a TF32 number, lo the TF32 of the residual (low 13 mantissa bits clear)
+    assert torch.equal((hi.view(torch.int32) & 0x1FFF), torch.zeros_like(hi, dtype=torch.int32))
+    assert torch.equal((lo.view(torch.int32) & 0x1FFF), torch.zeros_like(lo, dtype=torch.int32))
+    dWc = torch.randn(nb, Co, Am * F, generator=g).cuda()
+    dX = torch.randn(Co, F, generator=g).cuda()
+    D = tg.compose_post_wgrad(coef, torch.tensor(block_of, dtype=torch.int32).cuda(), dWc, dX, F, F)
+    refD = torch.einsum("bsam,bcmf->csaf", coef.double(), dWc.double().view(nb, Co, Am, F)).reshape(Co, S * A * F)
+    assert torch.equal(D[:, :F], dX)
+    assert relerr(D[:, F:], refD) < 2e-6
+    D0 = tg.compose_post_wgrad(coef, torch.tensor(block_of, dtype=torch.int32).cuda(), dWc, None, F, F)
+    assert float(D0[:, :F].abs().max()) == 0.0 and torch.equal(D0[:, F:], D[:, F:])
+
+
+def test_weight_prep_kernels_match_the_torch_formulation_of_the_layer(monkeypatch):
+    """The fused layer with the library's weight-space kernels against the same layer with the torch formulation
+    (MMA_WPREP=0): output and every gradient at 5e-6 (the summation order of the small products differs, and with it
+    the last bits of the weights the 3xTF32 GEMMs see)."""
+    import mma_b200
+    from mma_b200 import fused_layer
+    from mma_b200.synthetic import degree_histogram
+    torch.manual_seed(5)
+    N, E, F = 3000, 40000, 128
+    ei = torch.randint(0, N, (2, E))
+    conv = mma_b200.MMAConv(F, F, ["mean", "sum", "min", "max", "std"], ["identity", "amplification", "attenuation", "linear"],
+                            degree_histogram(ei, N), towers=1, strict_reference=False).cuda()
+    params = list(conv.parameters()) + conv.mask_parameters()
+    graph = mma_b200.Graph(ei[0].cuda(), ei[1].cuda(), N, sort_rows=True)
+    x = torch.randn(N, F).cuda().requires_grad_()
+    gy = torch.randn(N, F).cuda()
+    res = {}
+    for flag in (True, False):
+        monkeypatch.setattr(fused_layer, "WPREP", flag)
+        conv._calls = 0
+        y = conv(x, graph)
+        res[flag] = [y.detach()] + [t.detach() for t in torch.autograd.grad(y, [x] + params, gy)]
+    for a, b in zip(res[True], res[False]):
+        assert relerr(a, b.double()) < 5e-6
