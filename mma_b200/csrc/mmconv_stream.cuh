@@ -41,6 +41,19 @@ __device__ __forceinline__ void cp_async_pred(uint32_t dst, const void *src, boo
                      :: "r"(dst), "l"(src), "r"((int)pred) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// copy iff cnt > U (U a compile-time slot number): the predicate is formed inside, one SETP per copy
+template <int BYTES, int U>
+__device__ __forceinline__ void cp_async_if_gt(uint32_t dst, const void *src, int cnt) {
+    if constexpr (BYTES == 16)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.gt.s32 p, %2, %3;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}"
+                     :: "r"(dst), "l"(src), "r"(cnt), "n"(U) : "memory");
+    else if constexpr (BYTES == 8)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.gt.s32 p, %2, %3;\n\t@p cp.async.ca.shared.global [%0], [%1], 8;\n\t}"
+                     :: "r"(dst), "l"(src), "r"(cnt), "n"(U) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.gt.s32 p, %2, %3;\n\t@p cp.async.ca.shared.global [%0], [%1], 4;\n\t}"
+                     :: "r"(dst), "l"(src), "r"(cnt), "n"(U) : "memory");
+}
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
@@ -300,11 +313,20 @@ struct RowRing {
         if (n > 0) {
             if (i_pos >= idx_base + 32) { idx_base += 32; request_chunk(idx_base + 64); }
             const uint32_t dst = base + (uint32_t)(ring_i * 4 * rowb);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int j = col_at(i_pos + u);            // u >= n: a stale slot, the copy is predicated off
-                cp_async_pred<VEC * 4>(dst + (uint32_t)(u * rowb), Qc + (uint64_t)(uint32_t)j * ldq_b, live && u < n);
+            const int cnt = live ? n : 0;                   // slots u >= cnt: a stale index, the copy is predicated off
+            const int sl = i_pos & 127;
+            int j0, j1, j2, j3;
+            if (sl <= 124) {                                // the four entries are consecutive slots of the window
+                const uint32_t a = idx_smem + (uint32_t)(sl * 4);
+                asm volatile("ld.shared.b32 %0, [%4];\n\tld.shared.b32 %1, [%4+4];\n\tld.shared.b32 %2, [%4+8];\n\t"
+                             "ld.shared.b32 %3, [%4+12];" : "=r"(j0), "=r"(j1), "=r"(j2), "=r"(j3) : "r"(a));
+            } else {
+                j0 = col_at(i_pos); j1 = col_at(i_pos + 1); j2 = col_at(i_pos + 2); j3 = col_at(i_pos + 3);
             }
+            cp_async_if_gt<VEC * 4, 0>(dst, Qc + (uint64_t)(uint32_t)j0 * ldq_b, cnt);
+            cp_async_if_gt<VEC * 4, 1>(dst + (uint32_t)rowb, Qc + (uint64_t)(uint32_t)j1 * ldq_b, cnt);
+            cp_async_if_gt<VEC * 4, 2>(dst + (uint32_t)(2 * rowb), Qc + (uint64_t)(uint32_t)j2 * ldq_b, cnt);
+            cp_async_if_gt<VEC * 4, 3>(dst + (uint32_t)(3 * rowb), Qc + (uint64_t)(uint32_t)j3 * ldq_b, cnt);
         }
         cp_async_commit();
         i_pos += n;

@@ -52,20 +52,57 @@ __global__ void peer_wait_kernel(const unsigned long long *epoch, const unsigned
     __threadfence_system();
 }
 
-// one thread per 4 columns of one row; slices are contiguous [rows, w]
+// out = sum of the slices in ascending order.  Slices are contiguous [rows, w]; a thread owns UNR 16-byte pieces of
+// the output (a block-stride apart, so every load instruction of the warp covers whole lines) and issues the loads of
+// ALL slices for all of them before the first add: n_slices x UNR x 16 B in flight per thread (the first version had
+// one piece per thread and a load -> add chain: 2.6 TB/s at 2 slices, 0.6 ms of a 14 ms step).
+template <int NS>
 __global__ void __launch_bounds__(256) sum_slices_kernel(SliceList sl, int n_slices, int64_t rows, int w,
                                                          float *__restrict__ out, int64_t ldo) {
+    constexpr int UNR = NS <= 2 ? 4 : 2;
     const int per_row = w >> 2;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows * per_row) return;
-    const int64_t r = i / per_row;
-    const int c = (int)(i - r * per_row) * 4;
-    float4 acc = __ldcs(reinterpret_cast<const float4 *>(sl.p[0] + r * w + c));
-    for (int k = 1; k < n_slices; ++k) {
-        const float4 v = __ldcs(reinterpret_cast<const float4 *>(sl.p[k] + r * w + c));
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    const int64_t total = rows * per_row;
+    const int ns = NS > 0 ? NS : n_slices;
+    for (int64_t i0 = (int64_t)blockIdx.x * (256 * UNR) + threadIdx.x; i0 < total; i0 += (int64_t)gridDim.x * (256 * UNR)) {
+        if constexpr (NS > 0) {
+            float4 v[UNR][NS];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int64_t i = i0 + (int64_t)u * 256;
+                if (i < total) {
+                    const int64_t r = i / per_row;
+                    const int64_t off = r * w + (i - r * per_row) * 4;
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) v[u][k] = __ldcs(reinterpret_cast<const float4 *>(sl.p[k] + off));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int64_t i = i0 + (int64_t)u * 256;
+                if (i < total) {
+                    float4 acc = v[u][0];
+#pragma unroll
+                    for (int k = 1; k < NS; ++k) { acc.x += v[u][k].x; acc.y += v[u][k].y; acc.z += v[u][k].z; acc.w += v[u][k].w; }
+                    const int64_t r = i / per_row;
+                    *reinterpret_cast<float4 *>(out + r * ldo + (i - r * per_row) * 4) = acc;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int64_t i = i0 + (int64_t)u * 256;
+                if (i >= total) continue;
+                const int64_t r = i / per_row;
+                const int64_t off = r * w + (i - r * per_row) * 4;
+                float4 acc = __ldcs(reinterpret_cast<const float4 *>(sl.p[0] + off));
+                for (int k = 1; k < ns; ++k) {
+                    const float4 t = __ldcs(reinterpret_cast<const float4 *>(sl.p[k] + off));
+                    acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+                }
+                *reinterpret_cast<float4 *>(out + r * ldo + (i - r * per_row) * 4) = acc;
+            }
+        }
     }
-    *reinterpret_cast<float4 *>(out + r * ldo + c) = acc;
 }
 
 }  // namespace mma
@@ -167,10 +204,16 @@ extern "C" int mma_sum_slices(const float *const *slices_host, int n_slices, int
         if (!slices_host[i] || !aligned16(slices_host[i])) return MMA_ERR_INVALID;
         sl.p[i] = slices_host[i];
     }
-    const int64_t threads = rows * (w / 4);
-    if ((threads + 255) / 256 > INT32_MAX) return MMA_ERR_UNSUPPORTED;
-    sum_slices_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        sl, n_slices, rows, w, out, ldo);
+    const int64_t pieces = rows * (w / 4);
+    const int64_t want = (pieces + 511) / 512;
+    const unsigned grid = (unsigned)(want < (int64_t)kSMs * 16 ? want : (int64_t)kSMs * 16);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch (n_slices) {
+        case 2: sum_slices_kernel<2><<<grid, 256, 0, st>>>(sl, n_slices, rows, w, out, ldo); break;
+        case 4: sum_slices_kernel<4><<<grid, 256, 0, st>>>(sl, n_slices, rows, w, out, ldo); break;
+        case 8: sum_slices_kernel<8><<<grid, 256, 0, st>>>(sl, n_slices, rows, w, out, ldo); break;
+        default: sum_slices_kernel<0><<<grid, 256, 0, st>>>(sl, n_slices, rows, w, out, ldo); break;
+    }
     MMA_LAUNCH_CHECK();
     return MMA_OK;
 }

@@ -182,24 +182,37 @@ class PeerExchange:
 
     # ---------------------------------------------------------------- forward: all-gather of Q, window by window
     def push_q(self, Q: Tensor, rows: int) -> None:
-        """Q [rows, F] (unit column stride; may be a column view of a wider matrix): columns of window k go, as strided
-        2-D copies straight out of Q (no pack pass), into rows [rank * max_rows, +rows) of every rank's recv_q; phase k
-        announces the window.  The copy stream first waits for all ranks' entry announcement (their receive buffers
-        are free)."""
+        """Q [rows, F] (unit column stride; may be a column view of a wider matrix) goes into rows [rank * max_rows,
+        +rows) of every rank's recv_q; phase k announces window k.  One window (the default): a local copy makes the
+        source contiguous, the peer copies are 1-D.  Several windows: the columns of window k go as strided 2-D copies
+        straight out of Q.  The copy stream first waits for all ranks' entry announcement (their receive buffers are
+        free)."""
         if Q.stride(1) != 1 or Q.dtype != torch.float32 or Q.shape[1] != self.F:
             raise RuntimeError("push_q: Q must be fp32 [rows, F] with unit column stride")
         cur = torch.cuda.current_stream(self.dev)
+        lib = _lib.lib()
+        own_ptr = self.region.base[self.rank] + self._off_recv + 4 * self.rank * self.max_rows * self.F
+        staged = len(self.windows) == 1 and Q.stride(0) != self.F
+        if staged:
+            # Q is a column block of a wider matrix ([P | Q | XW] of the projection GEMM): pushed as it lies, every peer
+            # copy would be a 2-D copy of 512-byte rows, which the copy engines move at ~440 GB/s.  One LOCAL strided copy
+            # into this rank's own block of its gathered buffer (where K1 reads it anyway) makes the source contiguous:
+            # the seven peer copies then are 1-D and run at the engines' full rate (590 GB/s per GPU at 8 GPUs).
+            with torch.cuda.device(self.dev):
+                _lib.check(lib.mma_peer_copy_2d(own_ptr, self.F * 4, Q.data_ptr(), Q.stride(0) * 4, self.F * 4, rows,
+                                                cur.cuda_stream), "mma_peer_copy_2d")
         ev = torch.cuda.Event()
         ev.record(cur)
         for st in self.streams:
             st.wait_event(ev)
             self.wait(PHASE_ENTER, st)
-        lib = _lib.lib()
         spitch, dpitch = Q.stride(0) * 4, self.F * 4
-        full = len(self.windows) == 1 and Q.stride(0) == self.F
+        full = len(self.windows) == 1 and (staged or Q.stride(0) == self.F)
         for k, (s_, w) in enumerate(zip(self.windows, self.widths)):
-            src = Q.data_ptr() + 4 * s_.start
+            src = (own_ptr if staged else Q.data_ptr()) + 4 * s_.start
             for o in self._peer_order():
+                if staged and o == self.rank:
+                    continue                                # already in place
                 dst = self.region.base[o] + self._off_recv + 4 * (self.rank * self.max_rows * self.F + s_.start)
                 with torch.cuda.device(self.dev):
                     if full:
