@@ -126,6 +126,7 @@ class PeerExchange:
         self.err = torch.zeros(1, dtype=torch.int32, device=device)
         self.streams = [torch.cuda.Stream(device=device, priority=-1) for _ in range(max(1, min(n_copy_streams, world)))]
         self.fwd_calls = 0          # host-side count of forward calls (guards the gathered Q a backward re-reads)
+        self._own_part: Optional[Tensor] = None     # partial-dQ tensor whose own-rank block sum_slices() reads in place
         torch.cuda.synchronize(device)
         dist.barrier(group)
 
@@ -236,6 +237,12 @@ class PeerExchange:
         ev.record(cur)
         st = self._stream_for(o)
         st.wait_event(ev)
+        if o == self.rank:
+            # this rank's own block never travels: sum_slices() reads it where it lies (`own`), and only the flag is
+            # set -- one 1/world-sized local copy less at the tail of the exchange, which is the critical path
+            self._own_part = part
+            self._announce(self.PHASE_BWD, [o])
+            return
         nbytes = self.max_rows * self.F * 4
         dst = self.region.base[o] + self._off_slice + 4 * self.rank * self.max_rows * self.F
         src = part.data_ptr() + 4 * o * self.max_rows * self.F
@@ -253,10 +260,15 @@ class PeerExchange:
         """out (a [rows, F] view with unit column stride) = sum over ranks, ascending, of the arrived slices -- after
         waiting for PHASE_BWD on the current stream."""
         self.wait(self.PHASE_BWD)
-        ptrs = (C.c_void_p * self.world)(*[self.slices[r].data_ptr() for r in range(self.world)])
+        where = [self.slices[r].data_ptr() for r in range(self.world)]
+        own = self._own_part
+        if own is not None:                                 # this rank's own partial block, in place (push_partial_block)
+            where[self.rank] = own.data_ptr() + 4 * self.rank * self.max_rows * self.F
+        ptrs = (C.c_void_p * self.world)(*where)
         with _lib.kernel_scope("mma_sum_slices", self.dev):
             _lib.check(_lib.lib().mma_sum_slices(ptrs, self.world, rows, self.F, out.data_ptr(), out.stride(0),
                                                  _lib.stream_ptr(self.dev)), "mma_sum_slices")
+        self._own_part = None                               # the summing kernel is enqueued: stream order keeps the block alive
 
     def join(self) -> None:
         """The current stream waits for everything enqueued on the copy streams (end of a call / of a capture)."""
