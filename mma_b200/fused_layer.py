@@ -42,6 +42,10 @@ G_ORDER = os.environ.get("MMA_G_ORDER", "csc")       # order of the per-edge gra
 # small GEMM + composition kernels (csrc/weight_prep.cu, ~15 launches per step); "0" = the torch formulation (~60 launches,
 # kept as the readable statement of the algebra and for A/B runs).
 WPREP = os.environ.get("MMA_WPREP", "1") == "1"
+# Sharded backward: the mask GEMMs' dQ-independent two thirds (dx = dP W_i + dOut W_cx, the dP / dOut rows of dW1, the
+# bias gradient) run BEFORE the wait for the reduce-scatter and only the dQ third after it.  "auto": from 4 ranks up
+# (there the reduce-scatter is exposed; at 2 ranks it hides completely and the split only adds a pass over dx and x).
+SPLIT_MASK_BWD = os.environ.get("MMA_SPLIT_MASK_BWD", "auto")
 
 # Parity hook (bench.py --verify, tests): when set to a dict, every forward leaves references to its raw aggregates
 # and arg indices there (Z in CSR-row order, arg_min / arg_max as CSR slots), so a sharded run can be compared bit for
@@ -314,6 +318,10 @@ class _FusedMMAConv(torch.autograd.Function):
                 hi3, lo3, hiT, loT = tg.compose_post_weight(plan.coef_big, WlW, F, F, True)
                 hi, lo, wct = hi3.view(-1, K), lo3.view(-1, K), (hiT.view(-1, Co), loT.view(-1, Co))
             bw = (wct, tg.split_weight(W1.t()))
+            if sg is not None and (SPLIT_MASK_BWD == "1" or (SPLIT_MASK_BWD == "auto" and sg.world >= 4)) \
+                    and F % 128 == 0 and EXCHANGE == "peer":
+                # the same transposed weight cut into its dQ-independent part [W_i^T | W_cx^T] and its dQ part W_j^T
+                bw = bw + (tg.split_weight(torch.cat([W1[:F], W1[2 * F:]], dim=0).t()), tg.split_weight(W1[F:2 * F].t()))
         else:
             WlWy = torch.matmul(Wl, Wy.view(Fo, S, A * F).permute(1, 0, 2))                         # [S, Co, A*F]
             if plan.big:
@@ -453,6 +461,16 @@ class _FusedMMAConv(torch.autograd.Function):
             else:
                 dWy = g if dWy is None else dWy + g
         del dO
+        has_bm, has_bp, has_bl = ctx.has_b
+        dbm = None
+        split = ex is not None and bw is not None and len(bw) == 4
+        dx = torch.empty((n, F), dtype=torch.float32, device=dev)
+        if split:
+            # everything of the mask GEMMs that does not need dQ, while the slices are still arriving
+            tg.linear(dPQ[:, :F], bw[2][0], bw[2][1], F, A1=d_out, out=dx, name="gemm_mask_dgrad")
+            dW_pe = tg.wgrad(dPQ[:, :F], x, G1=d_out, name="gemm_mask_wgrad")                       # rows [dP ; dOut]
+            if has_bm:
+                dbm = tg.colsum(dPQ[:, :F])
         if ex is not None:
             ex.sum_slices(dPQ[:, F:2 * F], n)
             ex.join()
@@ -468,8 +486,11 @@ class _FusedMMAConv(torch.autograd.Function):
             Wcx = Wl @ Wx
             W1 = torch.cat([Wm[:, :F], Wm[:, F:2 * F], Wcx], dim=0)
             w1hi, w1lo = tg.split_weight(W1.t())
-        dx = torch.empty((n, F), dtype=torch.float32, device=dev)
-        if (2 * F) % 128 == 0:
+        if split:
+            tg.linear(dPQ[:, F:2 * F], bw[3][0], bw[3][1], F, out=dx, add=dx, name="gemm_mask_dgrad")   # dx += dQ W_j
+            dW_q = tg.wgrad(dPQ[:, F:2 * F], x, name="gemm_mask_wgrad")
+            dW1 = torch.cat([dW_pe[:F], dW_q, dW_pe[F:]], dim=0)
+        elif (2 * F) % 128 == 0:
             tg.linear(dPQ, w1hi, w1lo, F, A1=d_out, out=dx, name="gemm_mask_dgrad")
             dW1 = tg.wgrad(dPQ, x, G1=d_out, name="gemm_mask_wgrad")
         else:
@@ -490,8 +511,8 @@ class _FusedMMAConv(torch.autograd.Function):
         else:
             dWl = dWl + dWcx @ Wx.t()
             dWp = torch.cat([Wl.t() @ dWcx, dWy if dWy is not None else torch.zeros_like(Wy)], dim=1)
-        has_bm, has_bp, has_bl = ctx.has_b
-        dbm = (tg.colsum(dPQ[:, :F]) if F % 4 == 0 else dPQ[:, :F].sum(0)) if has_bm else None
+        if has_bm and dbm is None:
+            dbm = tg.colsum(dPQ[:, :F]) if F % 4 == 0 else dPQ[:, :F].sum(0)
         dbp = dbc @ Wl if has_bp else None
         return dx, dWm, dbm, dWp, dbp, dWl, (dbc if has_bl else None), dR, None, None, None, None
 

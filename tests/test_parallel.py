@@ -215,7 +215,11 @@ def _gpu_layer_worker(rank, world, port, n, E, Fd):
         torch.manual_seed(11); conv._calls = 0
         yf = conv(xf, full)
         gf = torch.autograd.grad(yf, [xf] + params, gy.to(dev))
-        for balance in ("nodes", "edges"):
+        from mma_b200 import fused_layer
+        # ("edges", "1"): the backward's mask GEMMs cut into their dQ-independent part (before the wait for the
+        # reduce-scatter) and their dQ part (after it) -- what bench.py's sharded step runs from 4 ranks up
+        for balance, split in (("nodes", "auto"), ("edges", "1")):
+            fused_layer.SPLIT_MASK_BWD = split
             sg = par.ShardedGraph(src.to(dev), dst.to(dev), n, rank, world, balance=balance)
             xl = x[sg.lo:sg.hi].to(dev).requires_grad_()
             torch.manual_seed(11); conv._calls = 0
