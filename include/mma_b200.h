@@ -180,6 +180,69 @@ int mmconv_aggregate_bwd_dst(const int32_t *rowptr, const int32_t *col, const in
                              float *dP, int64_t lddp, int col0, int ncols, int flags, mma_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * The same two calls through ONE versioned argument block -- what a binding that is written by hand should use
+ * (the positional forms above are kept for existing callers).  Set struct_size = sizeof(mma_k1_args_t) and zero
+ * the rest before filling it in; fields are only ever APPENDED, a library that knows more fields than the caller's
+ * struct_size covers treats them as 0 / NULL, one that knows fewer rejects a block with non-zero bytes beyond its own
+ * size (MMA_ERR_UNSUPPORTED).  Field meanings are those of the positional parameters of the same name.
+ * Forward reads everything up to `ncols` except gslot / G / ldg / dP / lddp and writes Y, arg_min, arg_max, stat_mean,
+ * stat_var; the backward destination pass reads Y as dY and arg_min .. stat_var as the saved tensors of the forward,
+ * and writes G (at gslot) and dP.
+ * ---------------------------------------------------------------------- */
+typedef struct mma_k1_args {
+    uint32_t struct_size;           /* sizeof(mma_k1_args_t) of the CALLER */
+    int32_t flags;                  /* MMA_K1_ARGS_LOCAL */
+    /* graph: destination CSR and its optional acceleration tables */
+    const int32_t *rowptr, *col, *perm, *edge_gid;
+    int64_t E_total;
+    const int32_t *row_map, *rng_row;
+    int64_t rng_row0;
+    const int32_t *row_chunks;
+    int64_t n_chunks;
+    const int32_t *vrowptr;
+    int64_t n_vrows;
+    const int32_t *seg_tab, *split_tab;
+    int64_t n_split;
+    float *seg_ws;
+    int64_t n_rows, E;
+    /* message operands */
+    const float *P;
+    int64_t ldp;
+    const float *Q;
+    int64_t ldq;
+    const float *R;
+    int64_t ldr;
+    const float *keep;
+    int64_t ldk;
+    /* dropout */
+    float p_drop;
+    int32_t reserved0;
+    uint64_t seed;
+    const uint64_t *seed_dev;
+    /* aggregators / scalers */
+    int32_t T, F_in, A, S;
+    const int32_t *aggr_kinds, *scaler_kinds;
+    const float *scale_tab;
+    int64_t tab_stride;
+    /* aggregates (forward: out; backward: dY in) and what the forward saves for the backward */
+    float *Y;
+    int64_t ldy;
+    int32_t *arg_min, *arg_max;
+    float *stat_mean, *stat_var;
+    /* backward destination pass only */
+    const int32_t *gslot;
+    float *G;
+    int64_t ldg;
+    float *dP;
+    int64_t lddp;
+    /* column window */
+    int32_t col0, ncols;
+} mma_k1_args_t;
+
+int mmconv_aggregate_fwd_args(const mma_k1_args_t *args, mma_stream_t stream);
+int mmconv_aggregate_bwd_dst_args(const mma_k1_args_t *args, mma_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * K3 / transpose pass: deterministic segmented row sum (CSR SpMM)
  *   out[i, c] = sum_{k in [ptr[i], ptr[i+1])} val[k] * src[idx[k], c]      (val NULL = 1)
  * Used as (a) K1 backward source pass: dQ[j] = sum of G rows of j's out-edges

@@ -24,6 +24,24 @@ ACT_SIGMOID, ACT_RAW = 0, 1
 
 _vp, _i64, _i32, _f32, _u64, _u32 = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_uint64, C.c_uint32
 
+
+
+class K1Args(C.Structure):
+    """mma_k1_args_t (include/mma_b200.h): the versioned argument block of mmconv_aggregate_fwd_args / _bwd_dst_args."""
+    _fields_ = [("struct_size", _u32), ("flags", _i32),
+                ("rowptr", _vp), ("col", _vp), ("perm", _vp), ("edge_gid", _vp), ("E_total", _i64),
+                ("row_map", _vp), ("rng_row", _vp), ("rng_row0", _i64), ("row_chunks", _vp), ("n_chunks", _i64),
+                ("vrowptr", _vp), ("n_vrows", _i64), ("seg_tab", _vp), ("split_tab", _vp), ("n_split", _i64),
+                ("seg_ws", _vp), ("n_rows", _i64), ("E", _i64),
+                ("P", _vp), ("ldp", _i64), ("Q", _vp), ("ldq", _i64), ("R", _vp), ("ldr", _i64), ("keep", _vp), ("ldk", _i64),
+                ("p_drop", _f32), ("reserved0", _i32), ("seed", _u64), ("seed_dev", _vp),
+                ("T", _i32), ("F_in", _i32), ("A", _i32), ("S", _i32), ("aggr_kinds", _vp), ("scaler_kinds", _vp),
+                ("scale_tab", _vp), ("tab_stride", _i64),
+                ("Y", _vp), ("ldy", _i64), ("arg_min", _vp), ("arg_max", _vp), ("stat_mean", _vp), ("stat_var", _vp),
+                ("gslot", _vp), ("G", _vp), ("ldg", _i64), ("dP", _vp), ("lddp", _i64),
+                ("col0", _i32), ("ncols", _i32)]
+
+
 _SIGS = {
     "mma_b200_version": ([], C.c_int),
     "mma_last_cuda_error": ([], C.c_char_p),
@@ -39,6 +57,8 @@ _SIGS = {
                                   _vp, _i64, _f32, _u64, _vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _i64,
                                   _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp],
                                  C.c_int),
+    "mmconv_aggregate_fwd_args": ([C.POINTER(K1Args), _vp], C.c_int),
+    "mmconv_aggregate_bwd_dst_args": ([C.POINTER(K1Args), _vp], C.c_int),
     "mma_gather_rows": ([_vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp, _i64, _vp], C.c_int),
     "mma_segment_sum_rows": ([_vp, _vp, _vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp], C.c_int),
     "mma_nc_aggregate_fwd": ([_vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32,

@@ -1144,3 +1144,41 @@ extern "C" int mmconv_aggregate_bwd_dst(const int32_t *rowptr, const int32_t *co
     MMA_LAUNCH_CHECK();
     return MMA_OK;
 }
+
+// ---- versioned argument block (include/mma_b200.h: mma_k1_args_t) ----
+static int load_k1_args(const mma_k1_args_t *in, mma_k1_args_t &a) {
+    constexpr size_t kV1 = offsetof(mma_k1_args_t, ncols) + sizeof(int32_t);              // the first published layout
+    if (!in || in->struct_size < kV1) return MMA_ERR_INVALID;
+    memset(&a, 0, sizeof(a));
+    const size_t have = in->struct_size, known = sizeof(mma_k1_args_t);
+    memcpy(&a, in, have < known ? have : known);
+    if (have > known) {                          // a newer caller: fields this library does not know must be unset
+        const unsigned char *extra = reinterpret_cast<const unsigned char *>(in) + known;
+        for (size_t i = 0; i < have - known; ++i)
+            if (extra[i]) return MMA_ERR_UNSUPPORTED;
+    }
+    return MMA_OK;
+}
+
+extern "C" int mmconv_aggregate_fwd_args(const mma_k1_args_t *args, mma_stream_t stream) {
+    mma_k1_args_t a;
+    const int rc = load_k1_args(args, a);
+    if (rc != MMA_OK) return rc;
+    return mmconv_aggregate_fwd(a.rowptr, a.col, a.perm, a.edge_gid, a.E_total, a.row_map, a.rng_row, a.rng_row0,
+                                a.row_chunks, a.n_chunks, a.vrowptr, a.n_vrows, a.seg_tab, a.split_tab, a.n_split, a.seg_ws,
+                                a.n_rows, a.E, a.P, a.ldp, a.Q, a.ldq, a.R, a.ldr, a.keep, a.ldk, a.p_drop, a.seed,
+                                a.seed_dev, a.T, a.F_in, a.A, a.aggr_kinds, a.S, a.scaler_kinds, a.scale_tab, a.tab_stride,
+                                a.Y, a.ldy, a.arg_min, a.arg_max, a.stat_mean, a.stat_var, a.col0, a.ncols, a.flags, stream);
+}
+
+extern "C" int mmconv_aggregate_bwd_dst_args(const mma_k1_args_t *args, mma_stream_t stream) {
+    mma_k1_args_t a;
+    const int rc = load_k1_args(args, a);
+    if (rc != MMA_OK) return rc;
+    return mmconv_aggregate_bwd_dst(a.rowptr, a.col, a.perm, a.edge_gid, a.E_total, a.row_map, a.rng_row, a.rng_row0,
+                                    a.row_chunks, a.n_chunks, a.vrowptr, a.n_vrows, a.seg_tab, a.split_tab, a.n_split,
+                                    a.seg_ws, a.n_rows, a.E, a.P, a.ldp, a.Q, a.ldq, a.R, a.ldr, a.keep, a.ldk, a.p_drop,
+                                    a.seed, a.seed_dev, a.T, a.F_in, a.A, a.aggr_kinds, a.S, a.scaler_kinds, a.scale_tab,
+                                    a.tab_stride, a.Y, a.ldy, a.arg_min, a.arg_max, a.stat_mean, a.stat_var, a.gslot, a.G,
+                                    a.ldg, a.dP, a.lddp, a.col0, a.ncols, a.flags, stream);
+}

@@ -7,6 +7,8 @@ from __future__ import annotations
 
 from typing import Dict, Optional, Sequence
 
+import ctypes as C
+
 import torch
 from torch import Tensor
 
@@ -55,25 +57,44 @@ def k1_forward(graph: Graph, P, Q, R, keep, *, T: int, F_in: int, akinds, skinds
     sharded path: a narrow gathered window addressed with global column indices).  seed_dev: int64
     device tensor holding the dropout seed (read at run time: CUDA-graph replays draw fresh masks)."""
     dev = graph.device
-    ak, sk = _lib.i32_array(akinds), _lib.i32_array(skinds)
-    chunks = graph.k1_chunks()
     seg = graph.k1_segments()
     seg_ws = (torch.empty((seg.n_slots, 6, T * F_in), dtype=torch.float32, device=dev)
               if seg is not None and seg.n_slots else None)
+    a, keepalive = _k1_args(graph, seg, seg_ws, P, Q, R, keep, T, F_in, akinds, skinds, tab, p_drop, seed, seed_dev, q_ptr,
+                            ldq, col0, ncols, local_args)
+    a.Y, a.ldy = _lib.ptr(Y), Y.stride(0)
+    a.arg_min, a.arg_max, a.stat_mean, a.stat_var = _lib.ptr(arg_min), _lib.ptr(arg_max), _lib.ptr(mean), _lib.ptr(var)
     with _lib.kernel_scope("mmconv_aggregate_fwd", dev):
-        _lib.check(_lib.lib().mmconv_aggregate_fwd(
-            _lib.ptr(graph.rowptr), _lib.ptr(graph.col), _lib.ptr(graph.perm), _lib.ptr(graph.gid), graph.E_total,
-            _lib.ptr(graph.row_map), _lib.ptr(graph.rng_row), int(graph.rng_row0), _lib.ptr(chunks),
-            0 if chunks is None else chunks.numel() - 1,
-            None if seg is None else _lib.ptr(seg.vrowptr), 0 if seg is None else seg.n_vrows,
-            None if seg is None else _lib.ptr(seg.seg_tab), None if seg is None else _lib.ptr(seg.split_tab),
-            0 if seg is None else seg.n_split, _lib.ptr(seg_ws), graph.n_dst, graph.E,
-            _lib.ptr(P), _ld(P), (_lib.ptr(Q) if q_ptr is None else q_ptr), (_ld(Q) if ldq is None else ldq),
-            _lib.ptr(R), _ld(R), _lib.ptr(keep), _ld(keep),
-            float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.ptr(seed_dev), T, F_in, len(akinds), ak, len(skinds), sk,
-            _lib.ptr(tab), 0 if tab is None else tab.shape[1],
-            _lib.ptr(Y), Y.stride(0), _lib.ptr(arg_min), _lib.ptr(arg_max), _lib.ptr(mean), _lib.ptr(var),
-            col0, ncols, _lib.K1_ARGS_LOCAL if local_args else 0, _lib.stream_ptr(dev)), "mmconv_aggregate_fwd")
+        _lib.check(_lib.lib().mmconv_aggregate_fwd_args(C.byref(a), _lib.stream_ptr(dev)), "mmconv_aggregate_fwd")
+
+
+def _k1_args(graph: Graph, seg, seg_ws, P, Q, R, keep, T, F_in, akinds, skinds, tab, p_drop, seed, seed_dev, q_ptr, ldq,
+             col0, ncols, local_args):
+    """The versioned argument block (include/mma_b200.h: mma_k1_args_t) for `graph`'s destination CSR and these
+    operands; the second value keeps the host arrays it points to alive until the call has been made."""
+    ak, sk = _lib.i32_array(akinds), _lib.i32_array(skinds)
+    chunks = graph.k1_chunks()
+    a = _lib.K1Args()
+    a.struct_size = C.sizeof(_lib.K1Args)
+    a.flags = _lib.K1_ARGS_LOCAL if local_args else 0
+    a.rowptr, a.col, a.perm, a.edge_gid = _lib.ptr(graph.rowptr), _lib.ptr(graph.col), _lib.ptr(graph.perm), _lib.ptr(graph.gid)
+    a.E_total = graph.E_total
+    a.row_map, a.rng_row, a.rng_row0 = _lib.ptr(graph.row_map), _lib.ptr(graph.rng_row), int(graph.rng_row0)
+    a.row_chunks, a.n_chunks = _lib.ptr(chunks), 0 if chunks is None else chunks.numel() - 1
+    if seg is not None:
+        a.vrowptr, a.n_vrows = _lib.ptr(seg.vrowptr), seg.n_vrows
+        a.seg_tab, a.split_tab, a.n_split = _lib.ptr(seg.seg_tab), _lib.ptr(seg.split_tab), seg.n_split
+    a.seg_ws = _lib.ptr(seg_ws)
+    a.n_rows, a.E = graph.n_dst, graph.E
+    a.P, a.ldp = _lib.ptr(P), _ld(P)
+    a.Q, a.ldq = (_lib.ptr(Q) if q_ptr is None else q_ptr), (_ld(Q) if ldq is None else ldq)
+    a.R, a.ldr, a.keep, a.ldk = _lib.ptr(R), _ld(R), _lib.ptr(keep), _ld(keep)
+    a.p_drop, a.seed, a.seed_dev = float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.ptr(seed_dev)
+    a.T, a.F_in, a.A, a.S = T, F_in, len(akinds), len(skinds)
+    a.aggr_kinds, a.scaler_kinds = C.cast(ak, C.c_void_p), C.cast(sk, C.c_void_p)
+    a.scale_tab, a.tab_stride = _lib.ptr(tab), 0 if tab is None else tab.shape[1]
+    a.col0, a.ncols = col0, ncols
+    return a, (ak, sk, chunks)
 
 
 def k1_backward_dst(graph: Graph, P, Q, R, keep, *, T: int, F_in: int, akinds, skinds, tab, p_drop: float,
@@ -82,26 +103,16 @@ def k1_backward_dst(graph: Graph, P, Q, R, keep, *, T: int, F_in: int, akinds, s
                     ldq: Optional[int] = None, seed_dev: Optional[Tensor] = None) -> None:
     """One launch of mmconv_aggregate_bwd_dst (destination pass of K1's backward)."""
     dev = graph.device
-    ak, sk = _lib.i32_array(akinds), _lib.i32_array(skinds)
-    chunks = graph.k1_chunks()
     seg = graph.k1_segments()
     seg_ws = (torch.empty((seg.n_slots, T * F_in), dtype=torch.float32, device=dev)
               if seg is not None and seg.n_slots else None)
+    a, keepalive = _k1_args(graph, seg, seg_ws, P, Q, R, keep, T, F_in, akinds, skinds, tab, p_drop, seed, seed_dev, q_ptr,
+                            ldq, col0, ncols, local_args)
+    a.Y, a.ldy = _lib.ptr(dY), dY.stride(0)
+    a.arg_min, a.arg_max, a.stat_mean, a.stat_var = _lib.ptr(arg_min), _lib.ptr(arg_max), _lib.ptr(mean), _lib.ptr(var)
+    a.gslot, a.G, a.ldg, a.dP, a.lddp = _lib.ptr(gslot), _lib.ptr(G), ldg, _lib.ptr(dP), lddp
     with _lib.kernel_scope("mmconv_aggregate_bwd_dst", dev):
-        _lib.check(_lib.lib().mmconv_aggregate_bwd_dst(
-            _lib.ptr(graph.rowptr), _lib.ptr(graph.col), _lib.ptr(graph.perm), _lib.ptr(graph.gid), graph.E_total,
-            _lib.ptr(graph.row_map), _lib.ptr(graph.rng_row), int(graph.rng_row0), _lib.ptr(chunks),
-            0 if chunks is None else chunks.numel() - 1,
-            None if seg is None else _lib.ptr(seg.vrowptr), 0 if seg is None else seg.n_vrows,
-            None if seg is None else _lib.ptr(seg.seg_tab), None if seg is None else _lib.ptr(seg.split_tab),
-            0 if seg is None else seg.n_split, _lib.ptr(seg_ws), graph.n_dst, graph.E,
-            _lib.ptr(P), _ld(P), (_lib.ptr(Q) if q_ptr is None else q_ptr), (_ld(Q) if ldq is None else ldq),
-            _lib.ptr(R), _ld(R), _lib.ptr(keep), _ld(keep),
-            float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.ptr(seed_dev), T, F_in, len(akinds), ak, len(skinds), sk,
-            _lib.ptr(tab), 0 if tab is None else tab.shape[1],
-            _lib.ptr(dY), dY.stride(0), _lib.ptr(arg_min), _lib.ptr(arg_max), _lib.ptr(mean), _lib.ptr(var),
-            _lib.ptr(gslot), _lib.ptr(G), ldg, _lib.ptr(dP), lddp, col0, ncols,
-            _lib.K1_ARGS_LOCAL if local_args else 0, _lib.stream_ptr(dev)), "mmconv_aggregate_bwd_dst")
+        _lib.check(_lib.lib().mmconv_aggregate_bwd_dst_args(C.byref(a), _lib.stream_ptr(dev)), "mmconv_aggregate_bwd_dst")
 
 
 class _MMConvAggregate(torch.autograd.Function):

@@ -108,3 +108,48 @@ def test_integration_stub_matches_the_abi():
     decl = re.search(r"\nint mmconv_aggregate_fwd\((.*?)\);", hdr, re.S).group(1)
     assert len([a for a in decl.split(",") if a.strip()]) == len(toks)
 
+
+
+def test_k1_args_struct_layout_matches_the_header(tmp_path):
+    """mma_k1_args_t as gcc lays it out from include/mma_b200.h against the ctypes Structure that binds it: size and
+    the offset of every field (the versioned block is what a hand-written binding uses instead of 47 positional
+    arguments, so its layout IS the ABI)."""
+    import subprocess
+    fields = [f[0] for f in _lib.K1Args._fields_]
+    src = tmp_path / "layout.c"
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "mma_b200.h")}"',
+             'int main(void) {', '  printf("%zu\\n", sizeof(mma_k1_args_t));']
+    lines += [f'  printf("%zu\\n", offsetof(mma_k1_args_t, {f}));' for f in fields]
+    lines += ['  return 0;', '}']
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-o", str(exe), str(src)])
+    out = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert out[0] == ctypes.sizeof(_lib.K1Args)
+    for f, off in zip(fields, out[1:]):
+        assert getattr(_lib.K1Args, f).offset == off, f
+
+
+def test_k1_args_versioning_without_gpu():
+    l = _lib.lib()
+    a = _lib.K1Args()
+    assert l.mmconv_aggregate_fwd_args(None, None) == _lib.ERR_INVALID
+    a.struct_size = 16                                       # shorter than the first published layout
+    assert l.mmconv_aggregate_fwd_args(ctypes.byref(a), None) == _lib.ERR_INVALID
+    a.struct_size = ctypes.sizeof(_lib.K1Args)              # well-formed but empty: rejected by the argument checks
+    assert l.mmconv_aggregate_fwd_args(ctypes.byref(a), None) == _lib.ERR_INVALID
+    assert l.mmconv_aggregate_bwd_dst_args(ctypes.byref(a), None) == _lib.ERR_INVALID
+
+    class Newer(ctypes.Structure):                           # a caller built against a later header
+        _fields_ = [("base", _lib.K1Args), ("new_field", ctypes.c_int64)]
+    n = Newer()
+    n.base.struct_size = ctypes.sizeof(Newer)
+    fn = l.mmconv_aggregate_fwd_args
+    saved = fn.argtypes
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    try:
+        assert fn(ctypes.addressof(n), None) == _lib.ERR_INVALID        # unknown field unset: accepted, then the usual checks
+        n.new_field = 7
+        assert fn(ctypes.addressof(n), None) == _lib.ERR_UNSUPPORTED    # unknown field SET: this library cannot honour it
+    finally:
+        fn.argtypes = saved
