@@ -10,9 +10,11 @@ over NVLink 5 / NVSwitch) for the plumbing.  The reference has no distributed co
        backward: reduce-scatter of the per-rank partial dQ (sum over ranks, fixed ring order).
      min/max arg indices and the Philox dropout are keyed by GLOBAL edge ids (edge_gid), so the
      sharded result equals the single-GPU result bit-for-bit for min/max and within fp32
-     rounding for the rest.  The exchanges are pipelined over FEATURE SLICES (columns are
-     independent under every aggregator), so the collective of slice k+1 overlaps the
-     aggregation kernel of slice k on a side stream.
+     rounding for the rest.  Two carriers for the exchanges: the fused layer (fused_layer.py, what bench.py
+     runs) moves them over NVLink peer memory on the copy engines (peer.py); the aggregate-only entry point
+     of this module (`sharded_mmconv_aggregate`) uses NCCL collectives pipelined over FEATURE SLICES (columns
+     are independent under every aggregator: the collective of slice k+1 overlaps the aggregation kernel of
+     slice k on a side stream) -- it is also the gloo-testable statement of the protocol.
 (ii) BATCHES OF SMALL GRAPHS (ZINC-like) -> plain data parallel: split the block-diagonal batch
      by graphs (no halo), all-reduce weight gradients only (`allreduce_grads`).
 
