@@ -12,7 +12,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmma_b200.so")
+LIB_PATH = os.environ.get("MMA_B200_LIB") or os.path.join(_HERE, "libmma_b200.so")     # override: A/B of two builds (dev tools)
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_WORKSPACE = 0, -1, -2, -3, -4
 MAX_AGGR, MAX_SCALER = 8, 8

@@ -68,6 +68,7 @@ struct alignas(64) NtParams {
     int64_t ldadd;
     int add_in;
     int relu;                   // epilogue: C = max(C, 0) after bias / addend (MMA_GEMM_RELU)
+    int n256;                   // streaming kernel: A_hi B_hi and A_hi B_lo as one N = 256 MMA (MMA_GEMM_N256)
 };
 
 struct Tile { int64_t row0, row_end; int b_off, n0; };
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_kernel(const __grid_con
 
     if (warp == 0) {
         // ===================================================================== TMA producer: activations (HBM)
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t it = 0;
             for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
                 const Tile tl = locate_tile(p, t);
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_kernel(const __grid_con
         }
     } else if (warp == 10) {
         // ===================================================================== TMA producer: weights (L2)
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t it = 0;
             for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
                 const Tile tl = locate_tile(p, t);
@@ -247,8 +248,9 @@ __global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_kernel(const __grid_con
         }
     } else if (warp == 1) {
         // ===================================================================== MMA issuer
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc_tf32(BM, BN, 0, 0);
+            constexpr uint32_t idesc2 = umma_idesc_tf32(BM, 2 * BN, 0, 0);
             uint32_t it = 0, ti = 0;
             for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
                 const uint32_t buf = ti & 1u;
@@ -267,17 +269,28 @@ __global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_kernel(const __grid_con
                         const uint64_t a_hi = umma_desc_sw128(pa + k * 32, 16, 1024);
                         const uint64_t a_lo = umma_desc_sw128(pl + k * 32, 16, 1024);
                         const uint64_t b_hi = umma_desc_sw128(pb + k * 32, 16, 1024);
-                        const uint64_t b_lo = umma_desc_sw128(pb + B_BYTES + k * 32, 16, 1024);
                         const uint32_t first = (kb | k) != 0;
                         // The tensor core truncates when it adds into the fp32 accumulator, a bias that grows
                         // with the length of the accumulation chain.  The two small cross terms go to their
                         // own accumulator (2^-11 of the magnitude, so their truncation is negligible) and the
                         // main chain is 1 MMA per K step instead of 3; the epilogue adds the two.
-                        if (p.mode != 2) {
+                        //
+                        // A_hi B_hi (main) and A_hi B_lo (correction) are ONE instruction of N = 256: the weight slot
+                        // holds B_hi and B_lo back to back (128 rows of 128 B each, 8-row groups 1024 B apart), so a
+                        // descriptor at B_hi with N = 256 runs straight on into B_lo, and the two accumulators are
+                        // adjacent in tensor memory -- A_hi crosses shared memory once instead of twice (20 instead
+                        // of 24 KB of operand reads per K step; the kernel is shared-memory bound), 2 MMAs instead of 3.
+                        if (p.mode != 2 && p.n256) {
+                            umma_tf32_ss(d_tmem, a_hi, b_hi, idesc2, first);             // [main | corr] (+)= A_hi [B_hi ; B_lo]^T
+                            umma_tf32_ss(d_tmem + BN, a_lo, b_hi, idesc, 1u);            // corr += A_lo B_hi^T
+                        } else if (p.mode != 2) {
+                            const uint64_t b_lo = umma_desc_sw128(pb + B_BYTES + k * 32, 16, 1024);
                             umma_tf32_ss(d_tmem + BN, a_lo, b_hi, idesc, first);
                             umma_tf32_ss(d_tmem + BN, a_hi, b_lo, idesc, 1u);
+                            umma_tf32_ss(d_tmem, a_hi, b_hi, idesc, first);
+                        } else {
+                            umma_tf32_ss(d_tmem, a_hi, b_hi, idesc, first);
                         }
-                        umma_tf32_ss(d_tmem, a_hi, b_hi, idesc, first);
                     }
                     tc_commit(a_empty(sa));             // slots reusable once these MMAs retire
                     if (p.mode != 2) tc_commit(lo_empty(sl));
@@ -432,7 +445,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) gemm_nt_ares_kernel(const __gri
 
     if (warp == 0) {
         // ===================================================================== TMA producer: activations (HBM)
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t it = 0;
             for (int64_t t = blockIdx.x; t < p.n_tiles_m; t += gridDim.x) {
                 const Tile tl = locate_tile(p, t * p.n_tiles_n);
@@ -446,7 +459,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) gemm_nt_ares_kernel(const __gri
         }
     } else if (warp == 14) {
         // ===================================================================== TMA producer: weights (L2)
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t it = 0;
             for (int64_t t = blockIdx.x; t < p.n_tiles_m; t += gridDim.x) {
                 const Tile tl = locate_tile(p, t * p.n_tiles_n);
@@ -464,7 +477,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) gemm_nt_ares_kernel(const __gri
         }
     } else if (warp == 1) {
         // ===================================================================== MMA issuer
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr int AR_SPLIT = 1;                      // column slices per sub-tile issued as separate MMAs (see below)
             constexpr int AR_HN = AR_BN / AR_SPLIT;
             constexpr uint32_t idesc = umma_idesc_tf32(BM, AR_HN, 0, 0);
@@ -693,7 +706,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_con
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t it = 0;
             for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
                 const Unit x = locate(u);
@@ -713,7 +726,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_con
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc_tf32(BM, BN, 1, 1);
             uint32_t it = 0, ti = 0;
             for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++ti) {
@@ -1004,6 +1017,8 @@ extern "C" int mma_linear_tf32x3(const float *A0, int64_t lda0, int K0, const fl
         MMA_LAUNCH_CHECK();
         return MMA_OK;
     }
+    static const bool n256_on = [] { const char *e = getenv("MMA_GEMM_N256"); return !(e && e[0] == '0'); }();
+    p.n256 = n256_on ? 1 : 0;
     MMA_CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NT_SMEM_BYTES));
     const int64_t n_tiles = p.n_tiles_m * p.n_tiles_n;
     const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);

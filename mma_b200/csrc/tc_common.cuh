@@ -14,6 +14,16 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a CONVERGED warp.  The single-thread roles (TMA producer, MMA issuer) branch on this rather than on
+// `lane == 0`: ptxas knows that exactly one thread is active behind elect.sync and emits UTCHMMA / UTMALDG back to back;
+// behind `lane == 0` it wraps every one of them in an ELECT / PLOP3 / BRA.U.ANY loop (5 extra instructions and a branch
+// per MMA on the thread whose issue rate bounds the GEMMs).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(p));
+    return p != 0;
+}
+
 // ----------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
