@@ -43,9 +43,11 @@ constexpr int BAR_BYTES = 256;
 constexpr int NT_NA = 5, NT_NL = 2, NT_NB = 3;
 constexpr int NT_SMEM_BYTES = (NT_NA + NT_NL) * A_BYTES + NT_NB * 2 * B_BYTES + EPI_BYTES + BAR_BYTES + 1024;
 constexpr int NT_THREADS = 352;                           // + 1 warp: the B (weight) producer
-//   wgrad: raw [G | A] ring | [G_lo | A_lo] ring
+//   wgrad: raw [G | A | A_lo] ring | G_lo ring.  A_lo sits right behind the raw A tile of its stage so that ONE MMA of
+//   N = 256 runs over [A_hi ; A_lo] (see the kernel)
 constexpr int WG_NR = 4, WG_NL = 2;
-constexpr int WG_SMEM_BYTES = (WG_NR + WG_NL) * (A_BYTES + B_BYTES) + EPI_BYTES + BAR_BYTES + 1024;
+constexpr int WG_SLOT_BYTES = A_BYTES + 2 * B_BYTES;     // 48 KB
+constexpr int WG_SMEM_BYTES = WG_NR * WG_SLOT_BYTES + WG_NL * A_BYTES + BAR_BYTES + 1024;
 static_assert(NT_SMEM_BYTES <= 232448 && WG_SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory per CTA");
 constexpr int THREADS = 320;
 constexpr int TMEM_COLS = 512;   // 2 tiles in flight x (main + correction) accumulators of 128 columns
@@ -652,6 +654,7 @@ struct alignas(64) WgParams {
     int n_split;                // output rows n < n_split come from map_g0, the rest from map_g1 (at n - n_split)
     int tiles_n, tiles_k, mode;
     int N, K;
+    int n256;                   // G_hi A_hi and G_hi A_lo as one N = 256 MMA (MMA_GEMM_WG_N256)
     int64_t n_slabs;
     const int32_t *slab_tab;    // [n_slabs][4] = row0, row_end, out_slot, -
     float *part;                // [slots][N][K]
@@ -661,10 +664,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_con
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
-    constexpr int RAW_BYTES = A_BYTES + B_BYTES;           // one raw stage: G [4 x 4 KB] | A [4 x 4 KB]
-    const uint32_t lo_base = smem_base + WG_NR * RAW_BYTES;   // lo stage: G_lo | A_lo
-    const uint32_t epi_base = lo_base + WG_NL * RAW_BYTES;
-    const uint32_t bar_base = epi_base + EPI_BYTES;
+    constexpr int RAW_BYTES = A_BYTES + B_BYTES;           // bytes TMA brings per stage: G [4 x 4 KB] | A [4 x 4 KB]
+    constexpr int SLOT = WG_SLOT_BYTES;                    // stage: G | A | A_lo (written by the converter)
+    const uint32_t lo_base = smem_base + WG_NR * SLOT;     // G_lo ring
+    const uint32_t bar_base = lo_base + WG_NL * A_BYTES;
     // barriers: full[NR] (TMA landed), empty[NR] (MMAs retired), lo_full[NL] (converted), lo_empty[NL]
     auto full_bar = [&](int i) { return bar_base + 8u * i; };
     auto empty_bar = [&](int i) { return bar_base + 8u * (WG_NR + i); };
@@ -679,7 +682,6 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles = p.tiles_n * p.tiles_k;
     const int64_t n_units = p.n_slabs * tiles;
-    // stage layout: G [4 x 4 KB] | G_lo | A [4 x 4 KB] | A_lo
     struct Unit { int row0, row_end, slot, n0, k0; };
     auto locate = [&](int64_t u) {
         Unit x;
@@ -715,7 +717,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_con
                 for (int r = x.row0; r < x.row_end; r += BK, ++it) {
                     const int s = it % WG_NR;
                     mbar_wait(empty_bar(s), ((it / WG_NR) & 1u) ^ 1u);
-                    const uint32_t sa = smem_base + s * RAW_BYTES;
+                    const uint32_t sa = smem_base + s * SLOT;
                     mbar_expect_tx(full_bar(s), RAW_BYTES);
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
@@ -728,6 +730,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_con
     } else if (warp == 1) {
         if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc_tf32(BM, BN, 1, 1);
+            constexpr uint32_t idesc2 = umma_idesc_tf32(BM, 2 * BN, 1, 1);
             uint32_t it = 0, ti = 0;
             for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++ti) {
                 const Unit x = locate(u);
@@ -741,18 +744,27 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_con
                     mbar_wait(full_bar(s), (it / WG_NR) & 1u);
                     mbar_wait(lo_full(sl), (it / WG_NL) & 1u);
                     tc_fence_after();
-                    const uint32_t sa = smem_base + s * RAW_BYTES, sq = lo_base + sl * RAW_BYTES;
+                    const uint32_t sa = smem_base + s * SLOT, sq = lo_base + sl * A_BYTES;
 #pragma unroll
                     for (int k = 0; k < BK / 8; ++k) {
                         const uint64_t g_hi = umma_desc(sa + k * 1024, 4096, 512, 1);
                         const uint64_t g_lo = umma_desc(sq + k * 1024, 4096, 512, 1);
                         const uint64_t a_hi = umma_desc(sa + A_BYTES + k * 1024, 4096, 512, 1);
-                        const uint64_t a_lo = umma_desc(sq + A_BYTES + k * 1024, 4096, 512, 1);
-                        if (p.mode != 2) {
-                            umma_tf32_ss(d_tmem + BN, g_lo, a_hi, idesc, acc);
-                            umma_tf32_ss(d_tmem + BN, g_hi, a_lo, idesc, 1u);
+                        if (p.mode != 2 && p.n256) {
+                            // G_hi A_hi (main) and G_hi A_lo (correction) as ONE instruction of N = 256: A_lo lies right
+                            // behind the raw A tile (8 column groups 4096 B apart), the two accumulators are adjacent
+                            // in tensor memory.  G_hi crosses shared memory once instead of twice -- the kernel is
+                            // bound by shared-memory wavefronts (ncu: tensor-core reads 52 % + LSU 48 % of the pipe)
+                            umma_tf32_ss(d_tmem, g_hi, a_hi, idesc2, acc);              // [main | corr] (+)= G_hi^T [A_hi | A_lo]
+                            umma_tf32_ss(d_tmem + BN, g_lo, a_hi, idesc, 1u);           // corr += G_lo^T A_hi
+                        } else {
+                            if (p.mode != 2) {
+                                const uint64_t a_lo = umma_desc(sa + A_BYTES + B_BYTES + k * 1024, 4096, 512, 1);
+                                umma_tf32_ss(d_tmem + BN, g_lo, a_hi, idesc, acc);
+                                umma_tf32_ss(d_tmem + BN, g_hi, a_lo, idesc, 1u);
+                            }
+                            umma_tf32_ss(d_tmem, g_hi, a_hi, idesc, acc);
                         }
-                        umma_tf32_ss(d_tmem, g_hi, a_hi, idesc, acc);
                         acc = 1u;
                     }
                     tc_commit(empty_bar(s));
@@ -776,8 +788,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_con
                     // 32 rows, raw operand as hi (the tensor core ignores the low 13 mantissa bits), lo = x - trunc(x)
 #pragma unroll
                     for (int op = 0; op < 2; ++op) {
-                        const float4 *a = reinterpret_cast<const float4 *>(smem + s * RAW_BYTES + op * A_BYTES);
-                        float4 *alo = reinterpret_cast<float4 *>(smem + (lo_base - smem_base) + sl * RAW_BYTES + op * A_BYTES);
+                        const float4 *a = reinterpret_cast<const float4 *>(smem + s * SLOT + op * A_BYTES);
+                        float4 *alo = reinterpret_cast<float4 *>(op == 0 ? smem + (lo_base - smem_base) + sl * A_BYTES
+                                                                         : smem + s * SLOT + A_BYTES + B_BYTES);
                         float4 v[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) v[i] = a[i * 128 + ct];
@@ -789,8 +802,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_con
                 } else {
 #pragma unroll
                     for (int op = 0; op < 2; ++op) {
-                        float4 *a = reinterpret_cast<float4 *>(smem + s * RAW_BYTES + op * A_BYTES);
-                        float4 *alo = reinterpret_cast<float4 *>(smem + (lo_base - smem_base) + sl * RAW_BYTES + op * A_BYTES);
+                        float4 *a = reinterpret_cast<float4 *>(smem + s * SLOT + op * A_BYTES);
+                        float4 *alo = reinterpret_cast<float4 *>(op == 0 ? smem + (lo_base - smem_base) + sl * A_BYTES
+                                                                         : smem + s * SLOT + A_BYTES + B_BYTES);
                         float4 v[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -821,7 +835,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_con
         }
     } else {
         const int wq = warp & 3;
-        float *stg = reinterpret_cast<float *>(smem + (epi_base - smem_base) + (warp - 6) * 4096);
+        float *stg = nullptr;                    // store_chunk writes straight from registers
         uint32_t ti = 0;
         for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++ti) {
             const Unit x = locate(u);
@@ -1048,6 +1062,8 @@ extern "C" int mma_wgrad_tf32x3(const float *G0, int64_t ldg0, int N0, const flo
     p.tiles_k = (K + BN - 1) / BN;
     p.mode = mode;
     p.n_slabs = n_slabs; p.slab_tab = slab_tab; p.part = part;
+    static const bool wg_n256 = [] { const char *e = getenv("MMA_GEMM_WG_N256"); return !(e && e[0] == '0'); }();
+    p.n256 = wg_n256 ? 1 : 0;
     MMA_CUDA_CHECK(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES));
     int sms = 0, dev = 0;
     MMA_CUDA_CHECK(cudaGetDevice(&dev));
