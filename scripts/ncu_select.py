@@ -1,5 +1,6 @@
 """Selected columns of an `ncu --set full` report as a small CSV for profiles/ (the .ncu-rep files themselves are too
-large to commit):  python scripts/ncu_select.py gpurun_out/X.ncu-rep profiles/X_selected.csv"""
+large to commit):  python scripts/ncu_select.py gpurun_out/X.ncu-rep profiles/X_selected.csv
+(the first argument may also be the `--page raw --csv` export of a report, made on the GPU box)"""
 import csv
 import subprocess
 import sys
@@ -17,11 +18,17 @@ COLS = ["ID", "Kernel Name", "launch__grid_size", "launch__block_size", "launch_
         "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio"]
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        # shared-memory pipe and L2 -> SM traffic (what bounds the tcgen05 GEMMs)
+        "l1tex__data_pipe_tc_wavefronts_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum", "derived__lts__lts2xbar_bytes.sum.per_second"]
 
 
 def main(rep, out):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if rep.endswith(".csv"):
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr = rows[0]
     idx = [hdr.index(c) for c in COLS if c in hdr]
