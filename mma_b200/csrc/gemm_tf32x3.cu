@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_kernel(const __grid_con
                         // holds B_hi and B_lo back to back (128 rows of 128 B each, 8-row groups 1024 B apart), so a
                         // descriptor at B_hi with N = 256 runs straight on into B_lo, and the two accumulators are
                         // adjacent in tensor memory -- A_hi crosses shared memory once instead of twice (20 instead
-                        // of 24 KB of operand reads per K step; the kernel is shared-memory bound), 2 MMAs instead of 3.
+                        // of 24 KB of operand reads per K step), 2 MMAs instead of 3: measured 8 % on the long-K GEMMs.
                         if (p.mode != 2 && p.n256) {
                             umma_tf32_ss(d_tmem, a_hi, b_hi, idesc2, first);             // [main | corr] (+)= A_hi [B_hi ; B_lo]^T
                             umma_tf32_ss(d_tmem + BN, a_lo, b_hi, idesc, 1u);            // corr += A_lo B_hi^T
@@ -753,8 +753,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_con
                         if (p.mode != 2 && p.n256) {
                             // G_hi A_hi (main) and G_hi A_lo (correction) as ONE instruction of N = 256: A_lo lies right
                             // behind the raw A tile (8 column groups 4096 B apart), the two accumulators are adjacent
-                            // in tensor memory.  G_hi crosses shared memory once instead of twice -- the kernel is
-                            // bound by shared-memory wavefronts (ncu: tensor-core reads 52 % + LSU 48 % of the pipe)
+                            // in tensor memory.  G_hi crosses shared memory once instead of twice, 2 MMAs per K step
+                            // instead of 3: measured 5-10 % (profiles/r2M_wgrad_n256_ab.log)
                             umma_tf32_ss(d_tmem, g_hi, a_hi, idesc2, acc);              // [main | corr] (+)= G_hi^T [A_hi | A_lo]
                             umma_tf32_ss(d_tmem + BN, g_lo, a_hi, idesc, 1u);           // corr += G_lo^T A_hi
                         } else {

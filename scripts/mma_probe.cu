@@ -18,7 +18,7 @@
 using namespace mma::tc;
 
 constexpr int R = 1536;                 // instructions per measurement
-constexpr int SMEM_BYTES = 160 * 1024;  // A region [0, 32 KB), B region [32 KB, 160 KB)
+constexpr int SMEM_BYTES = 176 * 1024;  // A region [0, 32 KB), B region [32 KB, 128 KB), LSU traffic of the contention test [128 KB, 160 KB)
 
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -137,6 +137,90 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(long long *cycles, int n_
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// ---- the same chains while four other warps (128 threads, like the converter warpgroup of the GEMM kernels) keep the
+// shared-memory pipe busy with 128-bit loads (LOAD = 1) or loads + stores (LOAD = 2) on tiles of their own: how the
+// tensor core's operand reads and LSU traffic share shared-memory bandwidth.
+#define CONTENDED(X)                                                                                \
+    X(0, 128, 128, 128, 1, "tf32 SS  3 x 128         | 4 warps LDS.128")                            \
+    X(0, 128, 128, 128, 2, "tf32 SS  3 x 128         | 4 warps LDS.128 + STS.128")                  \
+    X(0, 256, 128, 0, 1, "tf32 SS  256 + 128       | 4 warps LDS.128")                              \
+    X(0, 256, 128, 0, 2, "tf32 SS  256 + 128       | 4 warps LDS.128 + STS.128")                    \
+    X(1, 128, 128, 128, 1, "tf32 TS  3 x 128         | 4 warps LDS.128")                            \
+    X(1, 128, 128, 128, 2, "tf32 TS  3 x 128         | 4 warps LDS.128 + STS.128")                  \
+    X(2, 128, 128, 128, 2, "tf32 SS MN-major 3 x 128 | 4 warps LDS.128 + STS.128")                  \
+    X(2, 256, 128, 0, 2, "tf32 SS MN-major 256+128 | 4 warps LDS.128 + STS.128")
+
+__global__ void __launch_bounds__(160, 1) contend_kernel(long long *cycles, long long *lsu_bytes, int n_variants) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    __shared__ uint64_t bar_mem;
+    __shared__ uint32_t tmem_slot;
+    __shared__ int done;
+    __shared__ unsigned long long moved;
+    __shared__ long long chain_cycles;
+    __shared__ int chain_n;
+    const uint32_t bar = smem_u32(&bar_mem);
+    const int warp = threadIdx.x >> 5;
+    for (uint32_t i = threadIdx.x; i < (SMEM_BYTES - 1024) / 16; i += blockDim.x)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(base + i * 16), "f"(0.0f) : "memory");
+    fence_proxy_async();
+    if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t pa = base, pb = base + 32 * 1024;
+    const uint32_t rd = base + 128 * 1024, wr = base + 144 * 1024;       // one 16 KB tile each
+    const int ct = threadIdx.x - 32;
+    uint32_t phase = 0;
+    int v = 0;
+    float sink = 0.f;
+#define X(KIND, N0, N1, N2, LOAD, NAME)                                                                     \
+    {                                                                                                        \
+        if (threadIdx.x == 0) { done = 0; moved = 0ull; }                                                    \
+        __syncthreads();                                                                                     \
+        if (warp == 0) {                                                                                     \
+            if (elect_one()) {                                                                               \
+                int n = 0;                                                                                   \
+                chain_cycles = run_chain<KIND, N0, N1, N2>(tmem, pa, pb, bar, phase, &n);                    \
+                chain_n = n;                                                                                 \
+                *(volatile int *)&done = 1;                                                                  \
+            }                                                                                                \
+        } else {                                                                                             \
+            unsigned long long it = 0;                                                                       \
+            while (*(volatile int *)&done == 0) {                                                            \
+                float4 x[8];                                                                                 \
+                _Pragma("unroll") for (int i = 0; i < 8; ++i)                                                \
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"                                  \
+                                 : "=f"(x[i].x), "=f"(x[i].y), "=f"(x[i].z), "=f"(x[i].w)                    \
+                                 : "r"(rd + (i * 128 + ct) * 16));                                           \
+                if (LOAD == 2) {                                                                             \
+                    _Pragma("unroll") for (int i = 0; i < 8; ++i)                                            \
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(wr + (i * 128 + ct) * 16), \
+                                     "f"(x[i].x), "f"(x[i].y), "f"(x[i].z), "f"(x[i].w) : "memory");         \
+                } else {                                                                                     \
+                    _Pragma("unroll") for (int i = 0; i < 8; ++i) sink += x[i].x;                            \
+                }                                                                                            \
+                ++it;                                                                                        \
+            }                                                                                                \
+            atomicAdd(&moved, it * (LOAD == 2 ? 256ull : 128ull));                                           \
+        }                                                                                                    \
+        __syncthreads();                                                                                     \
+        if (threadIdx.x == 0) {                                                                              \
+            cycles[(size_t)blockIdx.x * n_variants + v] = chain_cycles * 1000 / chain_n;                     \
+            lsu_bytes[(size_t)blockIdx.x * n_variants + v] = (long long)(moved * 1000ull / (unsigned long long)chain_cycles); \
+        }                                                                                                    \
+        phase ^= 1u; ++v;                                                                                    \
+    }
+    CONTENDED(X)
+#undef X
+    if (sink == 12345.678f) cycles[0] = 0;        // keeps the loads of LOAD = 1 alive
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 int main() {
     std::vector<const char *> names;
 #define X(KIND, N0, N1, N2, NAME) names.push_back(NAME);
@@ -166,6 +250,31 @@ int main() {
             sum += c; if (c < mn) mn = c; if (c > mx) mx = c;
         }
         printf("%-72s %10.1f %10.1f %10.1f\n", names[v], sum / sms / 1000.0, mn / 1000.0, mx / 1000.0);
+    }
+    // ---- under shared-memory contention
+    std::vector<const char *> cn;
+#define X(KIND, N0, N1, N2, LOAD, NAME) cn.push_back(NAME);
+    CONTENDED(X)
+#undef X
+    const int nc = (int)cn.size();
+    long long *dcc, *dlb;
+    cudaMalloc(&dcc, (size_t)sms * nc * sizeof(long long));
+    cudaMalloc(&dlb, (size_t)sms * nc * sizeof(long long));
+    cudaFuncSetAttribute(contend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    for (int rep = 0; rep < 2; ++rep) {
+        contend_kernel<<<sms, 160, SMEM_BYTES>>>(dcc, dlb, nc);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("CUDA error (contention test): %s\n", cudaGetErrorString(e)); return 1; }
+    }
+    std::vector<long long> hcc((size_t)sms * nc), hlb((size_t)sms * nc);
+    cudaMemcpy(hcc.data(), dcc, hcc.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaMemcpy(hlb.data(), dlb, hlb.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    printf("\nwith LSU traffic beside the chain (operand bytes per instruction: SS N=128 8 KB, SS N=256 12 KB, TS N=128 4 KB):\n");
+    printf("%-72s %10s %14s\n", "variant", "cyc/instr", "LSU B/cycle");
+    for (int v = 0; v < nc; ++v) {
+        double sc = 0, sb = 0;
+        for (int b = 0; b < sms; ++b) { sc += hcc[(size_t)b * nc + v]; sb += hlb[(size_t)b * nc + v]; }
+        printf("%-72s %10.1f %14.1f\n", cn[v], sc / sms / 1000.0, sb / sms / 1000.0);
     }
     return 0;
 }
