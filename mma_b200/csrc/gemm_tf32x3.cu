@@ -375,9 +375,9 @@ __global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_kernel(const __grid_con
 // Short-K variant (K <= 128, several 128-column tiles per row block): the activation tile stays RESIDENT IN
 // TENSOR MEMORY.
 //
-// The kernel above is bound by shared-memory bandwidth: per tcgen05.mma it moves ~16 KB through shared memory
-// (A and B operand reads of three MMAs, the converter's read + write, the TMA fills) = ~135 cycles per MMA where
-// the tensor core needs 64, and it repeats the conversion of A for every 128-column tile of the same rows.  For
+// The kernel above retires an MMA every ~105-135 cycles where the tensor core needs 64: per tcgen05.mma ~16 KB move
+// through shared memory (operand reads, the converter's read + write, the TMA fills -- a third of it weight tiles
+// re-streamed from L2), and it repeats the conversion of A for every 128-column tile of the same rows.  For
 // the two GEMMs with K = 128 and 384 / 640 output columns (mask projection, dgrad of the post transform) this
 // variant
 //   * converts a [128 x K] activation tile ONCE per row block: TMA -> shared memory -> registers (a thread owns
